@@ -1,0 +1,145 @@
+"""Flattened (SoA) view of one sparsification window.
+
+This is the host-side mirror of ``mss_window_view`` in ``include/mss.h``: the pointer graph the
+reference walks in ``MapSparsification::Sparsifying`` (/root/reference/src/MapSparsification.cc:58-151)
+-- ``KeyFrame::mvpMapPoints`` + ``KeyFrame::mGrid`` on the keyframe side, ``MapPoint::mObservations`` /
+``MapPoint::nObs`` on the map-point side -- snapshotted once into plain arrays.
+
+Conventions:
+  * KF table = K window keyframes followed by H "outside" keyframes (keyframes that are not in the window
+    but observe at least one window map point, MapSparsification.cc:125-151).
+  * ``feat_ptr[K+1]``  slot ranges of the window keyframes (a slot is one entry of mvpMapPoints).
+  * ``feat_mp[F]``     map-point table index held by the slot, -1 = empty or bad (MapSparsification.cc:70,90).
+  * ``feat_cell[F]``   image-grid cell ``col*48+row`` of the slot's keypoint (64x48 grid, include/Frame.h:44-45),
+                       0xFFFF = keypoint not in the grid (Frame::PosInGrid false, src/Frame.cc:657-668).
+  * ``mp_nobs[M]``     MapPoint::Observations() (stereo observation counts 2, src/MapPoint.cc:155-158).
+  * ``mp_obs_ptr[M+1]``/``mp_obs_kf[O]``  MapPoint::mObservations as KF-table indices (>= K means outside KF).
+  * ``okf_total[H]``   KeyFrame::GetNumberMPs() of each outside keyframe (src/KeyFrame.cc:286-297).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+GRID_COLS = 64          # include/Frame.h:44
+GRID_ROWS = 48          # include/Frame.h:45
+N_CELLS = GRID_COLS * GRID_ROWS
+CELL_NONE = 0xFFFF
+
+
+@dataclass
+class WindowView:
+    K: int
+    H: int
+    feat_ptr: np.ndarray      # int32 [K+1]
+    feat_mp: np.ndarray       # int32 [F]
+    feat_cell: np.ndarray     # uint16 [F]
+    mp_nobs: np.ndarray       # int32 [M]
+    mp_obs_ptr: np.ndarray    # int32 [M+1]
+    mp_obs_kf: np.ndarray     # int32 [O]
+    okf_total: np.ndarray     # int32 [H]
+    kf_gid: np.ndarray = None  # uint64 [K+H]
+    mp_gid: np.ndarray = None  # uint64 [M]
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        c = np.ascontiguousarray
+        self.feat_ptr = c(self.feat_ptr, dtype=np.int32)
+        self.feat_mp = c(self.feat_mp, dtype=np.int32)
+        self.feat_cell = c(self.feat_cell, dtype=np.uint16)
+        self.mp_nobs = c(self.mp_nobs, dtype=np.int32)
+        self.mp_obs_ptr = c(self.mp_obs_ptr, dtype=np.int32)
+        self.mp_obs_kf = c(self.mp_obs_kf, dtype=np.int32)
+        self.okf_total = c(self.okf_total, dtype=np.int32)
+        if self.kf_gid is None:
+            self.kf_gid = np.arange(self.K + self.H, dtype=np.uint64)
+        if self.mp_gid is None:
+            self.mp_gid = np.arange(self.M, dtype=np.uint64)
+        self.kf_gid = c(self.kf_gid, dtype=np.uint64)
+        self.mp_gid = c(self.mp_gid, dtype=np.uint64)
+
+    # sizes ---------------------------------------------------------------------------------------------
+    @property
+    def F(self) -> int:
+        return int(self.feat_mp.shape[0])
+
+    @property
+    def M(self) -> int:
+        return int(self.mp_nobs.shape[0])
+
+    @property
+    def O(self) -> int:
+        return int(self.mp_obs_kf.shape[0])
+
+    def input_bytes(self) -> int:
+        """Bytes the engine has to read from the view (the H2D payload when the view lives on the host)."""
+        return int(self.feat_ptr.nbytes + self.feat_mp.nbytes + self.feat_cell.nbytes + self.mp_nobs.nbytes
+                   + self.mp_obs_ptr.nbytes + self.mp_obs_kf.nbytes + self.okf_total.nbytes)
+
+    def validate(self) -> None:
+        K, H, F, M, O = self.K, self.H, self.F, self.M, self.O
+        if K < 0 or H < 0:
+            raise ValueError("negative K/H")
+        if self.feat_ptr.shape != (K + 1,) or self.feat_ptr[0] != 0 or int(self.feat_ptr[-1]) != F:
+            raise ValueError("feat_ptr must be [K+1], start at 0 and end at F")
+        if np.any(np.diff(self.feat_ptr) < 0):
+            raise ValueError("feat_ptr must be non-decreasing")
+        if self.feat_cell.shape != (F,):
+            raise ValueError("feat_cell/feat_mp length mismatch")
+        if F and (self.feat_mp.min() < -1 or self.feat_mp.max() >= M):
+            raise ValueError("feat_mp out of range")
+        ok = (self.feat_cell < N_CELLS) | (self.feat_cell == CELL_NONE)
+        if not bool(np.all(ok)):
+            raise ValueError("feat_cell must be < 3072 or 0xFFFF")
+        if self.mp_obs_ptr.shape != (M + 1,) or self.mp_obs_ptr[0] != 0 or int(self.mp_obs_ptr[-1]) != O:
+            raise ValueError("mp_obs_ptr must be [M+1], start at 0 and end at O")
+        if np.any(np.diff(self.mp_obs_ptr) < 0):
+            raise ValueError("mp_obs_ptr must be non-decreasing")
+        if O and (self.mp_obs_kf.min() < 0 or self.mp_obs_kf.max() >= K + H):
+            raise ValueError("mp_obs_kf out of range")
+        if self.okf_total.shape != (H,):
+            raise ValueError("okf_total must be [H]")
+
+    # io ------------------------------------------------------------------------------------------------
+    _ARRAYS = ("feat_ptr", "feat_mp", "feat_cell", "mp_nobs", "mp_obs_ptr", "mp_obs_kf", "okf_total",
+               "kf_gid", "mp_gid")
+
+    def save(self, path: str) -> None:
+        np.savez_compressed(path, K=self.K, H=self.H, **{n: getattr(self, n) for n in self._ARRAYS})
+
+    @classmethod
+    def load(cls, path: str) -> "WindowView":
+        z = np.load(path)
+        return cls(K=int(z["K"]), H=int(z["H"]), **{n: z[n] for n in cls._ARRAYS})
+
+
+def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:
+    """Small helper for hand-written windows (tests, fixtures).
+
+    kf_slots : list (len K) of lists of (mp_index or -1, cell or None) per slot.
+    outside  : list (len H) of lists of mp indices observed by each outside keyframe.
+    """
+    outside = outside or []
+    H = len(outside)
+    M = len(mp_nobs)
+    feat_ptr = [0]
+    feat_mp, feat_cell = [], []
+    obs = [[] for _ in range(M)]
+    for k, slots in enumerate(kf_slots):
+        for (p, cell) in slots:
+            feat_mp.append(-1 if p is None else p)
+            feat_cell.append(CELL_NONE if cell is None else cell)
+            if p is not None and p >= 0 and k not in obs[p]:
+                obs[p].append(k)
+        feat_ptr.append(len(feat_mp))
+    for j, plist in enumerate(outside):
+        for p in plist:
+            obs[p].append(K + j)
+    ptr = np.zeros(M + 1, np.int32)
+    ptr[1:] = np.cumsum([len(o) for o in obs])
+    flat = np.array([k for o in obs for k in o], np.int32)
+    if okf_total is None:
+        okf_total = [len(pl) for pl in outside]
+    return WindowView(K=K, H=H, feat_ptr=np.array(feat_ptr), feat_mp=np.array(feat_mp, np.int32),
+                      feat_cell=np.array(feat_cell, np.uint16), mp_nobs=np.array(mp_nobs, np.int32),
+                      mp_obs_ptr=ptr, mp_obs_kf=flat, okf_total=np.array(okf_total, np.int32))
