@@ -1,0 +1,156 @@
+/* mss.h -- C-ABI of the B200-native sliding-window map-sparsification engine (libmss.so).
+ *
+ * The reference (fishmarch/MS-SLAM @ e4730ec) has no plugin/FFI layer for this path: MapSparsification::Sparsifying
+ * (/root/reference/src/MapSparsification.cc:58-171) builds a GUROBI model object by object and calls
+ * GRBModel::optimize() (:157).  This header is the boundary that replaces those GUROBI calls: the C++ class
+ * ms_slam_b200/host/MapSparsification.{h,cc} keeps the reference's public surface
+ * (/root/reference/include/MapSparsification.h:26-70) and calls the entry points below instead of
+ *   GRBEnv / GRBEnv::start            (MapSparsification.cc:6,20)        -> mss_create
+ *   GRBModel, addVar, addConstr, ...  (MapSparsification.cc:61-153)     -> the mss_window_view snapshot
+ *   GRBModel::optimize                (MapSparsification.cc:154-157)    -> mss_solve / mss_solve_batch
+ *   GRBVar::get(GRB_DoubleAttr_X)     (MapSparsification.cc:159-166)    -> mss_result.keep_bits
+ *   ~GRBEnv                                                             -> mss_destroy
+ *
+ * Plain C, plain pointers and sizes; no C++/torch types cross this boundary.  All functions return 0 (MSS_OK) or a
+ * negative mss_status and never throw.  A handle is single-threaded (one per sparsifier thread, like GRBEnv) and owns
+ * one CUDA stream and all device scratch (grown on demand, never shrunk, no allocation on the hot call after warm-up).
+ * There is no CPU fallback: without a usable CUDA device mss_create fails with MSS_E_CUDA.
+ */
+#ifndef MSS_H_
+#define MSS_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSS_VERSION 100            /* 0.1.0 */
+
+#define MSS_GRID_COLS 64           /* FRAME_GRID_COLS, /root/reference/include/Frame.h:45 */
+#define MSS_GRID_ROWS 48           /* FRAME_GRID_ROWS, /root/reference/include/Frame.h:44 */
+#define MSS_CELL_NONE 0xFFFFu      /* keypoint outside the grid (Frame::PosInGrid false, src/Frame.cc:657-668) */
+
+typedef enum mss_status {
+    MSS_OK = 0,
+    MSS_E_BADARG = -1,       /* NULL / inconsistent sizes / out-of-range index found in a view */
+    MSS_E_CUDA = -2,         /* CUDA runtime error (message in mss_last_error) */
+    MSS_E_NCCL = -3,         /* NCCL error or NCCL library not loadable */
+    MSS_E_NOMEM = -4,
+    MSS_E_NOCONVERGE = -5,   /* round cap hit; the returned selection is still feasible (every row at its best level) */
+    MSS_E_INTERNAL = -6
+} mss_status;
+
+typedef enum mss_memory {
+    MSS_MEM_HOST = 0,        /* pointers are host memory (pageable or pinned); the engine stages them itself */
+    MSS_MEM_DEVICE = 1       /* pointers are device memory on the engine's device; consumed in place */
+} mss_memory;
+
+typedef struct mss_handle mss_handle;
+
+/* Solver parameters = the reference's yaml keys (MapSparsification.cc:9-12) + the device algorithm's caps. */
+typedef struct mss_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t min_points;        /* Sparsification.N           (mnMinNum) */
+    float   lambda;            /* Sparsification.Lambda      (mfLambda: cost of one missing point in a keyframe row) */
+    float   grid_lambda;       /* Sparsification.GridLambda  (mfGridLambda: cost of one uncovered occupied cell) */
+    int32_t max_rounds;        /* cap on propagation+greedy rounds per window (0 -> 256) */
+    int32_t all_rule_steps;    /* greedy steps that use the strict conflict-free rule before falling back (0 -> 64) */
+    int32_t max_drop_rounds;   /* cap on reverse-delete rounds (0 -> 16) */
+    int32_t flags;             /* reserved, 0 */
+} mss_config;
+
+/* One window, flattened (SoA).  Snapshot of the pointer graph Sparsifying() walks:
+ *   KeyFrame::mvpMapPoints (include/KeyFrame.h:298) + KeyFrame::mGrid (:307)   -> feat_ptr / feat_mp / feat_cell
+ *   MapPoint::nObs (include/MapPoint.h:101), MapPoint::mObservations (:150)    -> mp_nobs / mp_obs_ptr / mp_obs_kf
+ *   KeyFrame::GetNumberMPs() of keyframes outside the window (KeyFrame.cc:286) -> okf_total
+ * KF table = K window keyframes then H outside keyframes.  Caller-owned, read-only, not retained past the call. */
+typedef struct mss_window_view {
+    int32_t K;                 /* window keyframes (vpKFs.size()) */
+    int32_t H;                 /* outside keyframes observing at least one window map point */
+    int32_t M;                 /* map-point table size */
+    int32_t F;                 /* feature slots = feat_ptr[K] */
+    int32_t O;                 /* observations  = mp_obs_ptr[M] */
+    int32_t memory;            /* mss_memory of every pointer below */
+    const int32_t*  feat_ptr;  /* [K+1] slot range of each window keyframe */
+    const int32_t*  feat_mp;   /* [F]   map-point table index, -1 = empty slot or bad map point (MapSparsification.cc:70,90) */
+    const uint16_t* feat_cell; /* [F]   col*48+row in the 64x48 grid, MSS_CELL_NONE = not in mGrid */
+    const int32_t*  mp_nobs;   /* [M]   MapPoint::Observations() */
+    const int32_t*  mp_obs_ptr;/* [M+1] */
+    const int32_t*  mp_obs_kf; /* [O]   KF-table index of each observation; >= K means outside keyframe (value - K) */
+    const int32_t*  okf_total; /* [H]   GetNumberMPs() of each outside keyframe */
+} mss_window_view;
+
+/* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view) or NULL. */
+typedef struct mss_result {
+    uint32_t* keep_bits;       /* [(M+31)/32] bit p = 1 keep map point p, 0 = SetBadFlag() it (MapSparsification.cc:162-165);
+                                  map points that are not variables of the window are always 1 */
+    int32_t*  kf_cov;          /* [K+H] points kept in each keyframe row (with multiplicity), may be NULL */
+    int32_t*  kf_slack;        /* [K+H] max(0, need - cov): the ILP's t_k / u_j at their optimum, may be NULL */
+    double    objective;       /* F(x) of SURVEY Appendix A.3 = sum c_p x_p + GridLambda*uncovered + Lambda*slack */
+    double    dual_bound;      /* lower bound on the ILP optimum proven on device (NaN when not computed) */
+    int64_t   sum_cost;        /* sum c_p over kept variables (costs are integers: nMax - nObs_p) */
+    int32_t   uncovered_cells; /* occupied cells left without a kept point */
+    int32_t   total_slack;     /* sum of kf_slack */
+    int32_t   n_max;           /* nMaxObservation (MapSparsification.cc:66-76) */
+    int32_t   n_vars;          /* distinct map points that are ILP variables */
+    int32_t   n_cells;         /* occupied-valid (keyframe, cell) rows */
+    int32_t   nnz;             /* valid grid-listed slots (incidences of the keyframe rows) */
+    int32_t   n_kept;          /* variables kept */
+    int32_t   rounds;          /* propagation + greedy + drop rounds executed */
+    int32_t   status;          /* MSS_OK or MSS_E_NOCONVERGE / MSS_E_BADARG for this window */
+    float     time_build_us;   /* device time: snapshot scan + outside-row assembly */
+    float     time_solve_us;   /* device time: selection + evaluation + bit packing */
+} mss_result;
+
+typedef struct mss_stats {
+    int64_t kernel_launches;   /* kernels of this library launched since mss_create */
+    int64_t solves;            /* windows solved on this rank since mss_create */
+    double  last_device_ms;    /* device time of the last mss_solve[_batch] kernel (CUDA events) */
+    double  last_total_ms;     /* host wall time of the last call */
+    int64_t last_h2d_bytes;    /* bytes staged host->device by the last call */
+    int64_t last_d2h_bytes;
+    int64_t device_bytes;      /* device scratch currently owned */
+    int32_t grid_ctas;         /* CTAs of the persistent kernel in the last call */
+    int32_t sm_count;
+} mss_stats;
+
+int         mss_version(void);
+int         mss_create(const mss_config* cfg, mss_handle** out);
+void        mss_destroy(mss_handle* h);
+const char* mss_last_error(const mss_handle* h);            /* never NULL; "" when no error */
+int         mss_set_params(mss_handle* h, int32_t min_points, float lambda, float grid_lambda);
+
+/* Solve one window (synchronous: returns after the result is in the caller's buffers). */
+int mss_solve(mss_handle* h, const mss_window_view* view, mss_result* result);
+
+/* Solve nwin independent windows in one launch.  With a communicator attached (mss_comm_init) window w is solved by
+ * rank w % nranks and the results of all windows are all-gathered (keep bits + per-row coverage only), so every rank
+ * returns all nwin results; views of windows owned by other ranks need only K, H, M filled in. */
+int mss_solve_batch(mss_handle* h, int32_t nwin, const mss_window_view* views, mss_result* results);
+
+/* Multi-GPU: one process per GPU.  Rank 0 calls mss_comm_unique_id, ships the 128 bytes to the other ranks by any
+ * means (torch.distributed broadcast, MPI, a file), then every rank calls mss_comm_init. */
+#define MSS_UNIQUE_ID_BYTES 128
+int mss_comm_unique_id(void* out_id128);
+int mss_comm_init(mss_handle* h, const void* id128, int32_t rank, int32_t nranks);
+int mss_comm_destroy(mss_handle* h);
+
+/* Pinned host memory for views/results that travel every call (optional; any host memory works). */
+void* mss_host_alloc(size_t bytes);
+void  mss_host_free(void* p);
+/* Device memory on the engine's device for callers that keep views resident (MSS_MEM_DEVICE). */
+void* mss_device_alloc(mss_handle* h, size_t bytes);
+void  mss_device_free(mss_handle* h, void* p);
+int   mss_memcpy_h2d(mss_handle* h, void* dst_device, const void* src_host, size_t bytes);
+int   mss_memcpy_d2h(mss_handle* h, void* dst_host, const void* src_device, size_t bytes);
+
+int   mss_get_stats(const mss_handle* h, mss_stats* out);
+/* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
+void* mss_stream(mss_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSS_H_ */

@@ -1,0 +1,546 @@
+// mss_engine.cu -- host side of libmss.so: device arena, batch layout, cooperative launch, result hand-back, NCCL
+// all-gather of the result slots, and the extern "C" entry points declared in include/mss.h.
+//
+// Replaces the GUROBI environment/model objects of the reference (GRBEnv mGRBEnv, GRBModel model:
+// /root/reference/include/MapSparsification.h:59, /root/reference/src/MapSparsification.cc:6,20,61,153-157).
+#include "../../include/mss.h"
+#include "mss_kernels.cuh"
+
+#include <dlfcn.h>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+using mss::Ctrl;
+using mss::Params;
+using mss::WinDesc;
+using mss::WinState;
+
+// ---- NCCL through dlopen: no link-time dependency, single-GPU users never touch it ------------------------------------
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+const int kNcclUint32 = 3;   // ncclUint32 (nccl.h ncclDataType_t)
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.ok) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(NcclComm))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy && g_nccl.GetErrorString;
+    if (!g_nccl.ok) err = "libnccl is missing required symbols";
+    return g_nccl.ok;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;     // elements
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct mss_handle {
+    mss_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    int max_ctas_per_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    // device arena
+    DevBuf<uint8_t> meta;            // WinDesc[] | row_win[] | tile_win[]
+    DevBuf<WinState> ws;
+    DevBuf<uint8_t> st;
+    DevBuf<unsigned long long> acc;
+    DevBuf<float> gain;
+    DevBuf<int> row_need;
+    DevBuf<int> ocnt, orow_ptr, ocursor, orow_var;
+    DevBuf<uint32_t> out;
+    DevBuf<uint8_t> stage;           // host views staged here
+    Ctrl* ctrl = nullptr;
+    // pinned host mirrors
+    uint8_t* h_meta = nullptr; size_t h_meta_cap = 0;
+    uint32_t* h_out = nullptr; size_t h_out_cap = 0;
+    Ctrl* h_ctrl = nullptr;
+    // comm
+    NcclComm comm = nullptr;
+    int rank = 0, nranks = 1;
+    // stats
+    mss_stats stats{};
+    int64_t device_bytes = 0;
+};
+
+namespace {
+
+#define MSS_CUDA(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                         \
+            return MSS_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+int ensure(mss_handle* h, DevBuf<T>& b, size_t n) {
+    if (n <= b.cap && b.p) return MSS_OK;
+    size_t ncap = b.cap ? b.cap : 1024;
+    while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+    if (b.p) { MSS_CUDA(h, cudaFree(b.p)); h->device_bytes -= (int64_t)(b.cap * sizeof(T)); b.p = nullptr; b.cap = 0; }
+    MSS_CUDA(h, cudaMalloc((void**)&b.p, ncap * sizeof(T)));
+    b.cap = ncap;
+    h->device_bytes += (int64_t)(ncap * sizeof(T));
+    return MSS_OK;
+}
+
+int ensure_pinned(mss_handle* h, void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap && *p) return MSS_OK;
+    size_t ncap = *cap ? *cap : 4096;
+    while (ncap < bytes) ncap = ncap + ncap / 2 + 4096;
+    if (*p) { MSS_CUDA(h, cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
+    MSS_CUDA(h, cudaHostAlloc(p, ncap, cudaHostAllocDefault));
+    *cap = ncap;
+    return MSS_OK;
+}
+
+template <class T>
+void release(DevBuf<T>& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+struct SlotLayout { int words_keep, rows, total; };
+inline SlotLayout slot_of(const mss_window_view& v) {
+    SlotLayout s;
+    s.words_keep = (v.M + 31) / 32;
+    s.rows = v.K + v.H;
+    s.total = mss::kHdrWords + s.words_keep + 2 * s.rows;
+    return s;
+}
+
+void fill_failsafe(const mss_window_view& v, mss_result& r, int status, bool host_mem, mss_handle* h) {
+    // deleting map points is irreversible: on any error keep everything (bitmask all ones)
+    const size_t words = (size_t)(v.M + 31) / 32;
+    if (r.keep_bits) {
+        if (host_mem) memset(r.keep_bits, 0xFF, words * 4);
+        else cudaMemsetAsync(r.keep_bits, 0xFF, words * 4, h->stream);
+    }
+    const size_t rows = (size_t)v.K + v.H;
+    if (host_mem) {
+        if (r.kf_cov) memset(r.kf_cov, 0, rows * 4);
+        if (r.kf_slack) memset(r.kf_slack, 0, rows * 4);
+    } else {
+        if (r.kf_cov) cudaMemsetAsync(r.kf_cov, 0, rows * 4, h->stream);
+        if (r.kf_slack) cudaMemsetAsync(r.kf_slack, 0, rows * 4, h->stream);
+    }
+    r.objective = NAN; r.dual_bound = NAN; r.sum_cost = 0; r.uncovered_cells = 0; r.total_slack = 0;
+    r.n_max = 0; r.n_vars = 0; r.n_cells = 0; r.nnz = 0; r.n_kept = 0; r.rounds = 0;
+    r.status = status; r.time_build_us = 0; r.time_solve_us = 0;
+}
+
+int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
+    if (v.K < 0 || v.H < 0 || v.M < 0) { h->err = "view: negative K/H/M"; return MSS_E_BADARG; }
+    if (!owned) return MSS_OK;
+    if (v.F < 0 || v.O < 0) { h->err = "view: negative F/O"; return MSS_E_BADARG; }
+    if (v.memory != MSS_MEM_HOST && v.memory != MSS_MEM_DEVICE) { h->err = "view: bad memory kind"; return MSS_E_BADARG; }
+    if (!v.feat_ptr || !v.mp_obs_ptr) { h->err = "view: feat_ptr / mp_obs_ptr is NULL"; return MSS_E_BADARG; }
+    if ((v.F > 0 && (!v.feat_mp || !v.feat_cell)) || (v.M > 0 && !v.mp_nobs) || (v.O > 0 && !v.mp_obs_kf) ||
+        (v.H > 0 && !v.okf_total)) { h->err = "view: NULL array with non-zero size"; return MSS_E_BADARG; }
+    if (v.memory == MSS_MEM_HOST) {
+        if (v.feat_ptr[0] != 0 || v.feat_ptr[v.K] != v.F) { h->err = "view: feat_ptr must start at 0 and end at F"; return MSS_E_BADARG; }
+        if (v.mp_obs_ptr[0] != 0 || v.mp_obs_ptr[v.M] != v.O) { h->err = "view: mp_obs_ptr must start at 0 and end at O"; return MSS_E_BADARG; }
+    }
+    return MSS_OK;
+}
+
+int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_result* results) {
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    h->err.clear();
+    if (!views || !results || nwin < 0) { h->err = "NULL views/results or negative nwin"; return MSS_E_BADARG; }
+    if (nwin == 0) return MSS_OK;
+    MSS_CUDA(h, cudaSetDevice(h->device));
+    const int nranks = h->nranks, rank = h->rank;
+
+    // ---- layout ---------------------------------------------------------------------------------------------------
+    std::vector<int> local;                 // windows solved on this rank
+    std::vector<int> out_off(nwin, 0);
+    int slot_stride = 0;
+    for (int w = 0; w < nwin; ++w) {
+        const bool owned = (w % nranks) == rank;
+        const int rc = validate_view(h, views[w], owned);
+        if (rc != MSS_OK) return rc;
+        if (owned) local.push_back(w);
+        slot_stride = std::max(slot_stride, slot_of(views[w]).total);
+    }
+    const int spr = (nwin + nranks - 1) / nranks;          // slots per rank
+    size_t out_words = 0;
+    if (nranks == 1) {
+        for (int w = 0; w < nwin; ++w) { out_off[w] = (int)out_words; out_words += (size_t)slot_of(views[w]).total; }
+    } else {
+        for (int w = 0; w < nwin; ++w) out_off[w] = ((w % nranks) * spr + w / nranks) * slot_stride;
+        out_words = (size_t)nranks * spr * slot_stride;
+    }
+    const int nl = (int)local.size();
+    long long Ktot = 0, Htot = 0, Mpad = 0, Ocap = 0;
+    size_t stage_bytes = 0;
+    for (int w : local) {
+        const mss_window_view& v = views[w];
+        Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ocap += v.O;
+        if (v.memory == MSS_MEM_HOST) {
+            stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + align_up((size_t)v.F * 2, 16) +
+                           align_up((size_t)v.M * 4, 16) + align_up((size_t)(v.M + 1) * 4, 16) + align_up((size_t)v.O * 4, 16) +
+                           align_up((size_t)v.H * 4, 16);
+        }
+    }
+    if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ocap > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
+    const int Rtot = (int)(Ktot + Htot);
+    const int ntiles = (int)(Mpad / mss::kVarTile);
+
+    int rc;
+    const size_t meta_bytes = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16) + align_up((size_t)std::max(Rtot, 1) * 4, 16) +
+                              align_up((size_t)std::max(ntiles, 1) * 4, 16);
+    if ((rc = ensure(h, h->meta, meta_bytes))) return rc;
+    if ((rc = ensure(h, h->ws, (size_t)std::max(nl, 1)))) return rc;
+    if ((rc = ensure(h, h->st, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->acc, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->gain, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->row_need, (size_t)Rtot + 16))) return rc;
+    if ((rc = ensure(h, h->ocnt, (size_t)Htot + 16))) return rc;
+    if ((rc = ensure(h, h->orow_ptr, (size_t)Htot + 16))) return rc;
+    if ((rc = ensure(h, h->ocursor, (size_t)Htot + 16))) return rc;
+    if ((rc = ensure(h, h->orow_var, (size_t)Ocap + 16))) return rc;
+    if ((rc = ensure(h, h->out, out_words + 16))) return rc;
+    if ((rc = ensure(h, h->stage, stage_bytes + 16))) return rc;
+    if ((rc = ensure_pinned(h, (void**)&h->h_meta, &h->h_meta_cap, meta_bytes))) return rc;
+    if ((rc = ensure_pinned(h, (void**)&h->h_out, &h->h_out_cap, (out_words + 16) * 4))) return rc;
+
+    // ---- stage host views, build descriptors ------------------------------------------------------------------------
+    WinDesc* hd = reinterpret_cast<WinDesc*>(h->h_meta);
+    int* h_row_win = reinterpret_cast<int*>(h->h_meta + align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16));
+    int* h_tile_win = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(h_row_win) + align_up((size_t)std::max(Rtot, 1) * 4, 16));
+    int64_t h2d = 0;
+    size_t soff = 0;
+    auto stage = [&](const void* src, size_t bytes) -> const void* {
+        uint8_t* dst = h->stage.p + soff;
+        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+        soff += align_up(bytes, 16);
+        h2d += (int64_t)bytes;
+        return dst;
+    };
+    int row_base = 0, orow_base = 0, var_base = 0;
+    for (int i = 0; i < nl; ++i) {
+        const mss_window_view& v = views[local[i]];
+        WinDesc d;
+        memset(&d, 0, sizeof(d));
+        if (v.memory == MSS_MEM_HOST) {
+            d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
+            d.feat_mp = (const int*)stage(v.feat_mp, (size_t)v.F * 4);
+            d.feat_cell = (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
+            d.mp_nobs = (const int*)stage(v.mp_nobs, (size_t)v.M * 4);
+            d.mp_obs_ptr = (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
+            d.mp_obs_kf = (const int*)stage(v.mp_obs_kf, (size_t)v.O * 4);
+            d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
+        } else {
+            d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
+            d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
+        }
+        d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O;
+        d.row_base = row_base; d.orow_base = orow_base; d.var_base = var_base;
+        d.out_off = out_off[local[i]];
+        d.owned = 1;
+        hd[i] = d;
+        for (int k = 0; k < v.K; ++k) h_row_win[row_base + k] = i;
+        const int tiles = (int)(align_up((size_t)std::max(v.M, 1), mss::kVarTile) / mss::kVarTile);
+        for (int t = 0; t < tiles; ++t) h_tile_win[var_base / mss::kVarTile + t] = i;
+        row_base += v.K; orow_base += v.H; var_base += tiles * mss::kVarTile;
+    }
+    {   // outside rows come after all keyframe rows
+        int jj = 0;
+        for (int i = 0; i < nl; ++i) {
+            const mss_window_view& v = views[local[i]];
+            for (int j = 0; j < v.H; ++j) h_row_win[Ktot + jj++] = i;
+        }
+    }
+    MSS_CUDA(h, cudaGetLastError());
+    MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
+    h2d += (int64_t)meta_bytes;
+
+    // ---- launch -------------------------------------------------------------------------------------------------------
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.win = reinterpret_cast<const WinDesc*>(h->meta.p);
+    P.ws = h->ws.p;
+    P.row_win = reinterpret_cast<const int*>(h->meta.p + ((uint8_t*)h_row_win - h->h_meta));
+    P.tile_win = reinterpret_cast<const int*>(h->meta.p + ((uint8_t*)h_tile_win - h->h_meta));
+    P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.row_need = h->row_need.p;
+    P.ocnt = h->ocnt.p; P.orow_ptr = h->orow_ptr.p; P.ocursor = h->ocursor.p; P.orow_var = h->orow_var.p;
+    P.out = h->out.p; P.ctrl = h->ctrl;
+    P.nwin = nl; P.Ktot = (int)Ktot; P.Htot = (int)Htot; P.Rtot = Rtot; P.Mpad = (int)Mpad; P.ntiles = ntiles;
+    P.N = h->cfg.min_points;
+    P.max_rounds = h->cfg.max_rounds; P.all_rule_steps = h->cfg.all_rule_steps; P.max_drop_rounds = h->cfg.max_drop_rounds;
+    P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
+
+    float dev_ms = 0.f;
+    int grid = 0;
+    if (nl > 0) {
+        const int max_grid = h->max_ctas_per_sm * h->sm_count;
+        grid = std::max(1, std::min(max_grid, std::max(Rtot, ntiles)));
+        void* args[] = {(void*)&P};
+        MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(grid), dim3(mss::kThreads), args, 0, h->stream));
+        MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        h->stats.kernel_launches += 1;
+    }
+    // ---- all-gather of the result slots (keep bits + row coverage only) ---------------------------------------------------
+    if (nranks > 1) {
+        const size_t count = (size_t)spr * slot_stride;
+        const int nrc = g_nccl.AllGather(h->out.p + (size_t)rank * count, h->out.p, count, kNcclUint32, h->comm, h->stream);
+        if (nrc != 0) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(nrc); return MSS_E_NCCL; }
+    }
+    // ---- hand-back ------------------------------------------------------------------------------------------------------
+    MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
+    MSS_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    int64_t d2h = (int64_t)(out_words * 4 + sizeof(Ctrl));
+    for (int w = 0; w < nwin; ++w) {       // device-resident result buffers are filled device-to-device
+        const mss_window_view& v = views[w];
+        mss_result& r = results[w];
+        if (v.memory != MSS_MEM_DEVICE) continue;
+        const SlotLayout s = slot_of(v);
+        const uint32_t* slot = h->out.p + out_off[w];
+        if (r.keep_bits && s.words_keep) MSS_CUDA(h, cudaMemcpyAsync(r.keep_bits, slot + mss::kHdrWords, (size_t)s.words_keep * 4, cudaMemcpyDeviceToDevice, h->stream));
+        if (r.kf_cov && s.rows) MSS_CUDA(h, cudaMemcpyAsync(r.kf_cov, slot + mss::kHdrWords + s.words_keep, (size_t)s.rows * 4, cudaMemcpyDeviceToDevice, h->stream));
+        if (r.kf_slack && s.rows) MSS_CUDA(h, cudaMemcpyAsync(r.kf_slack, slot + mss::kHdrWords + s.words_keep + s.rows, (size_t)s.rows * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
+
+    int ret = MSS_OK;
+    const double t_build_us = nl > 0 ? (double)(h->h_ctrl->t_build - h->h_ctrl->t_start) * 1e-3 : 0.0;
+    const double t_solve_us = nl > 0 ? (double)(h->h_ctrl->t_end - h->h_ctrl->t_build) * 1e-3 : 0.0;
+    for (int w = 0; w < nwin; ++w) {
+        const mss_window_view& v = views[w];
+        mss_result& r = results[w];
+        const SlotLayout s = slot_of(v);
+        const uint32_t* slot = h->h_out + out_off[w];
+        const bool host_mem = v.memory != MSS_MEM_DEVICE;
+        if (slot[14] != 0x4D535331u) {
+            fill_failsafe(v, r, MSS_E_BADARG, host_mem, h);
+            if (ret == MSS_OK) { ret = MSS_E_BADARG; h->err = "window " + std::to_string(w) + ": view failed device-side validation (index out of range, bad pointer table or > 1023 points in one grid cell); all map points kept"; }
+            continue;
+        }
+        if (host_mem) {
+            if (r.keep_bits) memcpy(r.keep_bits, slot + mss::kHdrWords, (size_t)s.words_keep * 4);
+            if (r.kf_cov) memcpy(r.kf_cov, slot + mss::kHdrWords + s.words_keep, (size_t)s.rows * 4);
+            if (r.kf_slack) memcpy(r.kf_slack, slot + mss::kHdrWords + s.words_keep + s.rows, (size_t)s.rows * 4);
+        }
+        r.status = (int32_t)slot[0];
+        r.rounds = (int32_t)slot[1];
+        r.n_max = (int32_t)slot[2];
+        r.n_vars = (int32_t)slot[3];
+        r.n_cells = (int32_t)slot[4];
+        r.nnz = (int32_t)slot[5];
+        r.n_kept = (int32_t)slot[6];
+        r.uncovered_cells = (int32_t)slot[7];
+        r.total_slack = (int32_t)slot[8];
+        r.sum_cost = (int64_t)(((uint64_t)slot[10] << 32) | slot[9]);
+        r.objective = (double)r.sum_cost + (double)h->cfg.grid_lambda * (double)r.uncovered_cells +
+                      (double)h->cfg.lambda * (double)r.total_slack;
+        r.dual_bound = NAN;
+        r.time_build_us = (float)t_build_us;
+        r.time_solve_us = (float)t_solve_us;
+        if (r.status != MSS_OK && ret == MSS_OK) { ret = r.status; h->err = "window " + std::to_string(w) + ": round cap reached (selection is feasible but may be loose)"; }
+    }
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));    // fail-safe memsets on device results
+    h->stats.solves += nl;
+    h->stats.last_device_ms = dev_ms;
+    h->stats.last_h2d_bytes = h2d;
+    h->stats.last_d2h_bytes = d2h;
+    h->stats.device_bytes = h->device_bytes;
+    h->stats.grid_ctas = grid;
+    h->stats.last_total_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
+    return ret;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+extern "C" {
+
+int mss_version(void) { return MSS_VERSION; }
+
+int mss_create(const mss_config* cfg, mss_handle** out) {
+    if (!cfg || !out) return MSS_E_BADARG;
+    *out = nullptr;
+    if (cfg->min_points < 0 || !(cfg->lambda >= 0.f) || !(cfg->grid_lambda >= 0.f)) return MSS_E_BADARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        fprintf(stderr, "libmss: no usable CUDA device (requested %d of %d); there is no CPU fallback\n", cfg->device, ndev);
+        return MSS_E_CUDA;
+    }
+    mss_handle* h = new (std::nothrow) mss_handle();
+    if (!h) return MSS_E_NOMEM;
+    h->cfg = *cfg;
+    if (h->cfg.max_rounds <= 0) h->cfg.max_rounds = 256;
+    if (h->cfg.all_rule_steps <= 0) h->cfg.all_rule_steps = 64;
+    if (h->cfg.max_drop_rounds < 0) h->cfg.max_drop_rounds = 0;
+    else if (h->cfg.max_drop_rounds == 0) h->cfg.max_drop_rounds = 16;
+    h->device = cfg->device;
+    auto fail = [&](const char* what, cudaError_t e) {
+        fprintf(stderr, "libmss: %s: %s\n", what, cudaGetErrorString(e));
+        mss_destroy(h);
+        return MSS_E_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    h->sm_count = prop.multiProcessorCount;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (!coop) { fprintf(stderr, "libmss: device does not support cooperative launch\n"); mss_destroy(h); return MSS_E_CUDA; }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->max_ctas_per_sm, mss::mss_persistent_kernel, mss::kThreads, 0)) != cudaSuccess)
+        return fail("occupancy query (was libmss built for this GPU? it ships sm_100a code only)", e);
+    if (h->max_ctas_per_sm <= 0) { fprintf(stderr, "libmss: kernel does not fit on an SM\n"); mss_destroy(h); return MSS_E_CUDA; }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaMalloc((void**)&h->ctrl, sizeof(Ctrl))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMemset(h->ctrl, 0, sizeof(Ctrl))) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    h->stats.sm_count = h->sm_count;
+    *out = h;
+    return MSS_OK;
+}
+
+void mss_destroy(mss_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->row_need);
+    release(h->ocnt); release(h->orow_ptr); release(h->ocursor); release(h->orow_var); release(h->out); release(h->stage);
+    if (h->ctrl) cudaFree(h->ctrl);
+    if (h->h_meta) cudaFreeHost(h->h_meta);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* mss_last_error(const mss_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int mss_set_params(mss_handle* h, int32_t min_points, float lambda, float grid_lambda) {
+    if (!h) return MSS_E_BADARG;
+    if (min_points < 0 || !(lambda >= 0.f) || !(grid_lambda >= 0.f)) { h->err = "bad parameters"; return MSS_E_BADARG; }
+    h->cfg.min_points = min_points; h->cfg.lambda = lambda; h->cfg.grid_lambda = grid_lambda;
+    return MSS_OK;
+}
+
+int mss_solve(mss_handle* h, const mss_window_view* view, mss_result* result) {
+    if (!h) return MSS_E_BADARG;
+    if (h->nranks > 1) { h->err = "mss_solve on a handle with a communicator: use mss_solve_batch"; return MSS_E_BADARG; }
+    return solve_batch_impl(h, 1, view, result);
+}
+
+int mss_solve_batch(mss_handle* h, int32_t nwin, const mss_window_view* views, mss_result* results) {
+    if (!h) return MSS_E_BADARG;
+    return solve_batch_impl(h, nwin, views, results);
+}
+
+int mss_comm_unique_id(void* out_id128) {
+    if (!out_id128) return MSS_E_BADARG;
+    std::string err;
+    if (!load_nccl(err)) { fprintf(stderr, "libmss: %s\n", err.c_str()); return MSS_E_NCCL; }
+    NcclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return MSS_E_NCCL;
+    memcpy(out_id128, &id, sizeof(id));
+    return MSS_OK;
+}
+
+int mss_comm_init(mss_handle* h, const void* id128, int32_t rank, int32_t nranks) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return MSS_E_BADARG;
+    if (!load_nccl(h->err)) return MSS_E_NCCL;
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    MSS_CUDA(h, cudaSetDevice(h->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc); h->comm = nullptr; return MSS_E_NCCL; }
+    h->rank = rank; h->nranks = nranks;
+    return MSS_OK;
+}
+
+int mss_comm_destroy(mss_handle* h) {
+    if (!h) return MSS_E_BADARG;
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr; h->rank = 0; h->nranks = 1;
+    return MSS_OK;
+}
+
+void* mss_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void mss_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* mss_device_alloc(mss_handle* h, size_t bytes) {
+    if (!h) return nullptr;
+    void* p = nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { h->err = "cudaMalloc failed"; return nullptr; }
+    return p;
+}
+void mss_device_free(mss_handle* h, void* p) { if (h && p) { cudaSetDevice(h->device); cudaFree(p); } }
+
+int mss_memcpy_h2d(mss_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h) return MSS_E_BADARG;
+    MSS_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSS_OK;
+}
+int mss_memcpy_d2h(mss_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h) return MSS_E_BADARG;
+    MSS_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSS_OK;
+}
+
+int mss_get_stats(const mss_handle* h, mss_stats* out) {
+    if (!h || !out) return MSS_E_BADARG;
+    *out = h->stats;
+    out->sm_count = h->sm_count;
+    out->device_bytes = h->device_bytes;
+    return MSS_OK;
+}
+
+void* mss_stream(mss_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"
