@@ -1,0 +1,191 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI (libmss.so via ctypes).
+
+Parity bar (BASELINE.json north_star / SURVEY 8c):
+  * keep-bitmask, per-row coverage/slack, counters: BIT-EXACT against the CPU emulation of the device algorithm;
+  * every coverage row at its attainable level, re-evaluated on the CPU from the raw view with integer arithmetic;
+  * F(x) <= 1.01 * ILP optimum (HiGHS at the reference's MIPGap 0.002; committed in tests/golden/config_bounds.json),
+    or <= 1.01 * LP bound where the ILP is out of reach (LP* <= ILP*, so this is sufficient);  tolerance: 1 %.
+"""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+from conftest import view_from_fixture, fixture_key, LAM, GLAM
+from ms_slam_b200 import make_view, msgen, WindowView
+from oracle import ilp_model as om, emulate as em
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 0.01      # north_star: selected-set cost within 1 % of the ILP optimum
+
+
+@pytest.fixture(scope="module")
+def eng(build_native):
+    from ms_slam_b200.engine import Engine
+    e = Engine(N=100, lam=LAM, grid_lam=GLAM, device=0)
+    yield e
+    e.close()
+
+
+def check_against_cpu(view, N, res, ref=None):
+    ref = ref or em.solve(view, N, LAM, GLAM)
+    assert np.array_equal(res.keep, ref["keep"]), "keep bitmask differs from the CPU emulation"
+    assert np.array_equal(res.kf_cov, ref["cov"]) and np.array_equal(res.kf_slack, ref["slack"])
+    assert (res.objective, res.n_kept, res.n_vars, res.n_cells, res.nnz, res.n_max, res.rounds) == \
+           (ref["objective"], ref["n_kept"], ref["n_vars"], ref["n_cells"], ref["nnz"], ref["n_max"], ref["rounds"])
+    # independent re-evaluation with the ILP model builder (not the emulator)
+    model = om.build_model(view, N)
+    x = om.keep_to_x(model, res.keep)
+    F, parts = om.objective(model, x, N, LAM, GLAM, parts=True)
+    assert F == res.objective
+    assert np.array_equal(parts["kf_cov"], res.kf_cov[:view.K]) and np.array_equal(parts["out_cov"], res.kf_cov[view.K:])
+    assert np.array_equal(parts["kf_slack"], res.kf_slack[:view.K]) and np.array_equal(parts["out_slack"], res.kf_slack[view.K:])
+    ok, _, _ = om.rows_satisfied(model, x, N)
+    assert ok, "a coverage row is below its attainable level"
+    nonvar = np.ones(view.M, bool)
+    nonvar[model.var_mp] = False
+    assert res.keep[nonvar].all(), "a map point that is not an ILP variable was deleted"
+    return F
+
+
+def test_known_answers(eng, known_answers):
+    for name, rec in known_answers.items():
+        view = view_from_fixture(rec)
+        eng.set_params(rec["N"], rec["lam"], rec["grid_lam"])
+        res = eng.solve(view)
+        F = check_against_cpu(view, rec["N"], res)
+        assert F == pytest.approx(rec["F_opt"], abs=1e-9), name
+        kept = sorted(np.nonzero(~res.keep)[0].tolist())
+        model = om.build_model(view, rec["N"])
+        kept_vars = sorted(int(p) for p in model.var_mp if res.keep[p])
+        assert kept_vars in rec["optimal_keep_sets"], (name, kept_vars, kept)
+
+
+@pytest.mark.parametrize("name,seed,over", [
+    ("c1", 0, {}), ("c1", 1, {}), ("c1", 2, {}), ("c1", 3, {}), ("c1", 4, {}), ("live", 0, {}), ("live", 1, {}),
+    ("c4", 0, dict(M=3000)), ("live", 0, dict(M=1500, H=20)), ("c3", 0, {}), ("c4", 1000, {}), ("c4", 1001, {})])
+def test_config_parity(eng, config_bounds, name, seed, over):
+    view, N = msgen.make_config(name, seed, **over)
+    eng.set_params(N, LAM, GLAM)
+    res = eng.solve(view)
+    F = check_against_cpu(view, N, res)
+    rec = config_bounds[fixture_key(name, seed, over)]
+    bound = rec["ilp"] if rec.get("ilp") is not None else rec["lp"]
+    assert rec["lp"] - 1e-6 <= F <= (1.0 + REL_TOL) * bound
+
+
+def test_c2_full_size(eng, config_bounds, emulation_golden):
+    """North-star window (500 KF x 200k MP): bit-exact vs the committed emulation checksum + CPU re-evaluation + LP bound."""
+    import hashlib
+    view, N = msgen.make_config("c2", 0)
+    eng.set_params(N, LAM, GLAM)
+    res = eng.solve(view)
+    gold = emulation_golden[fixture_key("c2", 0)]
+    assert hashlib.sha256(res.keep_bits.tobytes()).hexdigest() == gold["keep_sha256"]
+    assert (res.objective, res.n_kept, res.rounds) == (gold["objective"], gold["n_kept"], gold["rounds"])
+    model = om.build_model(view, N)
+    x = om.keep_to_x(model, res.keep)
+    F, parts = om.objective(model, x, N, LAM, GLAM, parts=True)
+    assert F == res.objective and np.array_equal(parts["kf_cov"], res.kf_cov[:view.K])
+    assert om.rows_satisfied(model, x, N)[0]
+    assert F <= (1.0 + REL_TOL) * config_bounds[fixture_key("c2", 0)]["lp"]
+    # size-independent properties: determinism / idempotence of the call
+    res2 = eng.solve(view)
+    assert np.array_equal(res.keep_bits, res2.keep_bits)
+    # improvement is monotone in the drop phase => no kept point is individually removable at a profit
+    kf_cov, cell_cov, out_cov = om.coverage(model, x)
+    crit_c = np.bincount(model.ent_var, weights=(x[model.ent_var] == 1) & (cell_cov[model.ent_cell] == 1), minlength=x.size)
+    crit_r = np.bincount(model.ent_var, weights=(x[model.ent_var] == 1) & (kf_cov[model.ent_kf] <= N), minlength=x.size)
+    crit_o = np.bincount(model.out_var, weights=(x[model.out_var] == 1) & (out_cov[model.out_kf] <= model.out_need[model.out_kf]), minlength=x.size)
+    dF = -model.cost + GLAM * crit_c + LAM * (crit_r + crit_o)
+    assert not ((x == 1) & (dF < 0)).any()
+
+
+def test_batch_equals_singles_and_device_views(eng):
+    from ms_slam_b200.engine import DeviceView
+    specs = [("live", 7, {}), ("c1", 2, {}), ("live", 8, dict(M=1500, H=20)), ("c4", 1002, dict(M=9000)), ("c1", 3, {})]
+    N = 100
+    eng.set_params(N, LAM, GLAM)
+    views = [msgen.make_config(n, s, **o)[0] for n, s, o in specs]
+    singles = [eng.solve(v) for v in views]
+    batch = eng.solve_batch(views)
+    dviews = [DeviceView(eng, v) for v in views]
+    dbatch = eng.solve_batch(dviews)
+    mixed = eng.solve_batch([dviews[0], views[1], dviews[2], views[3], views[4]])
+    for v, s, b, d, m in zip(views, singles, batch, dbatch, mixed):
+        ref = em.solve(v, N, LAM, GLAM)
+        for r in (s, b, d, m):
+            check_against_cpu(v, N, r, ref)
+    for d in dviews:
+        d.free()
+    assert eng.stats()["kernel_launches"] > 0
+
+
+def test_edge_cases(eng):
+    N = 3
+    eng.set_params(N, LAM, GLAM)
+    cases = {
+        "empty-window": make_view(0, [], [5, 6]),
+        "no-mps": make_view(2, [[], []], []),
+        "kf-without-slots": make_view(3, [[(0, 0), (1, 1)], [], [(1, 5)]], [7, 9]),
+        "all-bad-slots": make_view(1, [[(None, 3), (None, None)]], [4]),
+        "off-grid-only": make_view(1, [[(0, None), (1, None)]], [4, 9]),
+        "one-cell-crowd": make_view(1, [[(p, 17) for p in range(40)]], list(range(3, 43))),
+        "outside-only-need": make_view(1, [[(0, 0), (1, 1), (2, 2)]], [9, 9, 3], outside=[[0, 1, 2], [2]], okf_total=[3, 1]),
+    }
+    for name, view in cases.items():
+        res = eng.solve(view)
+        check_against_cpu(view, N, res)
+    # maximum cell index and maximum per-keyframe slot count in one window
+    rng = np.random.default_rng(5)
+    big = make_view(1, [[(int(p), int(c)) for p, c in zip(rng.permutation(5000), rng.integers(0, 3072, 5000))]],
+                    rng.integers(3, 60, 5000).tolist())
+    big.feat_cell[0] = 3071
+    eng.set_params(100, LAM, GLAM)
+    check_against_cpu(big, 100, eng.solve(big))
+
+
+def test_non_integer_lambdas(eng):
+    view, N = msgen.make_config("live", 11)
+    from ms_slam_b200.engine import Engine
+    lam, glam = 437.25, 9.75
+    e = Engine(N=N, lam=lam, grid_lam=glam)
+    res = e.solve(view)
+    ref = em.solve(view, N, lam, glam)
+    assert np.array_equal(res.keep, ref["keep"]) and res.objective == ref["objective"]
+    e.close()
+
+
+def test_invalid_view_is_fail_safe(eng):
+    """Error convention: negative status, never a crash, and the bitmask keeps every map point."""
+    from ms_slam_b200.engine import MssError, MSS_E_BADARG
+    view, N = msgen.make_config("c1", 0)
+    bad = WindowView(K=view.K, H=view.H, feat_ptr=view.feat_ptr, feat_mp=view.feat_mp.copy(), feat_cell=view.feat_cell,
+                     mp_nobs=view.mp_nobs, mp_obs_ptr=view.mp_obs_ptr, mp_obs_kf=view.mp_obs_kf, okf_total=view.okf_total)
+    bad.feat_mp[np.nonzero(bad.feat_mp >= 0)[0][0]] = view.M + 5          # out-of-range map-point index
+    eng.set_params(N, LAM, GLAM)
+    with pytest.raises(MssError) as ei:
+        eng.solve(bad)
+    assert ei.value.status == MSS_E_BADARG
+    res = eng.solve_batch([view, bad], raise_on_status=False)
+    assert res[1].status == MSS_E_BADARG and res[1].keep.all()             # keep everything
+    check_against_cpu(view, N, res[0])                                     # the healthy window is unaffected
+    # NULL pointers / inconsistent sizes are rejected on the host
+    from ms_slam_b200 import engine as E
+    cv = E.mss_window_view(2, 0, 5, 10, 0, E.MEM_HOST)
+    cr = E.mss_result()
+    assert eng.lib.mss_solve(eng.handle, C.byref(cv), C.byref(cr)) == MSS_E_BADARG
+
+
+def test_round_cap_reports_noconverge_but_stays_feasible(build_native):
+    from ms_slam_b200.engine import Engine, MSS_E_NOCONVERGE
+    view, N = msgen.make_config("c4", 0, M=3000)
+    e = Engine(N=N, lam=LAM, grid_lam=GLAM, max_rounds=3, max_drop_rounds=2)
+    res = e.solve(view, raise_on_status=False)
+    assert res.status == MSS_E_NOCONVERGE
+    ref = em.solve(view, N, LAM, GLAM, max_rounds=3, max_drop_rounds=2)
+    assert np.array_equal(res.keep, ref["keep"])
+    model = om.build_model(view, N)
+    assert om.rows_satisfied(model, om.keep_to_x(model, res.keep), N)[0]
+    e.close()
