@@ -7,6 +7,7 @@
 #include "mss_kernels.cuh"
 
 #include <dlfcn.h>
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -74,16 +75,18 @@ struct mss_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     // device arena
-    DevBuf<uint8_t> meta;            // WinDesc[] | row_win[] | tile_win[]
+    DevBuf<uint8_t> meta;            // WinDesc[] | GroupDesc[] | cta_grp[] | gwin[]
     DevBuf<WinState> ws;
     DevBuf<uint8_t> st;
     DevBuf<unsigned long long> acc;
     DevBuf<float> gain;
-    DevBuf<int> row_need;
-    DevBuf<int> ocnt, orow_ptr, ocursor, orow_var;
+    DevBuf<unsigned> deg;
+    DevBuf<uint32_t> ent, live;      // CSR entries / live lists (keyframe-row segments, then outside-row segments)
+    DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
     DevBuf<uint32_t> out;
     DevBuf<uint8_t> stage;           // host views staged here
-    Ctrl* ctrl = nullptr;
+    DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart
+    Ctrl* ctrl = nullptr;            // = sync.p
     // pinned host mirrors
     uint8_t* h_meta = nullptr; size_t h_meta_cap = 0;
     uint32_t* h_out = nullptr; size_t h_out_cap = 0;
@@ -91,6 +94,7 @@ struct mss_handle {
     // comm
     NcclComm comm = nullptr;
     int rank = 0, nranks = 1;
+    unsigned long long watchdog_ns = 20000000000ull;
     // stats
     mss_stats stats{};
     int64_t device_bytes = 0;
@@ -205,43 +209,85 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         out_words = (size_t)nranks * spr * slot_stride;
     }
     const int nl = (int)local.size();
-    long long Ktot = 0, Htot = 0, Mpad = 0, Ocap = 0;
+    long long Ktot = 0, Htot = 0, Mpad = 0, Ftot = 0, Otot = 0;
     size_t stage_bytes = 0;
     for (int w : local) {
         const mss_window_view& v = views[w];
-        Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ocap += v.O;
+        if (v.M > mss::kMaxWindowMps) { h->err = "view: more than 2^20 map points in one window"; return MSS_E_BADARG; }
+        if (v.K + v.H > mss::kMaxWindowRows) { h->err = "view: more than 65535 keyframe rows in one window"; return MSS_E_BADARG; }
+        Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ftot += v.F; Otot += v.O;
         if (v.memory == MSS_MEM_HOST) {
             stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + align_up((size_t)v.F * 2, 16) +
                            align_up((size_t)v.M * 4, 16) + align_up((size_t)(v.M + 1) * 4, 16) + align_up((size_t)v.O * 4, 16) +
                            align_up((size_t)v.H * 4, 16);
         }
     }
-    if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ocap > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
+    if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
     const int Rtot = (int)(Ktot + Htot);
-    const int ntiles = (int)(Mpad / mss::kVarTile);
+
+    // ---- groups: CTAs are split among the windows in proportion to their size; with more windows than CTAs every CTA
+    //      is a group of its own and works through a queue of windows (largest first, least-loaded group next) ----------
+    const int max_grid = std::max(1, h->max_ctas_per_sm * h->sm_count);
+    const int ngroups = std::max(1, std::min(nl, max_grid));
+    std::vector<std::vector<int>> gw(ngroups);
+    std::vector<double> gload(ngroups, 0.0);
+    auto work = [&](int i) { const mss_window_view& v = views[local[i]]; return 1.0 + (double)v.F + (double)v.O + 0.25 * (double)v.M; };
+    {
+        std::vector<int> order(nl);
+        for (int i = 0; i < nl; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
+        for (int i : order) {
+            int best = 0;
+            for (int g = 1; g < ngroups; ++g) if (gload[g] < gload[best]) best = g;
+            gw[best].push_back(i);
+            gload[best] += work(i);
+        }
+    }
+    std::vector<int> gcta(ngroups, 1);
+    if (nl > 0 && ngroups < max_grid) {
+        double total = 0.0;
+        for (double x : gload) total += x;
+        int used = ngroups;
+        for (int g = 0; g < ngroups; ++g) {
+            // a window cannot use more CTAs than it has rows or variable tiles
+            int cap = 1;
+            for (int i : gw[g]) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
+            const int want = (int)((double)(max_grid - ngroups) * gload[g] / std::max(total, 1.0));
+            gcta[g] = std::min(cap, 1 + want);
+            used += gcta[g] - 1;
+        }
+        (void)used;
+    }
+    int grid = 0;
+    for (int g = 0; g < ngroups; ++g) grid += gcta[g];
 
     int rc;
-    const size_t meta_bytes = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16) + align_up((size_t)std::max(Rtot, 1) * 4, 16) +
-                              align_up((size_t)std::max(ntiles, 1) * 4, 16);
+    const size_t off_grp = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16);
+    const size_t off_cta = off_grp + align_up((size_t)ngroups * sizeof(mss::GroupDesc), 16);
+    const size_t off_gwin = off_cta + align_up((size_t)std::max(grid, 1) * 4, 16);
+    const size_t meta_bytes = off_gwin + align_up((size_t)std::max(nl, 1) * 4, 16);
+    const size_t sync_words = 32 + (size_t)ngroups * 32;
     if ((rc = ensure(h, h->meta, meta_bytes))) return rc;
     if ((rc = ensure(h, h->ws, (size_t)std::max(nl, 1)))) return rc;
     if ((rc = ensure(h, h->st, (size_t)Mpad + 16))) return rc;
     if ((rc = ensure(h, h->acc, (size_t)Mpad + 16))) return rc;
     if ((rc = ensure(h, h->gain, (size_t)Mpad + 16))) return rc;
-    if ((rc = ensure(h, h->row_need, (size_t)Rtot + 16))) return rc;
-    if ((rc = ensure(h, h->ocnt, (size_t)Htot + 16))) return rc;
-    if ((rc = ensure(h, h->orow_ptr, (size_t)Htot + 16))) return rc;
-    if ((rc = ensure(h, h->ocursor, (size_t)Htot + 16))) return rc;
-    if ((rc = ensure(h, h->orow_var, (size_t)Ocap + 16))) return rc;
+    if ((rc = ensure(h, h->deg, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->ent, (size_t)(Ftot + Otot) + 16))) return rc;
+    if ((rc = ensure(h, h->live, (size_t)(Ftot + Otot) + 16))) return rc;
+    if ((rc = ensure(h, h->rows, (size_t)7 * ((size_t)Rtot + 16)))) return rc;
     if ((rc = ensure(h, h->out, out_words + 16))) return rc;
     if ((rc = ensure(h, h->stage, stage_bytes + 16))) return rc;
+    if ((rc = ensure(h, h->sync, sync_words))) return rc;
+    h->ctrl = reinterpret_cast<Ctrl*>(h->sync.p);
     if ((rc = ensure_pinned(h, (void**)&h->h_meta, &h->h_meta_cap, meta_bytes))) return rc;
     if ((rc = ensure_pinned(h, (void**)&h->h_out, &h->h_out_cap, (out_words + 16) * 4))) return rc;
 
     // ---- stage host views, build descriptors ------------------------------------------------------------------------
     WinDesc* hd = reinterpret_cast<WinDesc*>(h->h_meta);
-    int* h_row_win = reinterpret_cast<int*>(h->h_meta + align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16));
-    int* h_tile_win = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(h_row_win) + align_up((size_t)std::max(Rtot, 1) * 4, 16));
+    mss::GroupDesc* h_grp = reinterpret_cast<mss::GroupDesc*>(h->h_meta + off_grp);
+    int* h_cta_grp = reinterpret_cast<int*>(h->h_meta + off_cta);
+    int* h_gwin = reinterpret_cast<int*>(h->h_meta + off_gwin);
     int64_t h2d = 0;
     size_t soff = 0;
     auto stage = [&](const void* src, size_t bytes) -> const void* {
@@ -251,7 +297,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         h2d += (int64_t)bytes;
         return dst;
     };
-    int row_base = 0, orow_base = 0, var_base = 0;
+    int row_base = 0, slot_base = 0, obs_base = 0, var_base = 0;
     for (int i = 0; i < nl; ++i) {
         const mss_window_view& v = views[local[i]];
         WinDesc d;
@@ -269,20 +315,20 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
             d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
         }
         d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O;
-        d.row_base = row_base; d.orow_base = orow_base; d.var_base = var_base;
+        d.row_base = row_base; d.slot_base = slot_base; d.obs_base = obs_base; d.var_base = var_base;
         d.out_off = out_off[local[i]];
-        d.owned = 1;
         hd[i] = d;
-        for (int k = 0; k < v.K; ++k) h_row_win[row_base + k] = i;
-        const int tiles = (int)(align_up((size_t)std::max(v.M, 1), mss::kVarTile) / mss::kVarTile);
-        for (int t = 0; t < tiles; ++t) h_tile_win[var_base / mss::kVarTile + t] = i;
-        row_base += v.K; orow_base += v.H; var_base += tiles * mss::kVarTile;
+        row_base += v.K + v.H; slot_base += v.F; obs_base += v.O;
+        var_base += (int)align_up((size_t)std::max(v.M, 1), mss::kVarTile);
     }
-    {   // outside rows come after all keyframe rows
-        int jj = 0;
-        for (int i = 0; i < nl; ++i) {
-            const mss_window_view& v = views[local[i]];
-            for (int j = 0; j < v.H; ++j) h_row_win[Ktot + jj++] = i;
+    {
+        int cta = 0, wpos = 0;
+        for (int g = 0; g < ngroups; ++g) {
+            h_grp[g].cta0 = cta; h_grp[g].ncta = gcta[g];
+            h_grp[g].wbeg = wpos;
+            for (int i : gw[g]) h_gwin[wpos++] = i;
+            h_grp[g].wend = wpos;
+            for (int c = 0; c < gcta[g]; ++c) h_cta_grp[cta++] = g;
         }
     }
     MSS_CUDA(h, cudaGetLastError());
@@ -294,26 +340,34 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     memset(&P, 0, sizeof(P));
     P.win = reinterpret_cast<const WinDesc*>(h->meta.p);
     P.ws = h->ws.p;
-    P.row_win = reinterpret_cast<const int*>(h->meta.p + ((uint8_t*)h_row_win - h->h_meta));
-    P.tile_win = reinterpret_cast<const int*>(h->meta.p + ((uint8_t*)h_tile_win - h->h_meta));
-    P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.row_need = h->row_need.p;
-    P.ocnt = h->ocnt.p; P.orow_ptr = h->orow_ptr.p; P.ocursor = h->ocursor.p; P.orow_var = h->orow_var.p;
+    P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + off_grp);
+    P.cta_grp = reinterpret_cast<const int*>(h->meta.p + off_cta);
+    P.gwin = reinterpret_cast<const int*>(h->meta.p + off_gwin);
+    P.gbar = h->sync.p + 32;
+    P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.deg = h->deg.p;
+    P.ent = h->ent.p; P.live = h->live.p;
+    {
+        const size_t rs = (size_t)Rtot + 16;
+        P.row_off = h->rows.p; P.ent_n = h->rows.p + rs; P.live_n = h->rows.p + 2 * rs; P.row_need = h->rows.p + 3 * rs;
+        P.row_cov = h->rows.p + 4 * rs; P.row_ncell = h->rows.p + 5 * rs; P.ocursor = h->rows.p + 6 * rs;
+    }
     P.out = h->out.p; P.ctrl = h->ctrl;
-    P.nwin = nl; P.Ktot = (int)Ktot; P.Htot = (int)Htot; P.Rtot = Rtot; P.Mpad = (int)Mpad; P.ntiles = ntiles;
+    P.nwin = nl; P.ngroups = ngroups; P.Ftot = (int)Ftot;
     P.N = h->cfg.min_points;
     P.max_rounds = h->cfg.max_rounds; P.all_rule_steps = h->cfg.all_rule_steps; P.max_drop_rounds = h->cfg.max_drop_rounds;
     P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
+    P.watchdog_ns = h->watchdog_ns;
 
     float dev_ms = 0.f;
-    int grid = 0;
     if (nl > 0) {
-        const int max_grid = h->max_ctas_per_sm * h->sm_count;
-        grid = std::max(1, std::min(max_grid, std::max(Rtot, ntiles)));
         void* args[] = {(void*)&P};
+        MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
         MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(grid), dim3(mss::kThreads), args, 0, h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         h->stats.kernel_launches += 1;
+    } else {
+        grid = 0;
     }
     // ---- all-gather of the result slots (keep bits + row coverage only) ---------------------------------------------------
     if (nranks > 1) {
@@ -325,6 +379,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
     MSS_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
     int64_t d2h = (int64_t)(out_words * 4 + sizeof(Ctrl));
+    bool aborted = false;
     for (int w = 0; w < nwin; ++w) {       // device-resident result buffers are filled device-to-device
         const mss_window_view& v = views[w];
         mss_result& r = results[w];
@@ -337,6 +392,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     }
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
+    aborted = nl > 0 && h->h_ctrl->abort != 0;
 
     int ret = MSS_OK;
     const double t_build_us = nl > 0 ? (double)(h->h_ctrl->t_build - h->h_ctrl->t_start) * 1e-3 : 0.0;
@@ -347,6 +403,12 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         const SlotLayout s = slot_of(v);
         const uint32_t* slot = h->h_out + out_off[w];
         const bool host_mem = v.memory != MSS_MEM_DEVICE;
+        if (aborted) {
+            fill_failsafe(v, r, MSS_E_INTERNAL, host_mem, h);
+            ret = MSS_E_INTERNAL;
+            h->err = "device watchdog: a group barrier waited longer than the limit; launch aborted, all map points kept";
+            continue;
+        }
         if (slot[14] != 0x4D535331u) {
             fill_failsafe(v, r, MSS_E_BADARG, host_mem, h);
             if (ret == MSS_OK) { ret = MSS_E_BADARG; h->err = "window " + std::to_string(w) + ": view failed device-side validation (index out of range, bad pointer table or > 1023 points in one grid cell); all map points kept"; }
@@ -430,8 +492,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaMalloc((void**)&h->ctrl, sizeof(Ctrl))) != cudaSuccess) return fail("cudaMalloc", e);
-    if ((e = cudaMemset(h->ctrl, 0, sizeof(Ctrl))) != cudaSuccess) return fail("cudaMemset", e);
+    if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
     if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     h->stats.sm_count = h->sm_count;
     *out = h;
@@ -442,9 +503,8 @@ void mss_destroy(mss_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
-    release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->row_need);
-    release(h->ocnt); release(h->orow_ptr); release(h->ocursor); release(h->orow_var); release(h->out); release(h->stage);
-    if (h->ctrl) cudaFree(h->ctrl);
+    release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->deg);
+    release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);

@@ -1,43 +1,55 @@
-// mss_kernels.cuh -- device side of the sparsification engine (sm_100a).
+// mss_kernels.cuh -- device side of the sparsification engine (sm_100a), kernel generation 2.
 //
-// One persistent cooperative kernel solves a whole batch of independent windows.  What it replaces in the reference
-// (/root/reference/src/MapSparsification.cc):
-//   :66-76   nMaxObservation scan                         -> phase P1 (per keyframe row, block max -> atomicMax)
-//   :78-123  variable discovery + cell rows + KF rows     -> P1 marks variables; cell rows are never materialised:
-//                                                            a CTA owns one keyframe row and keeps its 64x48 cell table
-//                                                            in shared memory (cell rows are private to a keyframe)
-//   :125-151 outside-keyframe rows                        -> P2 count / P3 scan+rhs / P4 fill (CSR of outside rows)
-//   :153-157 GUROBI optimize()                            -> per-window phase machine PROP / GREEDY / DROP (below)
-//   :159-166 read-out of GRB_DoubleAttr_X                 -> EVAL: ballot-packed keep bits + row coverage + F(x)
+// One persistent cooperative kernel solves a whole batch of independent windows.  CTAs are partitioned into GROUPS, one
+// group per window (or a queue of windows per group when there are more windows than CTAs); a group synchronises with
+// its own release/acquire barrier in global memory, so windows never wait for each other (no grid-wide sync anywhere).
 //
-// Selection algorithm on the penalty form F(x), per variable state FREE / IN / OUT:
-//   PROP   exact dominance to a fixed point: ub_p <= 0 -> OUT, lb_p >= 0 -> IN  (bounds on p's marginal gain over
-//          every completion of the FREE points; see oracle/emulate.py for the formulas)
+// What it replaces in the reference (/root/reference/src/MapSparsification.cc):
+//   :66-76   nMaxObservation scan            -> W1 (per keyframe row: block max -> atomicMax)
+//   :78-123  variables + cell rows + KF rows -> W1 marks variables and writes the keyframe rows as a CSR of packed
+//                                               (map point, cell) entries, counting-sorted by cell in shared memory, so the
+//                                               entries of one cell row are a contiguous run of its keyframe row
+//   :125-151 outside-keyframe rows           -> W2 count / W3 scan + rhs / W4 fill (CSR of the outside rows)
+//   :153-157 GUROBI optimize()               -> per-window phase machine PROP / GREEDY / DROP on F(x)
+//   :159-166 read-out of GRB_DoubleAttr_X    -> EVAL: ballot-packed keep bits + row coverage + F(x)
+//
+// Selection algorithm, per variable state FREE / IN / OUT (oracle/emulate.py restates it on the CPU, bit for bit):
+//   PROP   exact dominance to a fixed point: ub_p <= 0 -> OUT, lb_p >= 0 -> IN
 //   GREEDY conflict-free step: a FREE point is taken iff it is the best candidate of every uncovered cell it lies in
 //          and within the top-deficit candidates of every deficient row it lies in
 //   DROP   budgeted reverse delete; per-cell / per-row budgets make the summed deltas exact
-// Every decision is made from integer counters accumulated with integer atomics and from keys with a unique
-// tie-break (gain, then lower map-point index), so the result is deterministic and independent of scheduling;
-// oracle/emulate.py reproduces it bit for bit on the CPU.
+// Every decision is made from integer counters (integer atomics) and keys with a unique tie-break, so the result does not
+// depend on scheduling, on the group partition or on the order of entries inside a list.
+//
+// Work per round is proportional to the UNDECIDED part of the window: round 1 is fused into the build (W1/W4), round 2
+// streams the CSR once, and from then on every row keeps a compacted "live list" of its FREE entries (cell field
+// rewritten to kCellCov once the cell is covered) plus a running row coverage, so later rounds touch only those.
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace mss {
 
-namespace cg = cooperative_groups;
-
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr int kCells = 64 * 48;
+constexpr int kCellsPerThread = kCells / kThreads;     // 12
 constexpr int kVarTile = 256;          // var_base alignment; one var-pass tile belongs to exactly one window
 constexpr int kHdrWords = 16;          // result-slot header
-constexpr unsigned kCellNone = 0xFFFFu;
-constexpr int kCellFieldMax = 1023;    // 10-bit per-cell counters
+constexpr unsigned kCellNone = 0xFFFFu;     // view: slot whose keypoint is not in the grid
+constexpr unsigned kCellCov = 0xFFFu;       // packed entry: "no cell / cell already covered"
+constexpr int kCellBits = 12;
+constexpr int kMaxWindowMps = 1 << 20;      // packed entry = (map point << 12) | cell
+constexpr int kMaxWindowRows = 65535;       // 16-bit per-variable row counters
+constexpr unsigned kEntInvalid = 0xFFFFFFFFu;
+constexpr unsigned kTabCov = 0x80000000u;   // cell table: bit 31 = cell has an IN point, low 16 bits = FREE count
+constexpr int kEpt = 8;                     // entries per thread held in registers (rows up to 2048 entries)
+constexpr int kRegRow = kThreads * kEpt;
 
 enum : uint8_t { ST_FREE = 0, ST_IN = 1, ST_OUT = 2, ST_NOTVAR = 3, ST_CAND = 4 };
-enum : int { MODE_DONE = 0, MODE_PROP = 1, MODE_GREEDY = 2, MODE_FORCE = 3, MODE_D1 = 4, MODE_D2 = 5, MODE_EVAL = 6 };
+enum : int { MODE_DONE = 0, MODE_PROP = 1, MODE_GREEDY = 2, MODE_FORCE = 3, MODE_D1 = 4, MODE_D2 = 5, MODE_EVAL = 6,
+             MODE_EVALV = 7 };
 enum : unsigned long long { FLAG_BLOCKED = 1ull, FLAG_NOMINATED = 2ull };
 enum : unsigned { ERR_INDEX = 1u, ERR_CELL_OVERFLOW = 2u, ERR_PTR = 4u };
 
@@ -50,50 +62,68 @@ struct WinDesc {
     const int* mp_obs_kf;
     const int* okf_total;
     int K, H, M, F, O;
-    int row_base;    // global id of the first keyframe row
-    int orow_base;   // index of the first outside row among all outside rows (global row id = Ktot + orow_base + j)
+    int row_base;    // first row of this window in the per-row arrays: K keyframe rows, then H outside rows
+    int slot_base;   // first entry of this window's keyframe rows in ent[] / live[]
+    int obs_base;    // first entry of this window's outside rows in ent[] / live[] (after all keyframe segments)
     int var_base;    // global variable index of map point 0 (multiple of kVarTile)
     int out_off;     // u32 word offset of this window's result slot
-    int owned;       // solved on this rank
-    int pad_;
+    int pad_[3];
 };
 
-struct WinState {
-    int mode, rounds, greedy_steps, drop_rounds;
-    unsigned changed, nfree, ncand, error;
-    int n_max, n_vars, n_cells, nnz;
-    int n_kept, uncovered, total_slack, status;
-    unsigned long long sum_cost;
+// per-phase counters; three copies rotate so that a copy is zeroed two phases before it is used again
+struct RoundCnt {
+    unsigned changed, nfree, sumdeg, ncand;
+    unsigned uncovered, slack, nkept, rows_live;
+    unsigned long long sumcost;
     unsigned long long pad_;
 };
 
+struct WinState {
+    int n_max, n_vars, n_cells, nnz;
+    unsigned error;
+    int pad_[3];
+    RoundCnt rc[3];
+};
+
+struct GroupDesc {
+    int cta0, ncta;      // CTAs [cta0, cta0 + ncta) work on this group's windows
+    int wbeg, wend;      // windows gwin[wbeg .. wend), solved one after the other
+};
+
 struct Ctrl {
-    unsigned ticket;
-    int n_active;
     unsigned long long t_start, t_build, t_end;
-    int iters;
+    int abort;           // set by the watchdog: a barrier waited longer than watchdog_ns
     int pad_;
 };
 
 struct Params {
     const WinDesc* win;
     WinState* ws;
-    const int* row_win;     // [Rtot] window of every row (keyframe rows first, then outside rows)
-    const int* tile_win;    // [ntiles]
-    uint8_t* st;            // [Mpad]
-    unsigned long long* acc;// [Mpad] packed counters / flags
-    float* gain;            // [Mpad]
-    int* row_need;          // [Rtot]
-    int* ocnt;              // [Htot]
-    int* orow_ptr;          // [Htot+1]
-    int* ocursor;           // [Htot]
-    int* orow_var;          // [Ocap]
-    uint32_t* out;          // result slots
+    const GroupDesc* grp;
+    const int* cta_grp;      // [grid] group of every CTA
+    const int* gwin;         // window lists of the groups
+    unsigned* gbar;          // one barrier counter per group, 128 B apart, zeroed before the launch
+    uint8_t* st;             // [Mpad] variable state
+    unsigned long long* acc; // [Mpad] packed 4 x 16-bit counters / flags
+    float* gain;             // [Mpad]
+    unsigned* deg;           // [Mpad] number of row entries of the variable
+    uint32_t* ent;           // [Ftot + Otot] CSR entries: keyframe rows at slot_base + feat_ptr[k], then outside rows
+    uint32_t* live;          // [Ftot + Otot] live lists (same segments)
+    int* row_off;            // [Rtot] first entry of the row's segment
+    int* ent_n;              // [Rtot] CSR entries of the row
+    int* live_n;             // [Rtot] live entries of the row
+    int* row_need;           // [Rtot]
+    int* row_cov;            // [Rtot] IN entries of the row (running)
+    int* row_ncell;          // [Rtot] occupied cells of the row
+    int* ocursor;            // [Rtot] fill cursor of the outside rows
+    uint32_t* out;           // result slots
     Ctrl* ctrl;
-    int nwin, Ktot, Htot, Rtot, Mpad, ntiles;
+    int nwin, ngroups;
+    int Ftot;                // outside-row segments start at ent + Ftot
     int N;
     int max_rounds, all_rule_steps, max_drop_rounds;
     double lam, glam;
+    unsigned long long watchdog_ns;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -103,6 +133,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ unsigned f32_orderable(float g) {
@@ -115,11 +153,50 @@ __device__ __forceinline__ unsigned long long make_key(float g, unsigned local_i
 }
 
 struct BlockScratch {
-    int red[3][kThreads / 32];
+    int red[3][kWarps];
+    int scan[kWarps];
     int bcast[4];
     unsigned hist[256];
-    unsigned long long sel_prefix;
 };
+
+struct GroupCtx {
+    unsigned* bar;
+    unsigned gen;
+    int ncta;
+    int cta;        // index of this CTA inside the group
+    int* s_abort;   // shared flag
+    unsigned long long t0;   // this CTA's start time (watchdog reference)
+};
+
+// Barrier of the CTAs of one group.  Thread 0 publishes the CTA's writes with a release add and waits with acquire
+// loads; bar.sync on both sides extends the ordering to the whole CTA (same construction as a cooperative grid sync,
+// but scoped to the CTAs that actually share the window).  Returns false when the launch is being aborted.
+__device__ __forceinline__ bool group_sync(const Params& P, GroupCtx& G) {
+    __syncthreads();
+    G.gen += 1u;
+    if (threadIdx.x == 0) {
+        int ab = 0;
+        if (G.ncta > 1) {
+            red_release_add_u32(G.bar, 1u);
+            const unsigned target = G.gen * (unsigned)G.ncta;
+            unsigned spins = 0;
+            while (ld_acquire_u32(G.bar) < target) {
+                if ((++spins & 0xFFu) == 0u) {
+                    if (*(volatile int*)&P.ctrl->abort) { ab = 1; break; }
+                    if (globaltimer_ns() - G.t0 > P.watchdog_ns) {
+                        atomicExch(&P.ctrl->abort, 1);
+                        ab = 1;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!ab) ab = *(volatile int*)&P.ctrl->abort;
+        *G.s_abort = ab;
+    }
+    __syncthreads();
+    return *G.s_abort == 0;
+}
 
 // block-wide sum of up to three ints, result broadcast to every thread
 __device__ __forceinline__ void block_sum3(BlockScratch& S, int& a, int& b, int& c) {
@@ -135,7 +212,7 @@ __device__ __forceinline__ void block_sum3(BlockScratch& S, int& a, int& b, int&
     __syncthreads();
     a = b = c = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) { a += S.red[0][w]; b += S.red[1][w]; c += S.red[2][w]; }
+    for (int w = 0; w < kWarps; ++w) { a += S.red[0][w]; b += S.red[1][w]; c += S.red[2][w]; }
 }
 
 __device__ __forceinline__ int block_max(BlockScratch& S, int a) {
@@ -147,56 +224,48 @@ __device__ __forceinline__ int block_max(BlockScratch& S, int a) {
     __syncthreads();
     int m = S.red[0][0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) m = max(m, S.red[0][w]);
+    for (int w = 1; w < kWarps; ++w) m = max(m, S.red[0][w]);
     return m;
 }
 
-// A row of the coverage problem: a window keyframe (entries = valid grid-listed slots, each in a cell) or an
-// outside keyframe (entries = variables it observes, no cells).
-struct Row {
-    const int* mp;            // keyframe row: feat_mp ; outside row: orow_var (global variable indices)
-    const uint16_t* cell;     // keyframe row only
-    int beg, end;
-    int var_base;
-    int need;
-    bool is_kf;
-};
-
-template <class Fn>
-__device__ __forceinline__ void for_each_entry(const Row& R, Fn fn) {
-    if (R.is_kf) {
-        for (int i = R.beg + (int)threadIdx.x; i < R.end; i += kThreads) {
-            const int mp = __ldg(R.mp + i);
-            if (mp < 0) continue;
-            const unsigned c = __ldg(R.cell + i);
-            if (c == kCellNone) continue;
-            fn(R.var_base + mp, (int)c);
-        }
-    } else {
-        for (int i = R.beg + (int)threadIdx.x; i < R.end; i += kThreads) fn(R.mp[i], -1);
+// exclusive prefix of one int per thread (thread order); total returned to every thread
+__device__ __forceinline__ int block_excl_scan(BlockScratch& S, int v, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
     }
+    __syncthreads();
+    if (lane == 31) S.scan[wid] = x;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) {
+        const int t = S.scan[q];
+        if (q < wid) woff += t;
+        tot += t;
+    }
+    total = tot;
+    return woff + x - v;
 }
 
-__device__ __forceinline__ Row make_row(const Params& P, int r, const WinDesc& D) {
-    Row R;
-    R.need = P.row_need[r];
-    R.var_base = D.var_base;
-    if (r < P.Ktot) {
-        const int k = r - D.row_base;
-        R.is_kf = true;
-        R.mp = D.feat_mp;
-        R.cell = D.feat_cell;
-        R.beg = __ldg(D.feat_ptr + k);
-        R.end = __ldg(D.feat_ptr + k + 1);
-    } else {
-        const int jj = r - P.Ktot;
-        R.is_kf = false;
-        R.mp = P.orow_var;
-        R.cell = nullptr;
-        R.beg = P.orow_ptr[jj];
-        R.end = P.orow_ptr[jj + 1];
+// exclusive prefix of one int per WARP (value taken from lane 0 of each warp); returns this warp's offset
+__device__ __forceinline__ int warp_excl_scan(BlockScratch& S, int warp_val, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) S.scan[wid] = warp_val;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) {
+        const int t = S.scan[q];
+        if (q < wid) woff += t;
+        tot += t;
     }
-    return R;
+    total = tot;
+    return woff;
 }
 
 // (rank+1)-th largest key (rank elements are larger, counting multiplicity) among the keys produced by `emit`.
@@ -206,7 +275,7 @@ __device__ unsigned long long block_kth_largest(BlockScratch& S, int rank, Emit 
     unsigned long long prefix = 0, mask = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         __syncthreads();
-        if (threadIdx.x < 256) S.hist[threadIdx.x] = 0;
+        S.hist[threadIdx.x] = 0;            // kThreads == 256 bins
         __syncthreads();
         emit([&](unsigned long long key) {
             if ((key & mask) == prefix) atomicAdd(&S.hist[(unsigned)(key >> shift) & 255u], 1u);
@@ -230,100 +299,9 @@ __device__ unsigned long long block_kth_largest(BlockScratch& S, int rank, Emit 
     return prefix;
 }
 
-// cell table word: [total:12 | nin:10 | nlow:10]   (nlow = FREE count in PROP/GREEDY, CAND count in D2)
-__device__ __forceinline__ int tab_low(unsigned t) { return (int)(t & 0x3FFu); }
-__device__ __forceinline__ int tab_in(unsigned t) { return (int)((t >> 10) & 0x3FFu); }
-__device__ __forceinline__ int tab_total(unsigned t) { return (int)(t >> 20); }
-
 __device__ __forceinline__ void zero_tab(unsigned* tab) {
-    for (int c = threadIdx.x; c < kCells; c += kThreads) tab[c] = 0u;
-}
-__device__ __forceinline__ void zero_keytab(unsigned long long* kt) {
-    for (int c = threadIdx.x; c < kCells; c += kThreads) kt[c] = 0ull;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// build phases
-// ---------------------------------------------------------------------------------------------------------------
-__device__ void p1_scan_row(const Params& P, int r, unsigned* tab, BlockScratch& S) {
-    const int w = P.row_win[r];
-    const WinDesc D = P.win[w];
-    const int k = r - D.row_base;
-    const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
-    unsigned err = 0;
-    if (beg < 0 || end < beg || end > D.F) {
-        if (threadIdx.x == 0) atomicOr(&P.ws[w].error, ERR_PTR);
-        if (threadIdx.x == 0) P.row_need[r] = P.N;
-        return;
-    }
-    zero_tab(tab);
-    __syncthreads();
-    int nmax = 0, nz = 0;
-    for (int i = beg + (int)threadIdx.x; i < end; i += kThreads) {
-        const int mp = __ldg(D.feat_mp + i);
-        if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
-        if (mp >= D.M) { err |= ERR_INDEX; continue; }
-        nmax = max(nmax, __ldg(D.mp_nobs + mp));                 // MapSparsification.cc:69-75: every valid slot
-        const unsigned c = __ldg(D.feat_cell + i);
-        if (c == kCellNone) continue;                           // not in mGrid: not a variable through this slot
-        if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
-        P.st[D.var_base + mp] = ST_FREE;                        // MapSparsification.cc:91-99 (same value from every writer)
-        atomicAdd(&tab[c], 1u);
-        ++nz;
-    }
-    __syncthreads();
-    int ncell = 0, z0 = 0;
-    for (int c = threadIdx.x; c < kCells; c += kThreads) {
-        const unsigned t = tab[c];
-        if (t) ++ncell;
-        if (t > (unsigned)kCellFieldMax) err |= ERR_CELL_OVERFLOW;
-    }
-    nmax = block_max(S, nmax);
-    block_sum3(S, nz, ncell, z0);
-    if (threadIdx.x == 0) {
-        atomicMax(&P.ws[w].n_max, nmax);
-        if (nz) atomicAdd(&P.ws[w].nnz, nz);
-        if (ncell) atomicAdd(&P.ws[w].n_cells, ncell);
-        P.row_need[r] = P.N;
-    }
-    if (err) atomicOr(&P.ws[w].error, err);
-}
-
-// per variable: count it, and count/fill its observations by outside keyframes (MapSparsification.cc:127-142)
-template <bool FILL>
-__device__ void p24_outside(const Params& P, int tile, BlockScratch& S) {
-    const int w = P.tile_win[tile];
-    const WinDesc D = P.win[w];
-    if (!D.owned) return;
-    const int g = tile * kVarTile + (int)threadIdx.x;
-    const int mp = g - D.var_base;
-    int nv = 0, z0 = 0, z1 = 0;
-    if (mp < D.M && P.st[g] == ST_FREE) {
-        nv = 1;
-        if (D.H > 0) {
-            const int ob = __ldg(D.mp_obs_ptr + mp), oe = __ldg(D.mp_obs_ptr + mp + 1);
-            if (ob < 0 || oe < ob || oe > D.O) {
-                atomicOr(&P.ws[w].error, ERR_PTR);
-            } else {
-                for (int o = ob; o < oe; ++o) {
-                    const int kf = __ldg(D.mp_obs_kf + o);
-                    if (kf < D.K) { if (kf < 0) atomicOr(&P.ws[w].error, ERR_INDEX); continue; }
-                    if (kf >= D.K + D.H) { atomicOr(&P.ws[w].error, ERR_INDEX); continue; }
-                    const int jj = D.orow_base + (kf - D.K);
-                    if (FILL) {
-                        const int pos = atomicAdd(&P.ocursor[jj], 1);
-                        P.orow_var[pos] = g;
-                    } else {
-                        atomicAdd(&P.ocnt[jj], 1);
-                    }
-                }
-            }
-        }
-    }
-    if (!FILL) {
-        block_sum3(S, nv, z0, z1);
-        if (threadIdx.x == 0 && nv) atomicAdd(&P.ws[w].n_vars, nv);
-    }
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) tab[threadIdx.x + j * kThreads] = 0u;
 }
 
 // canonical integer rhs of an outside row (reference: MapSparsification.cc:146-147)
@@ -333,224 +311,549 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
     return (int)ceil((double)r - 1e-5);
 }
 
-// block 0: exclusive scan of the outside-row counts, rhs of the outside rows, window error gate
-__device__ void p3_scan(const Params& P, BlockScratch& S) {
-    __shared__ int carry;
-    __shared__ int warp_tot[kThreads / 32];
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+// A row's entries held in registers: warp w owns a contiguous chunk of the list, lane-strided inside it, so global
+// accesses are coalesced and (warp, b, lane) order is list order (needed for the stable compaction).
+struct RowRegs {
+    uint32_t e[kEpt];
+    uint8_t s[kEpt];
+    int per, nb;
+};
+
+__device__ __forceinline__ void load_row(RowRegs& X, const uint32_t* __restrict__ src, int n, const uint8_t* __restrict__ st_w) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < P.Htot; base += kThreads) {
-        const int jj = base + (int)threadIdx.x;
-        const int v = (jj < P.Htot) ? P.ocnt[jj] : 0;
-        int x = v;
+    X.per = (((n + kWarps - 1) / kWarps) + 31) & ~31;
+    X.nb = X.per >> 5;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[wid] = x;
-        __syncthreads();
-        int woff = 0;
-        for (int q = 0; q < wid; ++q) woff += warp_tot[q];
-        const int excl = carry + woff + x - v;
-        if (jj < P.Htot) {
-            P.orow_ptr[jj] = excl;
-            P.ocursor[jj] = excl;
-            const int w = P.row_win[P.Ktot + jj];
-            const WinDesc& D = P.win[w];
-            const int total = D.owned ? __ldg(D.okf_total + (jj - D.orow_base)) : 0;
-            P.row_need[P.Ktot + jj] = outside_need(v, total, P.N);
-        }
-        __syncthreads();
-        if (threadIdx.x == kThreads - 1) carry = excl + v;
-        __syncthreads();
+    for (int b = 0; b < kEpt; ++b) {
+        const int idx = wid * X.per + b * 32 + lane;
+        X.e[b] = (b < X.nb && idx < n) ? src[idx] : kEntInvalid;
     }
-    if (threadIdx.x == 0) P.orow_ptr[P.Htot] = carry;
-    // windows whose view failed validation never enter the phase machine
-    int nact = 0, z0 = 0, z1 = 0;
-    for (int w = threadIdx.x; w < P.nwin; w += kThreads) {
-        WinState& s = P.ws[w];
-        if (s.mode != MODE_DONE) {
-            if (s.error) { s.mode = MODE_DONE; s.status = -1; }
-            else ++nact;
+#pragma unroll
+    for (int b = 0; b < kEpt; ++b) X.s[b] = (X.e[b] != kEntInvalid) ? st_w[X.e[b] >> kCellBits] : (uint8_t)ST_NOTVAR;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// W1: keyframe row -> nMax, variable marking, cell-sorted CSR segment, round-1 contributions
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, unsigned* tab, unsigned* cursor,
+                             BlockScratch& S) {
+    const int R = D.row_base + k;
+    const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
+    if (beg < 0 || end < beg || end > D.F) {
+        if (threadIdx.x == 0) {
+            atomicOr(&ws.error, ERR_PTR);
+            P.ent_n[R] = 0; P.live_n[R] = 0; P.row_need[R] = P.N; P.row_cov[R] = 0; P.row_ncell[R] = 0; P.row_off[R] = 0;
+        }
+        return;
+    }
+    zero_tab(tab);
+    __syncthreads();
+    unsigned err = 0;
+    int nmax = 0, nz = 0;
+    uint8_t* st_w = P.st + D.var_base;
+    for (int i = beg + (int)threadIdx.x; i < end; i += kThreads) {
+        const int mp = __ldg(D.feat_mp + i);
+        if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
+        if (mp >= D.M) { err |= ERR_INDEX; continue; }
+        nmax = max(nmax, __ldg(D.mp_nobs + mp));                 // MapSparsification.cc:69-75: every valid slot
+        const unsigned c = __ldg(D.feat_cell + i);
+        if (c == kCellNone) continue;                           // not in mGrid: not a variable through this slot
+        if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
+        st_w[mp] = ST_FREE;                                     // MapSparsification.cc:91-99 (same value from every writer)
+        atomicAdd(&tab[c], 1u);
+        ++nz;
+    }
+    nmax = block_max(S, nmax);
+    int z0 = 0, z1 = 0;
+    block_sum3(S, nz, z0, z1);                                  // nz = entries of the row; barriers publish tab
+    // exclusive scan of the cell histogram -> scatter cursors (counting sort by cell)
+    int local = 0, ncell = 0;
+    const int c0 = (int)threadIdx.x * kCellsPerThread;
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        const unsigned t = tab[c0 + j];
+        local += (int)t;
+        ncell += t ? 1 : 0;
+        if (t > 0xFFFFu) err |= ERR_CELL_OVERFLOW;
+    }
+    int total;
+    int base = block_excl_scan(S, local, total);
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        cursor[c0 + j] = (unsigned)base;
+        base += (int)tab[c0 + j];
+    }
+    block_sum3(S, ncell, z0, z1);                               // barriers publish cursor
+    const int seg = D.slot_base + beg;
+    // round 1 (everything FREE, nothing IN): every cell is uncovered, every row with N > 0 is deficient
+    const bool defi = P.N > 0;
+    const bool critr = defi && P.N >= nz;
+    uint32_t* ent = P.ent + seg;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    for (int i = beg + (int)threadIdx.x; i < end; i += kThreads) {
+        const int mp = __ldg(D.feat_mp + i);
+        if (mp < 0 || mp >= D.M) continue;
+        const unsigned c = __ldg(D.feat_cell + i);
+        if (c >= (unsigned)kCells) continue;
+        const unsigned pos = atomicAdd(&cursor[c], 1u);
+        ent[pos] = ((uint32_t)mp << kCellBits) | c;
+        unsigned long long add = 1ull;
+        if (tab[c] == 1u) add |= 1ull << 16;
+        if (defi) add |= 1ull << 32;
+        if (critr) add |= 1ull << 48;
+        atomicAdd(&acc_w[mp], add);
+    }
+    if (threadIdx.x == 0) {
+        P.ent_n[R] = nz; P.live_n[R] = 0; P.row_need[R] = P.N; P.row_cov[R] = 0; P.row_ncell[R] = ncell; P.row_off[R] = seg;
+        atomicMax(&ws.n_max, nmax);
+        if (nz) atomicAdd(&ws.nnz, nz);
+        if (ncell) atomicAdd(&ws.n_cells, ncell);
+    }
+    if (err) atomicOr(&ws.error, err);
+}
+
+// W2: per variable, count it and count its observations by outside keyframes (MapSparsification.cc:127-142)
+__device__ void w2_count_outside(const Params& P, const WinDesc& D, WinState& ws, int tile, BlockScratch& S) {
+    const int mp = tile * kVarTile + (int)threadIdx.x;
+    int nv = 0, z0 = 0, z1 = 0;
+    if (mp < D.M && P.st[D.var_base + mp] == ST_FREE) {
+        nv = 1;
+        if (D.H > 0) {
+            const int ob = __ldg(D.mp_obs_ptr + mp), oe = __ldg(D.mp_obs_ptr + mp + 1);
+            if (ob < 0 || oe < ob || oe > D.O) {
+                atomicOr(&ws.error, ERR_PTR);
+            } else {
+                for (int o = ob; o < oe; ++o) {
+                    const int kf = __ldg(D.mp_obs_kf + o);
+                    if (kf < D.K) { if (kf < 0) atomicOr(&ws.error, ERR_INDEX); continue; }
+                    if (kf >= D.K + D.H) { atomicOr(&ws.error, ERR_INDEX); continue; }
+                    atomicAdd(&P.ent_n[D.row_base + kf], 1);
+                }
+            }
         }
     }
-    block_sum3(S, nact, z0, z1);
-    if (threadIdx.x == 0) P.ctrl->n_active = nact;
+    block_sum3(S, nv, z0, z1);
+    if (threadIdx.x == 0 && nv) atomicAdd(&ws.n_vars, nv);
+}
+
+// W3 (one CTA per window): exclusive scan of the outside-row counts -> segments, rhs of the outside rows
+__device__ void w3_scan_outside(const Params& P, const WinDesc& D, BlockScratch& S) {
+    int carry = 0;
+    for (int base = 0; base < D.H; base += kThreads) {
+        const int j = base + (int)threadIdx.x;
+        const int R = D.row_base + D.K + j;
+        const int v = (j < D.H) ? P.ent_n[R] : 0;
+        int total;
+        const int excl = carry + block_excl_scan(S, v, total);
+        if (j < D.H) {
+            const int off = P.Ftot + D.obs_base + excl;
+            P.row_off[R] = off;
+            P.ocursor[R] = off;
+            P.row_need[R] = outside_need(v, __ldg(D.okf_total + j), P.N);
+            P.row_cov[R] = 0;
+            P.row_ncell[R] = 0;
+            P.live_n[R] = 0;
+        }
+        carry += total;
+    }
+}
+
+// Decision of a FREE variable from its packed counters (shared by W4 and the PROP variable phase)
+__device__ __forceinline__ void prop_decide(const Params& P, unsigned long long a, int cost_i, uint8_t* st, float* gain, unsigned deg,
+                                            int& changed, int& nfree, int& sumdeg) {
+    const double ubc = (double)(a & 0xFFFFu), lbc = (double)((a >> 16) & 0xFFFFu);
+    const double ubr = (double)((a >> 32) & 0xFFFFu), lbr = (double)(a >> 48);
+    const double cost = (double)cost_i;
+    const double ub = __dsub_rn(__dadd_rn(__dmul_rn(P.glam, ubc), __dmul_rn(P.lam, ubr)), cost);
+    const double lb = __dsub_rn(__dadd_rn(__dmul_rn(P.glam, lbc), __dmul_rn(P.lam, lbr)), cost);
+    if (ub <= 0.0) { *st = ST_OUT; changed += 1; }
+    else if (lb >= 0.0) { *st = ST_IN; changed += 1; }
+    else { *gain = (float)ub; nfree += 1; sumdeg += (int)deg; }
+}
+
+// W4: per variable, fill the outside rows, add their round-1 contributions and take the round-1 decision
+__device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& ws, int tile, BlockScratch& S) {
+    const int mp = tile * kVarTile + (int)threadIdx.x;
+    const int g = D.var_base + mp;
+    int changed = 0, nfree = 0, sumdeg = 0;
+    if (mp < D.M && P.st[g] == ST_FREE) {
+        unsigned long long a = P.acc[g];
+        P.acc[g] = 0ull;
+        unsigned nout = 0;
+        if (D.H > 0) {
+            const int ob = __ldg(D.mp_obs_ptr + mp), oe = __ldg(D.mp_obs_ptr + mp + 1);
+            for (int o = ob; o < oe; ++o) {
+                const int kf = __ldg(D.mp_obs_kf + o);
+                if (kf < D.K) continue;
+                const int R = D.row_base + kf;
+                const int pos = atomicAdd(&P.ocursor[R], 1);
+                P.ent[pos] = ((uint32_t)mp << kCellBits) | kCellCov;
+                ++nout;
+                const int need = P.row_need[R];
+                if (need > 0) {
+                    a += 1ull << 32;
+                    if (need >= P.ent_n[R]) a += 1ull << 48;
+                }
+            }
+        }
+        const unsigned deg = (unsigned)(a & 0xFFFFu) + nout;
+        P.deg[g] = deg;
+        prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], deg, changed, nfree, sumdeg);
+    }
+    block_sum3(S, changed, nfree, sumdeg);
+    if (threadIdx.x == 0) {
+        RoundCnt& rc = ws.rc[0];
+        if (changed) atomicAdd(&rc.changed, (unsigned)changed);
+        if (nfree) atomicAdd(&rc.nfree, (unsigned)nfree);
+        if (sumdeg) atomicAdd(&rc.sumdeg, (unsigned)sumdeg);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // row phases (one CTA per row at a time)
 // ---------------------------------------------------------------------------------------------------------------
-// sweep 1 shared by all modes: per-cell and per-row counts of (IN-like, low-like) entries
-template <class Classify>
-__device__ __forceinline__ void count_sweep(const Row& R, const Params& P, unsigned* tab, BlockScratch& S,
-                                            int& n_in, int& n_low, Classify cls) {
-    int a = 0, b = 0, c = 0;
-    for_each_entry(R, [&](int g, int cell) {
-        const unsigned add = cls(P.st[g]);          // bit10 = counts as IN, bit0 = counts as low, bit20 = total
-        if (add & (1u << 10)) ++a;
-        if (add & 1u) ++b;
-        if (cell >= 0 && add) atomicAdd(&tab[cell], add);
-    });
-    block_sum3(S, a, b, c);        // contains the barriers that publish tab
-    n_in = a;
-    n_low = b;
+// PROP: counts on the current state, contributions to the FREE variables, and the row's new live list.
+// Source list: the CSR (first PROP row phase of the window) or the previous live list.  Entries found IN are added to the
+// running coverage exactly once (they are not copied to the new list); entries found OUT are dropped.
+__device__ void row_prop(const Params& P, const WinDesc& D, RoundCnt& rc, int R, bool from_csr, unsigned* tab, BlockScratch& S) {
+    const int n = from_csr ? P.ent_n[R] : P.live_n[R];
+    if (n == 0) return;                                     // live_n[R] is already 0 (W1 / W3 / previous round)
+    const int off = P.row_off[R];
+    const uint32_t* src = (from_csr ? P.ent : P.live) + off;
+    uint32_t* dst = P.live + off;
+    const uint8_t* st_w = P.st + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int need = P.row_need[R];
+    const int cov0 = P.row_cov[R];
+    const int lane = threadIdx.x & 31;
+    if (n <= kRegRow) {
+        RowRegs X;
+        load_row(X, src, n, st_w);
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b)
+            if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
+        __syncthreads();
+        int cin = 0, cfree = 0, z = 0;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            if (X.e[b] == kEntInvalid) continue;
+            const unsigned cell = X.e[b] & kCellCov;
+            if (X.s[b] == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
+            else if (X.s[b] == ST_FREE) { ++cfree; if (cell != kCellCov) atomicAdd(&tab[cell], 1u); }
+        }
+        block_sum3(S, cin, cfree, z);                       // barriers publish tab
+        const int cov = cov0 + cin;
+        const int d = max(0, need - cov);
+        const bool defi = d > 0, critr = defi && d >= cfree;
+        int wcnt = 0;
+        unsigned m[kEpt];
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            const bool fr = (X.e[b] != kEntInvalid) && X.s[b] == ST_FREE;
+            if (fr) {
+                const unsigned cell = X.e[b] & kCellCov;
+                unsigned long long add = 0;
+                bool covered = true;
+                if (cell != kCellCov) {
+                    const unsigned t = tab[cell];
+                    covered = (t & kTabCov) != 0u;
+                    if (!covered) { add |= 1ull; if ((t & 0xFFFFu) == 1u) add |= 1ull << 16; }
+                }
+                if (defi) add |= 1ull << 32;
+                if (critr) add |= 1ull << 48;
+                if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
+                if (covered) X.e[b] |= kCellCov;
+            }
+            m[b] = __ballot_sync(0xFFFFFFFFu, fr);
+            wcnt += __popc(m[b]);
+        }
+        int total;
+        int pos = warp_excl_scan(S, wcnt, total);           // barrier: every read of src precedes the in-place writes
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            if ((m[b] >> lane) & 1u) dst[pos + __popc(m[b] & lt)] = X.e[b];
+            pos += __popc(m[b]);
+        }
+        if (threadIdx.x == 0) {
+            P.row_cov[R] = cov;
+            P.live_n[R] = cfree;
+            if (cfree) atomicAdd(&rc.rows_live, 1u);
+        }
+    } else {
+        // long row: two passes over the list in global memory
+        zero_tab(tab);
+        __syncthreads();
+        int cin = 0, cfree = 0, z = 0;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const uint32_t e = src[i];
+            const uint8_t s = st_w[e >> kCellBits];
+            const unsigned cell = e & kCellCov;
+            if (s == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
+            else if (s == ST_FREE) { ++cfree; if (cell != kCellCov) atomicAdd(&tab[cell], 1u); }
+        }
+        block_sum3(S, cin, cfree, z);
+        const int cov = cov0 + cin;
+        const int d = max(0, need - cov);
+        const bool defi = d > 0, critr = defi && d >= cfree;
+        int out_base = 0;
+        for (int base = 0; base < n; base += kThreads) {
+            const int i = base + (int)threadIdx.x;
+            uint32_t e = kEntInvalid;
+            bool fr = false;
+            if (i < n) {
+                e = src[i];
+                fr = st_w[e >> kCellBits] == ST_FREE;
+            }
+            if (fr) {
+                const unsigned cell = e & kCellCov;
+                unsigned long long add = 0;
+                bool covered = true;
+                if (cell != kCellCov) {
+                    const unsigned t = tab[cell];
+                    covered = (t & kTabCov) != 0u;
+                    if (!covered) { add |= 1ull; if ((t & 0xFFFFu) == 1u) add |= 1ull << 16; }
+                }
+                if (defi) add |= 1ull << 32;
+                if (critr) add |= 1ull << 48;
+                if (add) atomicAdd(&acc_w[e >> kCellBits], add);
+                if (covered) e |= kCellCov;
+            }
+            int total;
+            const int p = block_excl_scan(S, fr ? 1 : 0, total);    // barriers: chunk read before it is overwritten
+            if (fr) dst[out_base + p] = e;
+            out_base += total;
+        }
+        if (threadIdx.x == 0) {
+            P.row_cov[R] = cov;
+            P.live_n[R] = cfree;
+            if (cfree) atomicAdd(&rc.rows_live, 1u);
+        }
+    }
 }
 
-__device__ void row_prop(const Params& P, const Row& R, unsigned* tab, BlockScratch& S) {
-    if (R.is_kf) { zero_tab(tab); __syncthreads(); }
-    int cov, nfree;
-    count_sweep(R, P, tab, S, cov, nfree,
-                [](uint8_t s) -> unsigned { return s == ST_IN ? (1u << 10) : (s == ST_FREE ? 1u : 0u); });
-    if (nfree == 0) return;
-    const int d = max(0, R.need - cov);
-    const bool defi = d > 0;
-    const bool critr = defi && d >= nfree;
-    for_each_entry(R, [&](int g, int cell) {
-        if (P.st[g] != ST_FREE) return;
-        unsigned long long add = 0;
-        if (cell >= 0) {
-            const unsigned t = tab[cell];
-            if (tab_in(t) == 0) {
-                add |= 1ull;
-                if (tab_low(t) == 1) add |= 1ull << 16;
+// GREEDY: runs right after a PROP round that changed nothing, so the live list is exact (all FREE, cell field = covered
+// flag, row_cov current).
+__device__ void row_greedy(const Params& P, const WinDesc& D, int R, unsigned long long* keytab, BlockScratch& S) {
+    const int n = P.live_n[R];
+    if (n == 0) return;
+    const uint32_t* src = P.live + P.row_off[R];
+    const uint8_t* st_w = P.st + D.var_base;
+    const float* gain_w = P.gain + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int d = max(0, P.row_need[R] - P.row_cov[R]);
+    if (n <= kRegRow) {
+        RowRegs X;
+        load_row(X, src, n, st_w);
+        unsigned long long key[kEpt];
+        int nfree = 0;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            const bool fr = X.e[b] != kEntInvalid && X.s[b] == ST_FREE;
+            key[b] = fr ? make_key(gain_w[X.e[b] >> kCellBits], X.e[b] >> kCellBits) : 0ull;
+            if (fr) { ++nfree; if ((X.e[b] & kCellCov) != kCellCov) keytab[X.e[b] & kCellCov] = 0ull; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b)
+            if (key[b] && (X.e[b] & kCellCov) != kCellCov) atomicMax(&keytab[X.e[b] & kCellCov], key[b]);
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b)
+            if (key[b] && (X.e[b] & kCellCov) != kCellCov && keytab[X.e[b] & kCellCov] != key[b])
+                atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_BLOCKED);
+        if (d > 0) {
+            int z0 = 0, z1 = 0;
+            block_sum3(S, nfree, z0, z1);
+            if (nfree > d) {
+                const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
+#pragma unroll
+                    for (int b = 0; b < kEpt; ++b) if (key[b]) sink(key[b]);
+                });
+#pragma unroll
+                for (int b = 0; b < kEpt; ++b)
+                    if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], key[b] > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
+            } else {
+#pragma unroll
+                for (int b = 0; b < kEpt; ++b) if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_NOMINATED);
             }
         }
-        if (defi) add |= 1ull << 32;
-        if (critr) add |= 1ull << 48;
-        if (add) atomicAdd(&P.acc[g], add);
-    });
-}
-
-__device__ void row_greedy(const Params& P, const Row& R, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
-    if (R.is_kf) { zero_tab(tab); zero_keytab(keytab); __syncthreads(); }
-    int cov, nfree;
-    count_sweep(R, P, tab, S, cov, nfree,
-                [](uint8_t s) -> unsigned { return s == ST_IN ? (1u << 10) : (s == ST_FREE ? 1u : 0u); });
-    if (nfree == 0) return;
-    const int d = max(0, R.need - cov);
-    const unsigned vb = (unsigned)R.var_base;
-    if (R.is_kf) {
-        for_each_entry(R, [&](int g, int cell) {
-            if (P.st[g] != ST_FREE) return;
-            if (tab_in(tab[cell]) != 0) return;
-            atomicMax(&keytab[cell], make_key(P.gain[g], (unsigned)g - vb));
-        });
+    } else {
+        for (int c = threadIdx.x; c < kCells; c += kThreads) keytab[c] = 0ull;
         __syncthreads();
-        for_each_entry(R, [&](int g, int cell) {
-            if (P.st[g] != ST_FREE) return;
-            if (tab_in(tab[cell]) != 0) return;
-            if (make_key(P.gain[g], (unsigned)g - vb) != keytab[cell]) atomicOr(&P.acc[g], FLAG_BLOCKED);
-        });
-    }
-    if (d > 0) {
-        if (nfree > d) {
-            const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
-                for_each_entry(R, [&](int g, int) {
-                    if (P.st[g] == ST_FREE) sink(make_key(P.gain[g], (unsigned)g - vb));
+        int nfree = 0;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const uint32_t e = src[i];
+            const unsigned v = e >> kCellBits;
+            if (st_w[v] != ST_FREE) continue;
+            ++nfree;
+            if ((e & kCellCov) != kCellCov) atomicMax(&keytab[e & kCellCov], make_key(gain_w[v], v));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const uint32_t e = src[i];
+            const unsigned v = e >> kCellBits;
+            if (st_w[v] != ST_FREE || (e & kCellCov) == kCellCov) continue;
+            if (keytab[e & kCellCov] != make_key(gain_w[v], v)) atomicOr(&acc_w[v], FLAG_BLOCKED);
+        }
+        if (d > 0) {
+            int z0 = 0, z1 = 0;
+            block_sum3(S, nfree, z0, z1);
+            if (nfree > d) {
+                const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
+                    for (int i = threadIdx.x; i < n; i += kThreads) {
+                        const unsigned v = src[i] >> kCellBits;
+                        if (st_w[v] == ST_FREE) sink(make_key(gain_w[v], v));
+                    }
                 });
-            });
-            for_each_entry(R, [&](int g, int) {
-                if (P.st[g] != ST_FREE) return;
-                const bool adm = make_key(P.gain[g], (unsigned)g - vb) > thr;
-                atomicOr(&P.acc[g], adm ? FLAG_NOMINATED : FLAG_BLOCKED);
-            });
-        } else {
-            for_each_entry(R, [&](int g, int) {
-                if (P.st[g] == ST_FREE) atomicOr(&P.acc[g], FLAG_NOMINATED);
-            });
+                for (int i = threadIdx.x; i < n; i += kThreads) {
+                    const unsigned v = src[i] >> kCellBits;
+                    if (st_w[v] != ST_FREE) continue;
+                    atomicOr(&acc_w[v], make_key(gain_w[v], v) > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
+                }
+            } else {
+                for (int i = threadIdx.x; i < n; i += kThreads) {
+                    const unsigned v = src[i] >> kCellBits;
+                    if (st_w[v] == ST_FREE) atomicOr(&acc_w[v], FLAG_NOMINATED);
+                }
+            }
         }
     }
 }
 
-__device__ void row_d1(const Params& P, const Row& R, unsigned* tab, BlockScratch& S) {
-    if (R.is_kf) { zero_tab(tab); __syncthreads(); }
-    int cov, unused;
-    count_sweep(R, P, tab, S, cov, unused, [](uint8_t s) -> unsigned { return s == ST_IN ? (1u << 10) : 0u; });
-    if (cov == 0) return;
-    const bool critr = cov <= R.need;
-    for_each_entry(R, [&](int g, int cell) {
-        if (P.st[g] != ST_IN) return;
-        unsigned long long add = 0;
-        if (cell >= 0 && tab_in(tab[cell]) == 1) add |= 1ull;
-        if (critr) add |= 1ull << 32;
-        if (add) atomicAdd(&P.acc[g], add);
-    });
-}
-
-__device__ void row_d2(const Params& P, const Row& R, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
-    if (R.is_kf) { zero_tab(tab); zero_keytab(keytab); __syncthreads(); }
-    int cov, ncand;
-    count_sweep(R, P, tab, S, cov, ncand, [](uint8_t s) -> unsigned {
-        return s == ST_IN ? (1u << 10) : (s == ST_CAND ? ((1u << 10) | 1u) : 0u);
-    });
-    if (ncand == 0) return;
-    const unsigned vb = (unsigned)R.var_base;
-    if (R.is_kf) {
-        for_each_entry(R, [&](int g, int cell) {
-            if (P.st[g] != ST_CAND) return;
-            if (tab_in(tab[cell]) < 2) return;
-            atomicMax(&keytab[cell], make_key(P.gain[g], (unsigned)g - vb));
-        });
+// D1 (and EVAL): one sweep of the row's CSR segment: IN counts per cell and per row; D1 adds the criticality counters
+// of the IN points; both write the row's coverage / slack and the uncovered-cell count (the read-out uses the values of
+// the last sweep, which is the one that found nothing left to drop).
+__device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int R, bool accumulate, unsigned* tab, BlockScratch& S) {
+    const int n = P.ent_n[R];
+    const uint32_t* src = P.ent + P.row_off[R];
+    const uint8_t* st_w = P.st + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int need = P.row_need[R];
+    int cin = 0, ccells = 0, z = 0;
+    if (n > 0 && n <= kRegRow) {
+        RowRegs X;
+        load_row(X, src, n, st_w);
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b)
+            if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
         __syncthreads();
-        for_each_entry(R, [&](int g, int cell) {
-            if (P.st[g] != ST_CAND) return;
-            if (tab_in(tab[cell]) < 2) return;
-            if (make_key(P.gain[g], (unsigned)g - vb) != keytab[cell]) atomicOr(&P.acc[g], FLAG_BLOCKED);
-        });
-    }
-    const int u = cov - R.need;
-    if (u > 0 && ncand > u) {
-        const unsigned long long thr = block_kth_largest(S, u, [&](auto sink) {
-            for_each_entry(R, [&](int g, int) {
-                if (P.st[g] == ST_CAND) sink(make_key(P.gain[g], (unsigned)g - vb));
-            });
-        });
-        for_each_entry(R, [&](int g, int) {
-            if (P.st[g] != ST_CAND) return;
-            if (!(make_key(P.gain[g], (unsigned)g - vb) > thr)) atomicOr(&P.acc[g], FLAG_BLOCKED);
-        });
-    }
-}
-
-__device__ void row_eval(const Params& P, const Row& R, int r, int w, const WinDesc& D, unsigned* tab, BlockScratch& S) {
-    if (R.is_kf) { zero_tab(tab); __syncthreads(); }
-    int cov, unused;
-    count_sweep(R, P, tab, S, cov, unused,
-                [](uint8_t s) -> unsigned { return (1u << 20) | (s == ST_IN ? (1u << 10) : 0u); });
-    int unc = 0, z0 = 0, z1 = 0;
-    if (R.is_kf) {
-        for (int c = threadIdx.x; c < kCells; c += kThreads) {
-            const unsigned t = tab[c];
-            if (tab_total(t) > 0 && tab_in(t) == 0) ++unc;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
+            ++cin;
+            const unsigned cell = X.e[b] & kCellCov;
+            if (cell != kCellCov && atomicAdd(&tab[cell], 1u) == 0u) ++ccells;
         }
-        block_sum3(S, unc, z0, z1);
+        block_sum3(S, cin, ccells, z);
+        if (accumulate && cin > 0) {
+            const bool critr = cin <= need;
+#pragma unroll
+            for (int b = 0; b < kEpt; ++b) {
+                if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
+                const unsigned cell = X.e[b] & kCellCov;
+                unsigned long long add = 0;
+                if (cell != kCellCov && tab[cell] == 1u) add |= 1ull;
+                if (critr) add |= 1ull << 32;
+                if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
+            }
+        }
+    } else if (n > 0) {
+        zero_tab(tab);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const uint32_t e = src[i];
+            if (st_w[e >> kCellBits] != ST_IN) continue;
+            ++cin;
+            const unsigned cell = e & kCellCov;
+            if (cell != kCellCov && atomicAdd(&tab[cell], 1u) == 0u) ++ccells;
+        }
+        block_sum3(S, cin, ccells, z);
+        if (accumulate && cin > 0) {
+            const bool critr = cin <= need;
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const uint32_t e = src[i];
+                if (st_w[e >> kCellBits] != ST_IN) continue;
+                const unsigned cell = e & kCellCov;
+                unsigned long long add = 0;
+                if (cell != kCellCov && tab[cell] == 1u) add |= 1ull;
+                if (critr) add |= 1ull << 32;
+                if (add) atomicAdd(&acc_w[e >> kCellBits], add);
+            }
+        }
     }
     if (threadIdx.x == 0) {
-        const int slack = max(0, R.need - cov);
-        const int local = (r < P.Ktot) ? (r - D.row_base) : (D.K + (r - P.Ktot - D.orow_base));
+        const int slack = max(0, need - cin);
+        const int local = R - D.row_base;
         const int words = (D.M + 31) >> 5;
         uint32_t* slot = P.out + D.out_off + kHdrWords + words;
-        slot[local] = (uint32_t)cov;
+        slot[local] = (uint32_t)cin;
         slot[D.K + D.H + local] = (uint32_t)slack;
-        if (unc) atomicAdd(&P.ws[w].uncovered, unc);
-        if (slack) atomicAdd(&P.ws[w].total_slack, slack);
+        const int unc = P.row_ncell[R] - ccells;
+        if (unc) atomicAdd(&rc.uncovered, (unsigned)unc);
+        if (slack) atomicAdd(&rc.slack, (unsigned)slack);
+    }
+}
+
+// D2: budgets of the reverse delete (per cell: keep at least one IN point; per row: at most cov - need removals)
+__device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
+    const int n = P.ent_n[R];
+    if (n == 0) return;
+    const uint32_t* src = P.ent + P.row_off[R];
+    const uint8_t* st_w = P.st + D.var_base;
+    const float* gain_w = P.gain + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int need = P.row_need[R];
+    zero_tab(tab);
+    for (int c = threadIdx.x; c < kCells; c += kThreads) keytab[c] = 0ull;
+    __syncthreads();
+    int cov = 0, ncand = 0, z = 0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const uint32_t e = src[i];
+        const uint8_t s = st_w[e >> kCellBits];
+        if (s != ST_IN && s != ST_CAND) continue;
+        ++cov;
+        if (s == ST_CAND) ++ncand;
+        if ((e & kCellCov) != kCellCov) atomicAdd(&tab[e & kCellCov], 1u);
+    }
+    block_sum3(S, cov, ncand, z);
+    if (ncand == 0) return;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const uint32_t e = src[i];
+        const unsigned v = e >> kCellBits, cell = e & kCellCov;
+        if (st_w[v] != ST_CAND || cell == kCellCov || tab[cell] < 2u) continue;
+        atomicMax(&keytab[cell], make_key(gain_w[v], v));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const uint32_t e = src[i];
+        const unsigned v = e >> kCellBits, cell = e & kCellCov;
+        if (st_w[v] != ST_CAND || cell == kCellCov || tab[cell] < 2u) continue;
+        if (make_key(gain_w[v], v) != keytab[cell]) atomicOr(&acc_w[v], FLAG_BLOCKED);
+    }
+    const int u = cov - need;
+    if (u > 0 && ncand > u) {
+        const unsigned long long thr = block_kth_largest(S, u, [&](auto sink) {
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const unsigned v = src[i] >> kCellBits;
+                if (st_w[v] == ST_CAND) sink(make_key(gain_w[v], v));
+            }
+        });
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const unsigned v = src[i] >> kCellBits;
+            if (st_w[v] != ST_CAND) continue;
+            if (!(make_key(gain_w[v], v) > thr)) atomicOr(&acc_w[v], FLAG_BLOCKED);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // variable phases (one thread per map point of a 256-wide tile)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void var_phase(const Params& P, int tile, BlockScratch& S) {
-    const int w = P.tile_win[tile];
-    WinState& ws = P.ws[w];
-    const int mode = ws.mode;
-    if (mode == MODE_DONE) return;
-    const WinDesc D = P.win[w];
-    const int g = tile * kVarTile + (int)threadIdx.x;
-    const int mp = g - D.var_base;
+__device__ void var_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int greedy_steps, int tile,
+                          BlockScratch& S) {
+    const int mp = tile * kVarTile + (int)threadIdx.x;
+    const int g = D.var_base + mp;
     const bool inb = mp < D.M;
     const uint8_t s = inb ? P.st[g] : (uint8_t)ST_NOTVAR;
     int c0 = 0, c1 = 0, c2 = 0;
@@ -558,27 +861,23 @@ __device__ void var_phase(const Params& P, int tile, BlockScratch& S) {
     case MODE_PROP: {
         if (s == ST_FREE) {
             const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0;
-            const double ubc = (double)(a & 0xFFFFu), lbc = (double)((a >> 16) & 0xFFFFu);
-            const double ubr = (double)((a >> 32) & 0xFFFFu), lbr = (double)(a >> 48);
-            const double cost = (double)(ws.n_max - __ldg(D.mp_nobs + mp));
-            const double ub = __dsub_rn(__dadd_rn(__dmul_rn(P.glam, ubc), __dmul_rn(P.lam, ubr)), cost);
-            const double lb = __dsub_rn(__dadd_rn(__dmul_rn(P.glam, lbc), __dmul_rn(P.lam, lbr)), cost);
-            if (ub <= 0.0) { P.st[g] = ST_OUT; c0 = 1; }
-            else if (lb >= 0.0) { P.st[g] = ST_IN; c0 = 1; }
-            else { P.gain[g] = (float)ub; c1 = 1; }
+            if (a) P.acc[g] = 0ull;
+            prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], P.deg[g], c0, c1, c2);
         }
-        block_sum3(S, c0, c1, c2);
-        if (threadIdx.x == 0) {
-            if (c0) atomicAdd(&ws.changed, (unsigned)c0);
-            if (c1) atomicAdd(&ws.nfree, (unsigned)c1);
+        if (__syncthreads_or(s == ST_FREE)) {
+            block_sum3(S, c0, c1, c2);
+            if (threadIdx.x == 0) {
+                if (c0) atomicAdd(&rc.changed, (unsigned)c0);
+                if (c1) atomicAdd(&rc.nfree, (unsigned)c1);
+                if (c2) atomicAdd(&rc.sumdeg, (unsigned)c2);
+            }
         }
     } break;
     case MODE_GREEDY: {
         if (s == ST_FREE) {
             const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0;
-            const bool any_rule = ws.greedy_steps >= P.all_rule_steps;
+            if (a) P.acc[g] = 0ull;
+            const bool any_rule = greedy_steps >= P.all_rule_steps;
             const bool sel = (P.gain[g] > 0.0f && !(a & FLAG_BLOCKED)) || (any_rule && (a & FLAG_NOMINATED));
             if (sel) P.st[g] = ST_IN;
         }
@@ -589,23 +888,26 @@ __device__ void var_phase(const Params& P, int tile, BlockScratch& S) {
     case MODE_D1: {
         if (s == ST_IN) {
             const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0;
+            if (a) P.acc[g] = 0ull;
             const double critc = (double)(a & 0xFFFFu), critr = (double)((a >> 32) & 0xFFFFu);
             const double cost = (double)(ws.n_max - __ldg(D.mp_nobs + mp));
             const double dF = __dadd_rn(__dadd_rn(-cost, __dmul_rn(P.glam, critc)), __dmul_rn(P.lam, critr));
             if (dF < 0.0) { P.st[g] = ST_CAND; P.gain[g] = (float)(-dF); c0 = 1; }
         }
-        block_sum3(S, c0, c1, c2);
-        if (threadIdx.x == 0 && c0) atomicAdd(&ws.ncand, (unsigned)c0);
+        if (__syncthreads_or(c0)) {
+            block_sum3(S, c0, c1, c2);
+            if (threadIdx.x == 0 && c0) atomicAdd(&rc.ncand, (unsigned)c0);
+        }
     } break;
     case MODE_D2: {
         if (s == ST_CAND) {
             const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0;
+            if (a) P.acc[g] = 0ull;
             P.st[g] = (a & FLAG_BLOCKED) ? ST_IN : ST_OUT;
         }
     } break;
-    case MODE_EVAL: {
+    case MODE_EVAL:
+    case MODE_EVALV: {
         // read-out (MapSparsification.cc:159-166): bit = 0 only for variables the solve rejected
         const bool keep = inb && (s != ST_OUT);
         const unsigned word = __ballot_sync(0xFFFFFFFFu, keep);
@@ -616,160 +918,157 @@ __device__ void var_phase(const Params& P, int tile, BlockScratch& S) {
         int cost = kept ? (ws.n_max - __ldg(D.mp_nobs + mp)) : 0;    // < 2^31 per block: 256 * nMax
         block_sum3(S, kept, cost, c2);
         if (threadIdx.x == 0 && kept) {
-            atomicAdd(&ws.n_kept, kept);
-            atomicAdd(&ws.sum_cost, (unsigned long long)cost);
+            atomicAdd(&rc.nkept, (unsigned)kept);
+            atomicAdd(&rc.sumcost, (unsigned long long)cost);
         }
     } break;
     default: break;
     }
 }
 
-// per-window phase machine; run by the last CTA to finish the variable phase of an iteration
-__device__ void transition(const Params& P, int w) {
-    WinState& s = P.ws[w];
-    const WinDesc& D = P.win[w];
-    const int drop_mode = (P.max_drop_rounds > 0) ? MODE_D1 : MODE_EVAL;
-    switch (s.mode) {
-    case MODE_PROP: {
-        s.rounds++;
-        const unsigned changed = s.changed, nfree = s.nfree;
-        s.changed = 0; s.nfree = 0;
-        if (changed > 0 && s.rounds < P.max_rounds) s.mode = MODE_PROP;
-        else if (nfree == 0) s.mode = drop_mode;
-        else if (s.rounds >= P.max_rounds) { s.mode = MODE_FORCE; s.status = -5; }
-        else s.mode = MODE_GREEDY;
-    } break;
-    case MODE_GREEDY: s.greedy_steps++; s.rounds++; s.mode = MODE_PROP; break;
-    case MODE_FORCE: s.mode = drop_mode; break;
-    case MODE_D1: {
-        s.rounds++;
-        const unsigned nc = s.ncand;
-        s.ncand = 0;
-        s.mode = (nc == 0) ? MODE_EVAL : MODE_D2;
-    } break;
-    case MODE_D2: s.drop_rounds++; s.mode = (s.drop_rounds >= P.max_drop_rounds) ? MODE_EVAL : MODE_D1; break;
-    case MODE_EVAL: {
-        uint32_t* hdr = P.out + D.out_off;
-        hdr[0] = (uint32_t)s.status;
-        hdr[1] = (uint32_t)s.rounds;
-        hdr[2] = (uint32_t)s.n_max;
-        hdr[3] = (uint32_t)s.n_vars;
-        hdr[4] = (uint32_t)s.n_cells;
-        hdr[5] = (uint32_t)s.nnz;
-        hdr[6] = (uint32_t)s.n_kept;
-        hdr[7] = (uint32_t)s.uncovered;
-        hdr[8] = (uint32_t)s.total_slack;
-        hdr[9] = (uint32_t)(s.sum_cost & 0xFFFFFFFFull);
-        hdr[10] = (uint32_t)(s.sum_cost >> 32);
-        hdr[11] = s.error;
-        hdr[12] = (uint32_t)s.greedy_steps;
-        hdr[13] = (uint32_t)s.drop_rounds;
-        hdr[14] = 0x4D535331u;      // "MSS1": slot written
-        hdr[15] = (uint32_t)w;
-        s.mode = MODE_DONE;
-    } break;
-    default: break;
+// ---------------------------------------------------------------------------------------------------------------
+// one window, solved by the CTAs of one group
+// ---------------------------------------------------------------------------------------------------------------
+__device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
+    const WinDesc D = P.win[w];
+    WinState& ws = P.ws[w];
+    const int rows = D.K + D.H;
+    const int tiles = (D.M + kVarTile - 1) / kVarTile;
+    const int gt = G.cta * kThreads + (int)threadIdx.x, gsz = G.ncta * kThreads;
+
+    // ---- W0: state init ------------------------------------------------------------------------------------------
+    {
+        const int mpad = ((max(D.M, 1) + kVarTile - 1) / kVarTile) * kVarTile;
+        uint32_t* st32 = reinterpret_cast<uint32_t*>(P.st + D.var_base);
+        for (int i = gt; i < mpad / 4; i += gsz) st32[i] = 0x03030303u;            // ST_NOTVAR
+        for (int i = gt; i < mpad; i += gsz) P.acc[D.var_base + i] = 0ull;
+        for (int j = gt; j < D.H; j += gsz) P.ent_n[D.row_base + D.K + j] = 0;
+        if (G.cta == 0) {
+            uint32_t* z = reinterpret_cast<uint32_t*>(&ws);
+            for (int i = threadIdx.x; i < (int)(sizeof(WinState) / 4); i += kThreads) z[i] = 0u;
+            if (threadIdx.x == 0) P.out[D.out_off + 14] = 0u;                          // "slot not written"
+        }
     }
+    if (!group_sync(P, G)) return false;
+    // ---- W1: keyframe rows ---------------------------------------------------------------------------------------
+    for (int k = G.cta; k < D.K; k += G.ncta) {
+        w1_build_row(P, D, ws, k, tab, reinterpret_cast<unsigned*>(keytab), S);
+        __syncthreads();
+    }
+    if (!group_sync(P, G)) return false;
+    // ---- W2..W4: outside rows + round 1 ----------------------------------------------------------------------------
+    for (int t = G.cta; t < tiles; t += G.ncta) w2_count_outside(P, D, ws, t, S);
+    if (!group_sync(P, G)) return false;
+    if (G.cta == 0) w3_scan_outside(P, D, S);
+    if (!group_sync(P, G)) return false;
+    if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
+    for (int t = G.cta; t < tiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, S);
+    if (!group_sync(P, G)) return false;
+    if (w == P.gwin[P.grp[0].wbeg] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();
+
+    // ---- phase machine (every CTA of the group takes the same decisions from the same counters) ----------------------
+    const int drop_mode = (P.max_drop_rounds > 0) ? MODE_D1 : MODE_EVAL;
+    int rounds = 1, greedy_steps = 0, drop_rounds = 0, status = 0;
+    int seq = 0, mode;
+    bool from_csr = true;
+    unsigned unc_final = 0, slack_final = 0;
+    auto after_prop = [&](unsigned changed, unsigned nfree) {
+        if (changed > 0 && rounds < P.max_rounds) return (int)MODE_PROP;
+        if (nfree == 0) return drop_mode;
+        if (rounds >= P.max_rounds) { status = -5; return (int)MODE_FORCE; }
+        return (int)MODE_GREEDY;
+    };
+    mode = after_prop(ws.rc[0].changed, ws.rc[0].nfree);
+    while (mode != MODE_DONE) {
+        ++seq;
+        RoundCnt& rc = ws.rc[seq % 3];
+        if (G.cta == 0 && threadIdx.x < (int)(sizeof(RoundCnt) / 4))
+            reinterpret_cast<uint32_t*>(&ws.rc[(seq + 1) % 3])[threadIdx.x] = 0u;     // used by phase seq + 1
+        // row phase
+        if (mode != MODE_FORCE && mode != MODE_EVALV) {
+            for (int r = G.cta; r < rows; r += G.ncta) {
+                const int R = D.row_base + r;
+                switch (mode) {
+                case MODE_PROP: row_prop(P, D, rc, R, from_csr, tab, S); break;
+                case MODE_GREEDY: row_greedy(P, D, R, keytab, S); break;
+                case MODE_D1: row_d1_eval(P, D, rc, R, true, tab, S); break;
+                case MODE_D2: row_d2(P, D, R, tab, keytab, S); break;
+                case MODE_EVAL: row_d1_eval(P, D, rc, R, false, tab, S); break;
+                default: break;
+                }
+                __syncthreads();
+            }
+            if (!group_sync(P, G)) return false;
+        }
+        if (mode == MODE_PROP) from_csr = false;
+        // variable phase
+        for (int t = G.cta; t < tiles; t += G.ncta) var_phase(P, D, ws, rc, mode, greedy_steps, t, S);
+        if (!group_sync(P, G)) return false;
+        // transition
+        switch (mode) {
+        case MODE_PROP: ++rounds; mode = after_prop(rc.changed, rc.nfree); break;
+        case MODE_GREEDY: ++greedy_steps; ++rounds; mode = MODE_PROP; break;
+        case MODE_FORCE: mode = drop_mode; break;
+        case MODE_D1:
+            ++rounds;
+            if (rc.ncand == 0) { unc_final = rc.uncovered; slack_final = rc.slack; mode = MODE_EVALV; }
+            else mode = MODE_D2;
+            break;
+        case MODE_D2: ++drop_rounds; mode = (drop_rounds >= P.max_drop_rounds) ? MODE_EVAL : MODE_D1; break;
+        case MODE_EVAL: unc_final = rc.uncovered; slack_final = rc.slack;      // fallthrough
+        case MODE_EVALV: {
+            if (G.cta == 0 && threadIdx.x == 0) {
+                uint32_t* hdr = P.out + D.out_off;
+                hdr[0] = (uint32_t)status;
+                hdr[1] = (uint32_t)rounds;
+                hdr[2] = (uint32_t)ws.n_max;
+                hdr[3] = (uint32_t)ws.n_vars;
+                hdr[4] = (uint32_t)ws.n_cells;
+                hdr[5] = (uint32_t)ws.nnz;
+                hdr[6] = rc.nkept;
+                hdr[7] = unc_final;
+                hdr[8] = slack_final;
+                hdr[9] = (uint32_t)(rc.sumcost & 0xFFFFFFFFull);
+                hdr[10] = (uint32_t)(rc.sumcost >> 32);
+                hdr[11] = ws.error;
+                hdr[12] = (uint32_t)greedy_steps;
+                hdr[13] = (uint32_t)drop_rounds;
+                hdr[14] = 0x4D535331u;      // "MSS1": slot written
+                hdr[15] = (uint32_t)w;
+            }
+            mode = MODE_DONE;
+        } break;
+        default: mode = MODE_DONE; break;
+        }
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the persistent cooperative kernel
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) mss_persistent_kernel(const Params P) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ unsigned tab[kCells];
     __shared__ unsigned long long keytab[kCells];
     __shared__ BlockScratch S;
-    __shared__ int s_last;
+    __shared__ int s_abort;
 
-    const int gtid = blockIdx.x * kThreads + threadIdx.x;
-    const int gsize = gridDim.x * kThreads;
-
-    // ---- P0: state init --------------------------------------------------------------------------------------
-    if (gtid == 0) { P.ctrl->t_start = globaltimer_ns(); P.ctrl->ticket = 0u; P.ctrl->n_active = 0; P.ctrl->iters = 0; }
-    {
-        uint32_t* st32 = reinterpret_cast<uint32_t*>(P.st);
-        for (int i = gtid; i < P.Mpad / 4; i += gsize) st32[i] = 0x03030303u;       // ST_NOTVAR
-        for (int i = gtid; i < P.Mpad; i += gsize) P.acc[i] = 0ull;
-        for (int i = gtid; i < P.Htot; i += gsize) P.ocnt[i] = 0;
-        for (int w = gtid; w < P.nwin; w += gsize) {
-            WinState z;
-            memset(&z, 0, sizeof(z));
-            z.mode = P.win[w].owned ? MODE_PROP : MODE_DONE;
-            P.ws[w] = z;
-            if (P.win[w].owned) {
-                // header "not written" marker until EVAL completes
-                P.out[P.win[w].out_off + 14] = 0u;
-            }
-        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->t_start = globaltimer_ns();
+    const int gi = P.cta_grp[blockIdx.x];
+    const GroupDesc gd = P.grp[gi];
+    GroupCtx G;
+    G.bar = P.gbar + (size_t)gi * 32;
+    G.gen = 0u;
+    G.ncta = gd.ncta;
+    G.cta = (int)blockIdx.x - gd.cta0;
+    G.s_abort = &s_abort;
+    G.t0 = globaltimer_ns();
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
+    for (int wi = gd.wbeg; wi < gd.wend; ++wi) {
+        if (!solve_window(P, G, P.gwin[wi], tab, keytab, S)) break;
     }
-    grid.sync();
-    // ---- P1: keyframe rows: nMax, variable marking, cell statistics -------------------------------------------------
-    for (int r = blockIdx.x; r < P.Ktot; r += gridDim.x) {
-        if (!P.win[P.row_win[r]].owned) continue;
-        p1_scan_row(P, r, tab, S);
-        __syncthreads();
-    }
-    grid.sync();
-    // ---- P2..P4: outside rows ----------------------------------------------------------------------------------
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) p24_outside<false>(P, t, S);
-    grid.sync();
-    if (blockIdx.x == 0) p3_scan(P, S);
-    grid.sync();
-    if (P.Htot > 0) {
-        for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) p24_outside<true>(P, t, S);
-        grid.sync();
-    }
-    if (gtid == 0) P.ctrl->t_build = globaltimer_ns();
-
-    // ---- phase machine -----------------------------------------------------------------------------------------
-    unsigned iter = 0;
-    while (true) {
-        const int n_active = *((volatile int*)&P.ctrl->n_active);
-        if (n_active == 0) break;
-        for (int r = blockIdx.x; r < P.Rtot; r += gridDim.x) {
-            const int w = P.row_win[r];
-            const int mode = P.ws[w].mode;
-            if (mode == MODE_DONE || mode == MODE_FORCE) continue;
-            const WinDesc D = P.win[w];
-            const Row R = make_row(P, r, D);
-            switch (mode) {
-            case MODE_PROP: row_prop(P, R, tab, S); break;
-            case MODE_GREEDY: row_greedy(P, R, tab, keytab, S); break;
-            case MODE_D1: row_d1(P, R, tab, S); break;
-            case MODE_D2: row_d2(P, R, tab, keytab, S); break;
-            case MODE_EVAL: row_eval(P, R, r, w, D, tab, S); break;
-            default: break;
-            }
-            __syncthreads();
-        }
-        grid.sync();
-        for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) var_phase(P, t, S);
-        // last CTA to arrive advances every window's phase machine
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(&P.ctrl->ticket, 1u);
-            s_last = (ticket == (iter + 1u) * gridDim.x - 1u) ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            int nact = 0, z0 = 0, z1 = 0;
-            for (int w = threadIdx.x; w < P.nwin; w += kThreads) {
-                if (P.ws[w].mode != MODE_DONE) {
-                    transition(P, w);
-                    if (P.ws[w].mode != MODE_DONE) ++nact;
-                }
-            }
-            block_sum3(S, nact, z0, z1);
-            if (threadIdx.x == 0) { P.ctrl->n_active = nact; P.ctrl->iters = (int)iter + 1; }
-            __threadfence();
-        }
-        ++iter;
-        grid.sync();
-    }
-    if (gtid == 0) P.ctrl->t_end = globaltimer_ns();
+    if (G.cta == 0 && threadIdx.x == 0) atomicMax(&P.ctrl->t_end, globaltimer_ns());
 }
 
 }  // namespace mss
