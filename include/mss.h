@@ -150,6 +150,12 @@ int   mss_get_stats(const mss_handle* h, mss_stats* out);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
 void* mss_stream(mss_handle* h);
 
+/* Debug: per-phase device timeline of the windows solved on this rank by the next calls.  mss_debug_get_trace copies up
+ * to cap_pairs (phase << 24 | FREE points left, ns since the window started) pairs of local window i of the last call
+ * and returns how many.  Not part of the reference-facing surface. */
+int   mss_debug_trace(mss_handle* h, int32_t enable);
+int   mss_debug_get_trace(const mss_handle* h, int32_t local_window, uint32_t* out_pairs, int32_t cap_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,12 @@ struct mss_handle {
     DevBuf<unsigned long long> acc;
     DevBuf<float> gain;
     DevBuf<unsigned> deg;
+    DevBuf<uint8_t> seen;
+    DevBuf<int> vlist;               // [2][Mpad] FREE lists
+    DevBuf<uint2> trace;             // [nwin][kTraceCap], only when tracing is on
+    bool trace_on = false;
+    std::vector<uint2> h_trace;
+    int h_trace_nwin = 0;
     DevBuf<uint32_t> ent, live;      // CSR entries / live lists (keyframe-row segments, then outside-row segments)
     DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
     DevBuf<uint32_t> out;
@@ -95,6 +101,7 @@ struct mss_handle {
     NcclComm comm = nullptr;
     int rank = 0, nranks = 1;
     unsigned long long watchdog_ns = 20000000000ull;
+    int tail_vars = 64, tail_ents = 256;
     // stats
     mss_stats stats{};
     int64_t device_bytes = 0;
@@ -273,6 +280,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if ((rc = ensure(h, h->acc, (size_t)Mpad + 16))) return rc;
     if ((rc = ensure(h, h->gain, (size_t)Mpad + 16))) return rc;
     if ((rc = ensure(h, h->deg, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->seen, (size_t)Mpad + 16))) return rc;
+    if ((rc = ensure(h, h->vlist, (size_t)2 * Mpad + 16))) return rc;
+    if (h->trace_on && (rc = ensure(h, h->trace, (size_t)std::max(nl, 1) * mss::kTraceCap))) return rc;
     if ((rc = ensure(h, h->ent, (size_t)(Ftot + Otot) + 16))) return rc;
     if ((rc = ensure(h, h->live, (size_t)(Ftot + Otot) + 16))) return rc;
     if ((rc = ensure(h, h->rows, (size_t)7 * ((size_t)Rtot + 16)))) return rc;
@@ -344,7 +354,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     P.cta_grp = reinterpret_cast<const int*>(h->meta.p + off_cta);
     P.gwin = reinterpret_cast<const int*>(h->meta.p + off_gwin);
     P.gbar = h->sync.p + 32;
-    P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.deg = h->deg.p;
+    P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.deg = h->deg.p; P.seen = h->seen.p;
+    P.vlist = h->vlist.p; P.Mpad = (int)Mpad;
+    P.trace = h->trace_on ? h->trace.p : nullptr;
     P.ent = h->ent.p; P.live = h->live.p;
     {
         const size_t rs = (size_t)Rtot + 16;
@@ -357,13 +369,15 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     P.max_rounds = h->cfg.max_rounds; P.all_rule_steps = h->cfg.all_rule_steps; P.max_drop_rounds = h->cfg.max_drop_rounds;
     P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
     P.watchdog_ns = h->watchdog_ns;
+    P.tail_vars = std::min(h->tail_vars, mss::kTailVars); P.tail_ents = std::min(h->tail_ents, mss::kTailEnts);
 
     float dev_ms = 0.f;
     if (nl > 0) {
         void* args[] = {(void*)&P};
         MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
+        if (h->trace_on) MSS_CUDA(h, cudaMemsetAsync(h->trace.p, 0, (size_t)nl * mss::kTraceCap * sizeof(uint2), h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(grid), dim3(mss::kThreads), args, 0, h->stream));
+        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         h->stats.kernel_launches += 1;
     } else {
@@ -393,6 +407,11 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
     aborted = nl > 0 && h->h_ctrl->abort != 0;
+    if (h->trace_on && nl > 0) {
+        h->h_trace.resize((size_t)nl * mss::kTraceCap);
+        h->h_trace_nwin = nl;
+        MSS_CUDA(h, cudaMemcpy(h->h_trace.data(), h->trace.p, h->h_trace.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+    }
 
     int ret = MSS_OK;
     const double t_build_us = nl > 0 ? (double)(h->h_ctrl->t_build - h->h_ctrl->t_start) * 1e-3 : 0.0;
@@ -486,12 +505,16 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!coop) { fprintf(stderr, "libmss: device does not support cooperative launch\n"); mss_destroy(h); return MSS_E_CUDA; }
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->max_ctas_per_sm, mss::mss_persistent_kernel, mss::kThreads, 0)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute((const void*)mss::mss_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mss::kSmemBytes)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(max dynamic shared memory) (was libmss built for this GPU? it ships sm_100a code only)", e);
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->max_ctas_per_sm, mss::mss_persistent_kernel, mss::kThreads, mss::kSmemBytes)) != cudaSuccess)
         return fail("occupancy query (was libmss built for this GPU? it ships sm_100a code only)", e);
     if (h->max_ctas_per_sm <= 0) { fprintf(stderr, "libmss: kernel does not fit on an SM\n"); mss_destroy(h); return MSS_E_CUDA; }
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if (const char* tv = getenv("MSS_TAIL_VARS")) h->tail_vars = atoi(tv);
+    if (const char* te = getenv("MSS_TAIL_ENTS")) h->tail_ents = atoi(te);
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
     if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     h->stats.sm_count = h->sm_count;
@@ -504,7 +527,7 @@ void mss_destroy(mss_handle* h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->deg);
-    release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync);
+    release(h->seen); release(h->vlist); release(h->trace); release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -602,5 +625,19 @@ int mss_get_stats(const mss_handle* h, mss_stats* out) {
 }
 
 void* mss_stream(mss_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mss_debug_trace(mss_handle* h, int32_t enable) {
+    if (!h) return MSS_E_BADARG;
+    h->trace_on = enable != 0;
+    return MSS_OK;
+}
+
+int mss_debug_get_trace(const mss_handle* h, int32_t local_window, uint32_t* out_pairs, int32_t cap_pairs) {
+    if (!h || !out_pairs || local_window < 0 || local_window >= h->h_trace_nwin) return MSS_E_BADARG;
+    const uint2* t = h->h_trace.data() + (size_t)local_window * mss::kTraceCap;
+    const int n = std::min((int)t[mss::kTraceCap - 1].x, std::min((int)cap_pairs, mss::kTraceCap - 1));
+    for (int i = 0; i < n; ++i) { out_pairs[2 * i] = t[i].x; out_pairs[2 * i + 1] = t[i].y; }
+    return n;
+}
 
 }  // extern "C"

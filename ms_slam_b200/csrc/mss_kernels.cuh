@@ -46,6 +46,13 @@ constexpr unsigned kEntInvalid = 0xFFFFFFFFu;
 constexpr unsigned kTabCov = 0x80000000u;   // cell table: bit 31 = cell has an IN point, low 16 bits = FREE count
 constexpr int kEpt = 8;                     // entries per thread held in registers (rows up to 2048 entries)
 constexpr int kRegRow = kThreads * kEpt;
+constexpr int kWarpRow = 32;                // lists up to this long are handled by one warp
+constexpr int kTraceCap = 256;
+// shared-memory tail solver: capacity of the residual problem one CTA finishes on its own
+constexpr int kTailEnts = 2048;
+constexpr int kTailVars = 512;
+constexpr int kTailRows = 512;
+constexpr int kTailRowMax = 256;            // longest keyframe-row list the tail accepts (cell matching is O(n^2 / 32))
 
 enum : uint8_t { ST_FREE = 0, ST_IN = 1, ST_OUT = 2, ST_NOTVAR = 3, ST_CAND = 4 };
 enum : int { MODE_DONE = 0, MODE_PROP = 1, MODE_GREEDY = 2, MODE_FORCE = 3, MODE_D1 = 4, MODE_D2 = 5, MODE_EVAL = 6,
@@ -75,13 +82,14 @@ struct RoundCnt {
     unsigned changed, nfree, sumdeg, ncand;
     unsigned uncovered, slack, nkept, rows_live;
     unsigned long long sumcost;
-    unsigned long long pad_;
+    unsigned maxlive;        // longest live list with cells written by this PROP row phase
+    unsigned pad_;
 };
 
 struct WinState {
     int n_max, n_vars, n_cells, nnz;
     unsigned error;
-    int pad_[3];
+    int t_rounds, t_greedy, t_status;      // written by the tail CTA for the rest of the group
     RoundCnt rc[3];
 };
 
@@ -107,6 +115,9 @@ struct Params {
     unsigned long long* acc; // [Mpad] packed 4 x 16-bit counters / flags
     float* gain;             // [Mpad]
     unsigned* deg;           // [Mpad] number of row entries of the variable
+    uint8_t* seen;           // [Mpad] map point sits in a valid slot outside the grid (counts for nMax only)
+    int* vlist;              // [2][Mpad] compact lists of the FREE map points of every window (ping-pong)
+    uint2* trace;            // optional [nwin][kTraceCap] (phase, ns since the window started); nullptr = off
     uint32_t* ent;           // [Ftot + Otot] CSR entries: keyframe rows at slot_base + feat_ptr[k], then outside rows
     uint32_t* live;          // [Ftot + Otot] live lists (same segments)
     int* row_off;            // [Rtot] first entry of the row's segment
@@ -118,12 +129,13 @@ struct Params {
     int* ocursor;            // [Rtot] fill cursor of the outside rows
     uint32_t* out;           // result slots
     Ctrl* ctrl;
-    int nwin, ngroups;
+    int nwin, ngroups, Mpad;
     int Ftot;                // outside-row segments start at ent + Ftot
     int N;
     int max_rounds, all_rule_steps, max_drop_rounds;
     double lam, glam;
     unsigned long long watchdog_ns;
+    int tail_vars, tail_ents;    // residual size handed to the shared-memory tail (<= kTailVars / kTailEnts; 0 = never)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -157,6 +169,12 @@ struct BlockScratch {
     int scan[kWarps];
     int bcast[4];
     unsigned hist[256];
+    // row queue of the current chunk of this CTA's rows: long rows from the front, short rows from the back
+    unsigned short rowq[kThreads];
+    int rown[kThreads];
+    int qn[2];
+    unsigned rows_live, maxlive;
+    int tcnt[4];             // tail: changed, nfree
 };
 
 struct GroupCtx {
@@ -181,6 +199,7 @@ __device__ __forceinline__ bool group_sync(const Params& P, GroupCtx& G) {
             const unsigned target = G.gen * (unsigned)G.ncta;
             unsigned spins = 0;
             while (ld_acquire_u32(G.bar) < target) {
+                if (spins > 64u) __nanosleep(64);
                 if ((++spins & 0xFFu) == 0u) {
                     if (*(volatile int*)&P.ctrl->abort) { ab = 1; break; }
                     if (globaltimer_ns() - G.t0 > P.watchdog_ns) {
@@ -281,15 +300,12 @@ __device__ unsigned long long block_kth_largest(BlockScratch& S, int rank, Emit 
             if ((key & mask) == prefix) atomicAdd(&S.hist[(unsigned)(key >> shift) & 255u], 1u);
         });
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int cum = 0, b = 255;
-            for (; b > 0; --b) {
-                const int h = (int)S.hist[b];
-                if (cum + h > rank) break;
-                cum += h;
-            }
-            S.bcast[0] = b;
-            S.bcast[1] = rank - cum;
+        {
+            // thread t owns bin 255 - t: the exclusive prefix over threads is the number of keys in larger bins
+            const int h = (int)S.hist[255 - (int)threadIdx.x];
+            int total;
+            const int above = block_excl_scan(S, h, total);
+            if (above <= rank && rank < above + h) { S.bcast[0] = 255 - (int)threadIdx.x; S.bcast[1] = rank - above; }
         }
         __syncthreads();
         prefix |= (unsigned long long)S.bcast[0] << shift;
@@ -333,10 +349,12 @@ __device__ __forceinline__ void load_row(RowRegs& X, const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// W1: keyframe row -> nMax, variable marking, cell-sorted CSR segment, round-1 contributions
+// W1: keyframe row -> CSR segment (coalesced, slot order), cell statistics, round-1 contributions.
+// One spread-address memory operation per entry (the 64-bit reduction on the map point's counters); everything else is
+// coalesced or shared memory.  A map point becomes a variable exactly when its counters are non-zero after W1, so W2 can
+// derive the state array with coalesced stores; valid slots outside the grid only leave a "seen" mark for nMax.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, unsigned* tab, unsigned* cursor,
-                             BlockScratch& S) {
+__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, unsigned* tab, BlockScratch& S) {
     const int R = D.row_base + k;
     const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
     if (beg < 0 || end < beg || end > D.F) {
@@ -346,94 +364,214 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
         }
         return;
     }
-    zero_tab(tab);
-    __syncthreads();
-    unsigned err = 0;
-    int nmax = 0, nz = 0;
-    uint8_t* st_w = P.st + D.var_base;
-    for (int i = beg + (int)threadIdx.x; i < end; i += kThreads) {
-        const int mp = __ldg(D.feat_mp + i);
-        if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
-        if (mp >= D.M) { err |= ERR_INDEX; continue; }
-        nmax = max(nmax, __ldg(D.mp_nobs + mp));                 // MapSparsification.cc:69-75: every valid slot
-        const unsigned c = __ldg(D.feat_cell + i);
-        if (c == kCellNone) continue;                           // not in mGrid: not a variable through this slot
-        if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
-        st_w[mp] = ST_FREE;                                     // MapSparsification.cc:91-99 (same value from every writer)
-        atomicAdd(&tab[c], 1u);
-        ++nz;
-    }
-    nmax = block_max(S, nmax);
-    int z0 = 0, z1 = 0;
-    block_sum3(S, nz, z0, z1);                                  // nz = entries of the row; barriers publish tab
-    // exclusive scan of the cell histogram -> scatter cursors (counting sort by cell)
-    int local = 0, ncell = 0;
-    const int c0 = (int)threadIdx.x * kCellsPerThread;
-#pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        const unsigned t = tab[c0 + j];
-        local += (int)t;
-        ncell += t ? 1 : 0;
-        if (t > 0xFFFFu) err |= ERR_CELL_OVERFLOW;
-    }
-    int total;
-    int base = block_excl_scan(S, local, total);
-#pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        cursor[c0 + j] = (unsigned)base;
-        base += (int)tab[c0 + j];
-    }
-    block_sum3(S, ncell, z0, z1);                               // barriers publish cursor
+    const int nslots = end - beg;
     const int seg = D.slot_base + beg;
-    // round 1 (everything FREE, nothing IN): every cell is uncovered, every row with N > 0 is deficient
-    const bool defi = P.N > 0;
-    const bool critr = defi && P.N >= nz;
     uint32_t* ent = P.ent + seg;
     unsigned long long* acc_w = P.acc + D.var_base;
-    for (int i = beg + (int)threadIdx.x; i < end; i += kThreads) {
-        const int mp = __ldg(D.feat_mp + i);
-        if (mp < 0 || mp >= D.M) continue;
-        const unsigned c = __ldg(D.feat_cell + i);
-        if (c >= (unsigned)kCells) continue;
-        const unsigned pos = atomicAdd(&cursor[c], 1u);
-        ent[pos] = ((uint32_t)mp << kCellBits) | c;
-        unsigned long long add = 1ull;
-        if (tab[c] == 1u) add |= 1ull << 16;
-        if (defi) add |= 1ull << 32;
-        if (critr) add |= 1ull << 48;
-        atomicAdd(&acc_w[mp], add);
-    }
-    if (threadIdx.x == 0) {
-        P.ent_n[R] = nz; P.live_n[R] = 0; P.row_need[R] = P.N; P.row_cov[R] = 0; P.row_ncell[R] = ncell; P.row_off[R] = seg;
-        atomicMax(&ws.n_max, nmax);
-        if (nz) atomicAdd(&ws.nnz, nz);
-        if (ncell) atomicAdd(&ws.n_cells, ncell);
+    uint8_t* seen_w = P.seen + D.var_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool defi = P.N > 0;
+    unsigned err = 0;
+    if (nslots <= kRegRow) {
+        // slots in registers: warp w owns a contiguous chunk, lane-strided (coalesced loads, list order = slot order)
+        const int per = (((nslots + kWarps - 1) / kWarps) + 31) & ~31;
+        const int nb = per >> 5;
+        uint32_t e[kEpt];
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            const int idx = wid * per + b * 32 + lane;
+            int mp = -1;
+            unsigned c = kCellNone;
+            if (b < nb && idx < nslots) { mp = __ldg(D.feat_mp + beg + idx); c = __ldg(D.feat_cell + beg + idx); }
+            e[b] = kEntInvalid;
+            if (mp < -1 || mp >= D.M) err |= ERR_INDEX;
+            else if (mp >= 0) {
+                if (c == kCellNone) seen_w[mp] = 1;                             // valid slot, not in mGrid (MapSparsification.cc:69-75)
+                else if (c >= (unsigned)kCells) err |= ERR_INDEX;
+                else e[b] = ((uint32_t)mp << kCellBits) | c;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) if (e[b] != kEntInvalid) tab[e[b] & kCellCov] = 0u;
+        __syncthreads();
+        int nz = 0, ncell = 0, z = 0;
+        unsigned m[kEpt];
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            const bool v = e[b] != kEntInvalid;
+            if (v) { ++nz; if (atomicAdd(&tab[e[b] & kCellCov], 1u) == 0u) ++ncell; }
+            m[b] = __ballot_sync(0xFFFFFFFFu, v);
+        }
+        block_sum3(S, nz, ncell, z);                                    // barriers publish tab
+        int wcnt = 0;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) wcnt += __popc(m[b]);
+        int total;
+        int pos = warp_excl_scan(S, wcnt, total);
+        const bool critr = defi && P.N >= nz;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int b = 0; b < kEpt; ++b) {
+            if (e[b] != kEntInvalid) {
+                const unsigned t = tab[e[b] & kCellCov];
+                if (t > 0xFFFFu) err |= ERR_CELL_OVERFLOW;
+                // round 1 (everything FREE, nothing IN): every cell is uncovered, every row with N > 0 is deficient
+                unsigned long long add = 1ull;
+                if (t == 1u) add |= 1ull << 16;
+                if (defi) add |= 1ull << 32;
+                if (critr) add |= 1ull << 48;
+                atomicAdd(&acc_w[e[b] >> kCellBits], add);
+                ent[pos + __popc(m[b] & lt)] = e[b];
+            }
+            pos += __popc(m[b]);
+        }
+        if (threadIdx.x == 0) {
+            P.ent_n[R] = nz; P.live_n[R] = 0; P.row_need[R] = P.N; P.row_cov[R] = 0; P.row_ncell[R] = ncell; P.row_off[R] = seg;
+            if (nz) atomicAdd(&ws.nnz, nz);
+            if (ncell) atomicAdd(&ws.n_cells, ncell);
+        }
+    } else {
+        // long keyframe: same thing in two passes over global memory
+        zero_tab(tab);
+        __syncthreads();
+        int nz = 0, ncell = 0, z = 0;
+        for (int i = threadIdx.x; i < nslots; i += kThreads) {
+            const int mp = __ldg(D.feat_mp + beg + i);
+            if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
+            if (mp >= D.M) { err |= ERR_INDEX; continue; }
+            const unsigned c = __ldg(D.feat_cell + beg + i);
+            if (c == kCellNone) { seen_w[mp] = 1; continue; }
+            if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
+            ++nz;
+            if (atomicAdd(&tab[c], 1u) == 0u) ++ncell;
+        }
+        block_sum3(S, nz, ncell, z);
+        const bool critr = defi && P.N >= nz;
+        int out_base = 0;
+        for (int base = 0; base < nslots; base += kThreads) {
+            const int i = base + (int)threadIdx.x;
+            uint32_t e = kEntInvalid;
+            if (i < nslots) {
+                const int mp = __ldg(D.feat_mp + beg + i);
+                const unsigned c = __ldg(D.feat_cell + beg + i);
+                if (mp >= 0 && mp < D.M && c < (unsigned)kCells) e = ((uint32_t)mp << kCellBits) | c;
+            }
+            int total;
+            const int p = block_excl_scan(S, e != kEntInvalid ? 1 : 0, total);
+            if (e != kEntInvalid) {
+                const unsigned t = tab[e & kCellCov];
+                if (t > 0xFFFFu) err |= ERR_CELL_OVERFLOW;
+                unsigned long long add = 1ull;
+                if (t == 1u) add |= 1ull << 16;
+                if (defi) add |= 1ull << 32;
+                if (critr) add |= 1ull << 48;
+                atomicAdd(&acc_w[e >> kCellBits], add);
+                ent[out_base + p] = e;
+            }
+            out_base += total;
+        }
+        if (threadIdx.x == 0) {
+            P.ent_n[R] = nz; P.live_n[R] = 0; P.row_need[R] = P.N; P.row_cov[R] = 0; P.row_ncell[R] = ncell; P.row_off[R] = seg;
+            if (nz) atomicAdd(&ws.nnz, nz);
+            if (ncell) atomicAdd(&ws.n_cells, ncell);
+        }
     }
     if (err) atomicOr(&ws.error, err);
 }
 
-// W2: per variable, count it and count its observations by outside keyframes (MapSparsification.cc:127-142)
-__device__ void w2_count_outside(const Params& P, const WinDesc& D, WinState& ws, int tile, BlockScratch& S) {
-    const int mp = tile * kVarTile + (int)threadIdx.x;
-    int nv = 0, z0 = 0, z1 = 0;
-    if (mp < D.M && P.st[D.var_base + mp] == ST_FREE) {
-        nv = 1;
-        if (D.H > 0) {
-            const int ob = __ldg(D.mp_obs_ptr + mp), oe = __ldg(D.mp_obs_ptr + mp + 1);
-            if (ob < 0 || oe < ob || oe > D.O) {
-                atomicOr(&ws.error, ERR_PTR);
-            } else {
-                for (int o = ob; o < oe; ++o) {
-                    const int kf = __ldg(D.mp_obs_kf + o);
-                    if (kf < D.K) { if (kf < 0) atomicOr(&ws.error, ERR_INDEX); continue; }
-                    if (kf >= D.K + D.H) { atomicOr(&ws.error, ERR_INDEX); continue; }
-                    atomicAdd(&P.ent_n[D.row_base + kf], 1);
-                }
-            }
+// Observations of the map points of one super-tile (kSuper consecutive map points, kVpt per thread), flattened: they
+// are one contiguous range of mp_obs_kf, read coalesced; the owner of observation o is found by binary search in the
+// super-tile's pointers (shared memory).  Several map points per thread keep that many independent loads in flight.
+constexpr int kVpt = 4;
+constexpr int kSuper = kVarTile * kVpt;
+struct ObsTile {
+    int ptr[kSuper + 1];
+    unsigned add[kSuper];        // W4: [outside rows that are deficient : 16 | ... that need every candidate : 16]
+    unsigned nout[kSuper];       // W4: outside observations
+    uint8_t isvar[kSuper];
+};
+
+__device__ __forceinline__ int obs_owner(const ObsTile& O, int o) {
+    int lo = 0, hi = kSuper;                // ptr[lo] <= o < ptr[hi]
+#pragma unroll
+    for (int step = 0; step < 10; ++step) {
+        const int mid = (lo + hi) >> 1;
+        if (O.ptr[mid] <= o) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// loads the super-tile's pointers; returns false (and flags the window) when they are not a valid CSR
+__device__ __forceinline__ bool obs_tile_load(const WinDesc& D, WinState& ws, int base, ObsTile& O) {
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) O.ptr[j * kVarTile + threadIdx.x] = __ldg(D.mp_obs_ptr + min(base + j * kVarTile + (int)threadIdx.x, D.M));
+    if (threadIdx.x == 0) O.ptr[kSuper] = __ldg(D.mp_obs_ptr + min(base + kSuper, D.M));
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int p = O.ptr[j * kVarTile + threadIdx.x], q = O.ptr[j * kVarTile + threadIdx.x + 1];
+        bad |= p < 0 || p > D.O || q < p || q > D.O;
+    }
+    if (__syncthreads_or(bad)) {
+        if (threadIdx.x == 0) atomicOr(&ws.error, ERR_PTR);
+        return false;
+    }
+    return true;
+}
+
+// W2: per super-tile of map points: state array from the W1 counters, nMax (MapSparsification.cc:66-76), variable count,
+// and the number of variables every outside keyframe observes (MapSparsification.cc:127-142)
+__device__ void w2_vars_and_outside_counts(const Params& P, const WinDesc& D, WinState& ws, int stile, ObsTile& O, BlockScratch& S) {
+    const int base = stile * kSuper;
+    bool isvar[kVpt];
+    int nmax = 0, nv = 0;
+    unsigned long long a[kVpt];
+    uint8_t sn[kVpt];
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int mp = base + j * kVarTile + (int)threadIdx.x;
+        a[j] = mp < D.M ? P.acc[D.var_base + mp] : 0ull;
+        sn[j] = mp < D.M ? P.seen[D.var_base + mp] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int mp = base + j * kVarTile + (int)threadIdx.x;
+        isvar[j] = a[j] != 0ull;
+        if (mp < D.M || mp < ((D.M + kVarTile - 1) / kVarTile) * kVarTile) P.st[D.var_base + mp] = isvar[j] ? (uint8_t)ST_FREE : (uint8_t)ST_NOTVAR;
+        if (isvar[j] || sn[j]) nmax = max(nmax, __ldg(D.mp_nobs + mp));
+        nv += isvar[j] ? 1 : 0;
+    }
+    nmax = block_max(S, nmax);
+    int z0 = 0, z1 = 0;
+    block_sum3(S, nv, z0, z1);
+    if (threadIdx.x == 0) {
+        if (nmax > 0) atomicMax(&ws.n_max, nmax);
+        if (nv) atomicAdd(&ws.n_vars, nv);
+    }
+    if (D.H == 0 || nv == 0) return;
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) O.isvar[j * kVarTile + threadIdx.x] = isvar[j] ? 1 : 0;
+    if (!obs_tile_load(D, ws, base, O)) return;
+    const int p0 = O.ptr[0], p1 = O.ptr[kSuper];
+    unsigned err = 0;
+    for (int o0 = p0; o0 < p1; o0 += kThreads * kVpt) {
+        int kf[kVpt];
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int o = o0 + j * kThreads + (int)threadIdx.x;
+            kf[j] = o < p1 ? __ldg(D.mp_obs_kf + o) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int o = o0 + j * kThreads + (int)threadIdx.x;
+            if (o >= p1 || kf[j] < D.K) { if (kf[j] < 0) err |= ERR_INDEX; continue; }
+            if (kf[j] >= D.K + D.H) { err |= ERR_INDEX; continue; }
+            if (O.isvar[obs_owner(O, o)]) atomicAdd(&P.ent_n[D.row_base + kf[j]], 1);
         }
     }
-    block_sum3(S, nv, z0, z1);
-    if (threadIdx.x == 0 && nv) atomicAdd(&ws.n_vars, nv);
+    if (err) atomicOr(&ws.error, err);
+    __syncthreads();
 }
 
 // W3 (one CTA per window): exclusive scan of the outside-row counts -> segments, rhs of the outside rows
@@ -471,41 +609,98 @@ __device__ __forceinline__ void prop_decide(const Params& P, unsigned long long 
     else { *gain = (float)ub; nfree += 1; sumdeg += (int)deg; }
 }
 
-// W4: per variable, fill the outside rows, add their round-1 contributions and take the round-1 decision
-__device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& ws, int tile, BlockScratch& S) {
-    const int mp = tile * kVarTile + (int)threadIdx.x;
-    const int g = D.var_base + mp;
-    int changed = 0, nfree = 0, sumdeg = 0;
-    if (mp < D.M && P.st[g] == ST_FREE) {
-        unsigned long long a = P.acc[g];
-        P.acc[g] = 0ull;
-        unsigned nout = 0;
-        if (D.H > 0) {
-            const int ob = __ldg(D.mp_obs_ptr + mp), oe = __ldg(D.mp_obs_ptr + mp + 1);
-            for (int o = ob; o < oe; ++o) {
-                const int kf = __ldg(D.mp_obs_kf + o);
-                if (kf < D.K) continue;
-                const int R = D.row_base + kf;
-                const int pos = atomicAdd(&P.ocursor[R], 1);
-                P.ent[pos] = ((uint32_t)mp << kCellBits) | kCellCov;
-                ++nout;
-                const int need = P.row_need[R];
-                if (need > 0) {
-                    a += 1ull << 32;
-                    if (need >= P.ent_n[R]) a += 1ull << 48;
+// warp-aggregated bookkeeping of a PROP decision: counters + append of the still-FREE map points to the new list
+__device__ __forceinline__ void prop_commit(RoundCnt& rc, int* vdst, int mp, int changed, int nfree, int sumdeg) {
+    const int lane = threadIdx.x & 31;
+    const unsigned mk = __ballot_sync(0xFFFFFFFFu, nfree != 0);
+    const unsigned mc = __ballot_sync(0xFFFFFFFFu, changed != 0);
+    if (mk == 0u && mc == 0u) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sumdeg += __shfl_xor_sync(0xFFFFFFFFu, sumdeg, o);
+    int pos = 0;
+    if (lane == 0) {
+        if (mk) pos = (int)atomicAdd(&rc.nfree, (unsigned)__popc(mk));
+        if (mc) atomicAdd(&rc.changed, (unsigned)__popc(mc));
+        if (sumdeg) atomicAdd(&rc.sumdeg, (unsigned)sumdeg);
+    }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (nfree) vdst[pos + __popc(mk & ((1u << lane) - 1u))] = mp;
+}
+
+// W4: per super-tile of map points: fill the outside rows, add their round-1 contributions, take the round-1 decision
+__device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& ws, int stile, ObsTile& O) {
+    const int base = stile * kSuper;
+    bool isvar[kVpt];
+    unsigned long long a[kVpt];
+    int nobs[kVpt];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int mp = base + j * kVarTile + (int)threadIdx.x;
+        isvar[j] = mp < D.M && P.st[D.var_base + mp] == ST_FREE;
+    }
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int mp = base + j * kVarTile + (int)threadIdx.x;
+        a[j] = 0ull;
+        nobs[j] = 0;
+        if (isvar[j]) { a[j] = P.acc[D.var_base + mp]; nobs[j] = __ldg(D.mp_nobs + mp); any = true; }
+    }
+    unsigned nout[kVpt] = {0u, 0u, 0u, 0u};
+    if (D.H > 0 && __syncthreads_or(any)) {
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            O.isvar[j * kVarTile + threadIdx.x] = isvar[j] ? 1 : 0;
+            O.add[j * kVarTile + threadIdx.x] = 0u;
+            O.nout[j * kVarTile + threadIdx.x] = 0u;
+        }
+        if (obs_tile_load(D, ws, base, O)) {            // (validated in W2 already; W4 only runs on windows without errors)
+            const int p0 = O.ptr[0], p1 = O.ptr[kSuper];
+            for (int o0 = p0; o0 < p1; o0 += kThreads * kVpt) {
+                int kf[kVpt];
+#pragma unroll
+                for (int j = 0; j < kVpt; ++j) {
+                    const int o = o0 + j * kThreads + (int)threadIdx.x;
+                    kf[j] = o < p1 ? __ldg(D.mp_obs_kf + o) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < kVpt; ++j) {
+                    const int o = o0 + j * kThreads + (int)threadIdx.x;
+                    if (o >= p1 || kf[j] < D.K) continue;
+                    const int v = obs_owner(O, o);
+                    if (!O.isvar[v]) continue;
+                    const int R = D.row_base + kf[j];
+                    const int pos = atomicAdd(&P.ocursor[R], 1);
+                    P.ent[pos] = ((uint32_t)(base + v) << kCellBits) | kCellCov;
+                    const int need = P.row_need[R];
+                    unsigned add = 0u;
+                    if (need > 0) { add = 1u; if (need >= P.ent_n[R]) add |= 1u << 16; }
+                    if (add) atomicAdd(&O.add[v], add);
+                    atomicAdd(&O.nout[v], 1u);
                 }
             }
         }
-        const unsigned deg = (unsigned)(a & 0xFFFFu) + nout;
-        P.deg[g] = deg;
-        prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], deg, changed, nfree, sumdeg);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const unsigned ad = O.add[j * kVarTile + threadIdx.x];
+            a[j] += ((unsigned long long)(ad & 0xFFFFu) << 32) + ((unsigned long long)(ad >> 16) << 48);
+            nout[j] = O.nout[j * kVarTile + threadIdx.x];
+        }
+        __syncthreads();                                 // O is reused by the next super-tile
     }
-    block_sum3(S, changed, nfree, sumdeg);
-    if (threadIdx.x == 0) {
-        RoundCnt& rc = ws.rc[0];
-        if (changed) atomicAdd(&rc.changed, (unsigned)changed);
-        if (nfree) atomicAdd(&rc.nfree, (unsigned)nfree);
-        if (sumdeg) atomicAdd(&rc.sumdeg, (unsigned)sumdeg);
+#pragma unroll
+    for (int j = 0; j < kVpt; ++j) {
+        const int mp = base + j * kVarTile + (int)threadIdx.x;
+        const int g = D.var_base + mp;
+        int changed = 0, nfree = 0, sumdeg = 0;
+        if (isvar[j]) {
+            const unsigned deg = (unsigned)(a[j] & 0xFFFFu) + nout[j];
+            P.deg[g] = deg;
+            P.acc[g] = 0ull;
+            prop_decide(P, a[j], ws.n_max - nobs[j], &P.st[g], &P.gain[g], deg, changed, nfree, sumdeg);
+        }
+        prop_commit(ws.rc[0], P.vlist + D.var_base, mp, changed, nfree, sumdeg);
     }
 }
 
@@ -515,8 +710,7 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
 // PROP: counts on the current state, contributions to the FREE variables, and the row's new live list.
 // Source list: the CSR (first PROP row phase of the window) or the previous live list.  Entries found IN are added to the
 // running coverage exactly once (they are not copied to the new list); entries found OUT are dropped.
-__device__ void row_prop(const Params& P, const WinDesc& D, RoundCnt& rc, int R, bool from_csr, unsigned* tab, BlockScratch& S) {
-    const int n = from_csr ? P.ent_n[R] : P.live_n[R];
+__device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, bool from_csr, unsigned* tab, BlockScratch& S) {
     if (n == 0) return;                                     // live_n[R] is already 0 (W1 / W3 / previous round)
     const int off = P.row_off[R];
     const uint32_t* src = (from_csr ? P.ent : P.live) + off;
@@ -578,7 +772,7 @@ __device__ void row_prop(const Params& P, const WinDesc& D, RoundCnt& rc, int R,
         if (threadIdx.x == 0) {
             P.row_cov[R] = cov;
             P.live_n[R] = cfree;
-            if (cfree) atomicAdd(&rc.rows_live, 1u);
+            if (cfree) { S.rows_live += 1u; if (R - D.row_base < D.K) S.maxlive = max(S.maxlive, (unsigned)cfree); }   // thread 0 only
         }
     } else {
         // long row: two passes over the list in global memory
@@ -627,15 +821,14 @@ __device__ void row_prop(const Params& P, const WinDesc& D, RoundCnt& rc, int R,
         if (threadIdx.x == 0) {
             P.row_cov[R] = cov;
             P.live_n[R] = cfree;
-            if (cfree) atomicAdd(&rc.rows_live, 1u);
+            if (cfree) { S.rows_live += 1u; if (R - D.row_base < D.K) S.maxlive = max(S.maxlive, (unsigned)cfree); }   // thread 0 only
         }
     }
 }
 
 // GREEDY: runs right after a PROP round that changed nothing, so the live list is exact (all FREE, cell field = covered
 // flag, row_cov current).
-__device__ void row_greedy(const Params& P, const WinDesc& D, int R, unsigned long long* keytab, BlockScratch& S) {
-    const int n = P.live_n[R];
+__device__ void row_greedy(const Params& P, const WinDesc& D, int R, int n, unsigned long long* keytab, BlockScratch& S) {
     if (n == 0) return;
     const uint32_t* src = P.live + P.row_off[R];
     const uint8_t* st_w = P.st + D.var_base;
@@ -719,6 +912,88 @@ __device__ void row_greedy(const Params& P, const WinDesc& D, int R, unsigned lo
             }
         }
     }
+}
+
+// Warp-per-row variants for lists of at most 32 entries (one entry per lane).  Entries of one cell are found with
+// match.any instead of the shared-memory cell table, so eight short rows are in flight per CTA and none of them needs a
+// block barrier.  Same arithmetic as the block versions.
+__device__ __forceinline__ void warp_row_prop(const Params& P, const WinDesc& D, int R, int n, bool from_csr, unsigned& rows_live) {
+    const int lane = threadIdx.x & 31;
+    const int off = P.row_off[R];
+    const uint32_t* src = (from_csr ? P.ent : P.live) + off;
+    uint32_t* dst = P.live + off;
+    const uint8_t* st_w = P.st + D.var_base;
+    const bool valid = lane < n;
+    uint32_t e = valid ? src[lane] : kEntInvalid;
+    const int need = P.row_need[R], cov0 = P.row_cov[R];
+    const uint8_t s = valid ? st_w[e >> kCellBits] : (uint8_t)ST_NOTVAR;
+    const unsigned cell = e & kCellCov;
+    const bool hascell = valid && cell != kCellCov;
+    const unsigned mIN = __ballot_sync(0xFFFFFFFFu, s == ST_IN);
+    const unsigned mFR = __ballot_sync(0xFFFFFFFFu, s == ST_FREE);
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, hascell ? cell : 0x10000u);
+    const int cin = __popc(mIN), cfree = __popc(mFR);
+    const int cov = cov0 + cin;
+    const int d = max(0, need - cov);
+    const bool defi = d > 0, critr = defi && d >= cfree;
+    if (s == ST_FREE) {
+        unsigned long long add = 0;
+        bool covered = true;
+        if (hascell) {
+            covered = (grp & mIN) != 0u;
+            if (!covered) { add |= 1ull; if (__popc(grp & mFR) == 1) add |= 1ull << 16; }
+        }
+        if (defi) add |= 1ull << 32;
+        if (critr) add |= 1ull << 48;
+        if (add) atomicAdd(&P.acc[D.var_base + (e >> kCellBits)], add);
+        if (covered) e |= kCellCov;
+    }
+    __syncwarp();                                           // every lane has read src before the in-place writes
+    if (s == ST_FREE) dst[__popc(mFR & ((1u << lane) - 1u))] = e;
+    if (lane == 0) {
+        if (cin) P.row_cov[R] = cov;
+        P.live_n[R] = cfree;
+        if (cfree) rows_live += 1u;
+    }
+}
+
+__device__ __forceinline__ void warp_row_greedy(const Params& P, const WinDesc& D, int R, int n) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t* src = P.live + P.row_off[R];
+    const bool valid = lane < n;
+    const uint32_t e = valid ? src[lane] : kEntInvalid;
+    const unsigned v = e >> kCellBits;
+    const int d = max(0, P.row_need[R] - P.row_cov[R]);
+    const bool fr = valid && P.st[D.var_base + v] == ST_FREE;
+    const unsigned long long key = fr ? make_key(P.gain[D.var_base + v], v) : 0ull;
+    const unsigned cell = e & kCellCov;
+    const bool unc = fr && cell != kCellCov;
+    const unsigned mFR = __ballot_sync(0xFFFFFFFFu, fr);
+    const unsigned mU = __ballot_sync(0xFFFFFFFFu, unc);
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, unc ? cell : 0x10000u);
+    unsigned long long best = 0ull;
+    for (unsigned rem = mU; rem; rem &= rem - 1u) {
+        const int j = __ffs(rem) - 1;
+        const unsigned long long kj = __shfl_sync(0xFFFFFFFFu, key, j);
+        if ((grp >> j) & 1u) best = max(best, kj);
+    }
+    unsigned long long flags = 0ull;
+    if (unc && key != best) flags |= FLAG_BLOCKED;
+    if (d > 0) {
+        const int nfree = __popc(mFR);
+        if (nfree > d) {
+            int cge = 0;
+            for (unsigned rem = mFR; rem; rem &= rem - 1u) {
+                const int j = __ffs(rem) - 1;
+                const unsigned long long kj = __shfl_sync(0xFFFFFFFFu, key, j);
+                cge += (kj >= key) ? 1 : 0;
+            }
+            if (fr) flags |= (cge <= d) ? FLAG_NOMINATED : FLAG_BLOCKED;     // key > (d+1)-th largest  <=>  #{keys >= key} <= d
+        } else if (fr) {
+            flags |= FLAG_NOMINATED;
+        }
+    }
+    if (flags) atomicOr(&P.acc[D.var_base + v], flags);
 }
 
 // D1 (and EVAL): one sweep of the row's CSR segment: IN counts per cell and per row; D1 adds the criticality counters
@@ -848,43 +1123,47 @@ __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// variable phases (one thread per map point of a 256-wide tile)
+// variable phases
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void var_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int greedy_steps, int tile,
-                          BlockScratch& S) {
+// PROP / GREEDY / FORCE touch only FREE map points: they walk the compact list written by the last PROP phase
+// (one thread per listed map point; PROP writes the next list).  No block barrier inside.
+__device__ void var_list_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int greedy_steps,
+                               const int* vsrc, int nsrc, int* vdst, const GroupCtx& G) {
+    const bool any_rule = greedy_steps >= P.all_rule_steps;
+    for (int base = G.cta * kThreads; base < nsrc; base += G.ncta * kThreads) {
+        const int i = base + (int)threadIdx.x;
+        int mp = -1, g = 0;
+        uint8_t s = ST_NOTVAR;
+        if (i < nsrc) { mp = vsrc[i]; g = D.var_base + mp; s = P.st[g]; }
+        if (mode == MODE_PROP) {
+            int c0 = 0, c1 = 0, c2 = 0;
+            if (s == ST_FREE) {
+                const unsigned long long a = P.acc[g];
+                if (a) P.acc[g] = 0ull;
+                prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], P.deg[g], c0, c1, c2);
+            }
+            prop_commit(rc, vdst, mp, c0, c1, c2);
+        } else if (mode == MODE_GREEDY) {
+            if (s == ST_FREE) {
+                const unsigned long long a = P.acc[g];
+                if (a) P.acc[g] = 0ull;
+                const bool sel = (P.gain[g] > 0.0f && !(a & FLAG_BLOCKED)) || (any_rule && (a & FLAG_NOMINATED));
+                if (sel) P.st[g] = ST_IN;
+            }
+        } else {    // MODE_FORCE
+            if (s == ST_FREE) P.st[g] = ST_IN;
+        }
+    }
+}
+
+// D1 / D2 / EVAL look at every map point of a 256-wide tile (one thread per map point)
+__device__ void var_tile_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int tile, BlockScratch& S) {
     const int mp = tile * kVarTile + (int)threadIdx.x;
     const int g = D.var_base + mp;
     const bool inb = mp < D.M;
     const uint8_t s = inb ? P.st[g] : (uint8_t)ST_NOTVAR;
     int c0 = 0, c1 = 0, c2 = 0;
     switch (mode) {
-    case MODE_PROP: {
-        if (s == ST_FREE) {
-            const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0ull;
-            prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], P.deg[g], c0, c1, c2);
-        }
-        if (__syncthreads_or(s == ST_FREE)) {
-            block_sum3(S, c0, c1, c2);
-            if (threadIdx.x == 0) {
-                if (c0) atomicAdd(&rc.changed, (unsigned)c0);
-                if (c1) atomicAdd(&rc.nfree, (unsigned)c1);
-                if (c2) atomicAdd(&rc.sumdeg, (unsigned)c2);
-            }
-        }
-    } break;
-    case MODE_GREEDY: {
-        if (s == ST_FREE) {
-            const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0ull;
-            const bool any_rule = greedy_steps >= P.all_rule_steps;
-            const bool sel = (P.gain[g] > 0.0f && !(a & FLAG_BLOCKED)) || (any_rule && (a & FLAG_NOMINATED));
-            if (sel) P.st[g] = ST_IN;
-        }
-    } break;
-    case MODE_FORCE: {
-        if (s == ST_FREE) P.st[g] = ST_IN;
-    } break;
     case MODE_D1: {
         if (s == ST_IN) {
             const unsigned long long a = P.acc[g];
@@ -927,20 +1206,409 @@ __device__ void var_phase(const Params& P, const WinDesc& D, WinState& ws, Round
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// shared-memory tail: once the undecided part of a window is small, CTA 0 of the group copies it into shared memory
+// (FREE map points renumbered 0..nv-1, their row entries, the rows' running deficits) and runs the remaining PROP /
+// GREEDY rounds there with block barriers only; the other CTAs of the group wait at one group barrier.
+// Same arithmetic and tie-breaks (keys use the original map-point index) as the group-wide phases.
+// ---------------------------------------------------------------------------------------------------------------
+struct TailSmem {
+    uint32_t ent[kTailEnts];              // (local id << 12) | cell, row segments back to back
+    uint32_t acc_lo[kTailVars];            // [ubc:16 | lbc:16] or the GREEDY flags (32-bit: native shared-memory atomics)
+    uint32_t acc_hi[kTailVars];            // [ubr:16 | lbr:16]
+    float gain[kTailVars];
+    int cost[kTailVars];
+    uint32_t mp[kTailVars];               // original map-point index (tie-break, write-back)
+    int rdef[kTailRows];                  // need - coverage of the row (may be negative)
+    unsigned short rptr[kTailRows];
+    unsigned short rn[kTailRows];
+    unsigned short rsrc[kTailRows];       // window-local row index
+    uint8_t st[kTailVars];
+};
+
+// one row of the tail, any length: PROP row step (see row_prop)
+__device__ void tail_row_prop(TailSmem& T, int lid) {
+    const int lane = threadIdx.x & 31;
+    uint32_t* lst = T.ent + T.rptr[lid];
+    const int n = T.rn[lid];
+    if (n == 0) return;
+    const unsigned lt = (1u << lane) - 1u;
+    if (n <= 32) {
+        const bool valid = lane < n;
+        uint32_t e = valid ? lst[lane] : kEntInvalid;
+        const uint8_t s = valid ? T.st[e >> kCellBits] : (uint8_t)ST_NOTVAR;
+        const unsigned cell = e & kCellCov;
+        const bool hascell = valid && cell != kCellCov;
+        const unsigned mIN = __ballot_sync(0xFFFFFFFFu, s == ST_IN);
+        const unsigned mFR = __ballot_sync(0xFFFFFFFFu, s == ST_FREE);
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, hascell ? cell : 0x10000u);
+        const int cin = __popc(mIN), cfree = __popc(mFR);
+        const int def = T.rdef[lid] - cin;
+        const int d = max(0, def);
+        const bool defi = d > 0, critr = defi && d >= cfree;
+        if (s == ST_FREE) {
+            uint32_t lo = 0, hi = 0;
+            bool covered = true;
+            if (hascell) {
+                covered = (grp & mIN) != 0u;
+                if (!covered) { lo |= 1u; if (__popc(grp & mFR) == 1) lo |= 1u << 16; }
+            }
+            if (defi) hi |= 1u;
+            if (critr) hi |= 1u << 16;
+            if (lo) atomicAdd(&T.acc_lo[e >> kCellBits], lo);
+            if (hi) atomicAdd(&T.acc_hi[e >> kCellBits], hi);
+            if (covered) e |= kCellCov;
+        }
+        __syncwarp();
+        if (s == ST_FREE) lst[__popc(mFR & lt)] = e;
+        if (lane == 0) { T.rdef[lid] = def; T.rn[lid] = (unsigned short)cfree; }
+        return;
+    }
+    // long list: pass A counts, pass B matches every FREE entry against the whole list, pass C compacts
+    int cin = 0, cfree = 0;
+    for (int c = 0; c < n; c += 32) {
+        const int i = c + lane;
+        const uint8_t s = (i < n) ? T.st[lst[i] >> kCellBits] : (uint8_t)ST_NOTVAR;
+        cin += __popc(__ballot_sync(0xFFFFFFFFu, s == ST_IN));
+        cfree += __popc(__ballot_sync(0xFFFFFFFFu, s == ST_FREE));
+    }
+    const int def = T.rdef[lid] - cin;
+    const int d = max(0, def);
+    const bool defi = d > 0, critr = defi && d >= cfree;
+    for (int ca = 0; ca < n; ca += 32) {
+        const int ia = ca + lane;
+        const uint32_t ea = (ia < n) ? lst[ia] : kEntInvalid;
+        const bool fra = (ia < n) && T.st[ea >> kCellBits] == ST_FREE;
+        const unsigned cella = ea & kCellCov;
+        const bool hasa = fra && cella != kCellCov;
+        bool covered = false;
+        int nf = 0;
+        if (__any_sync(0xFFFFFFFFu, hasa)) {
+            // lists are cell-sorted (counting sort in W1, stable compactions since), so the entries of one cell sit next to
+            // each other: only chunks whose cell range overlaps this chunk's range can hold a match
+            const unsigned amin = __reduce_min_sync(0xFFFFFFFFu, hasa ? cella : 0xFFFFu);
+            const unsigned amax = __reduce_max_sync(0xFFFFFFFFu, hasa ? cella : 0u);
+            for (int cb = 0; cb < n; cb += 32) {
+                const int ib = cb + lane;
+                const uint32_t eb = (ib < n) ? lst[ib] : kEntInvalid;
+                const uint8_t sb = (ib < n) ? T.st[eb >> kCellBits] : (uint8_t)ST_NOTVAR;
+                // covered FREE entries may already carry kCellCov (rewritten below): they no longer match, which is fine
+                // because an IN entry of the same cell still does
+                const unsigned cellb = (sb == ST_IN || sb == ST_FREE) ? (eb & kCellCov) : kCellCov;
+                const bool hasb = cellb != kCellCov;
+                const unsigned bmin = __reduce_min_sync(0xFFFFFFFFu, hasb ? cellb : 0xFFFFu);
+                const unsigned bmax = __reduce_max_sync(0xFFFFFFFFu, hasb ? cellb : 0u);
+                if (bmin > amax || bmax < amin) continue;
+                for (unsigned rem = __ballot_sync(0xFFFFFFFFu, hasb && cellb >= amin && cellb <= amax); rem; rem &= rem - 1u) {
+                    const int j = __ffs(rem) - 1;
+                    const unsigned cj = __shfl_sync(0xFFFFFFFFu, cellb, j);
+                    const unsigned sj = __shfl_sync(0xFFFFFFFFu, (unsigned)sb, j);
+                    if (hasa && cj == cella) { if (sj == ST_IN) covered = true; else ++nf; }
+                }
+            }
+        }
+        __syncwarp();
+        if (fra) {
+            uint32_t lo = 0, hi = 0;
+            const bool cov2 = !hasa || covered;
+            if (!cov2) { lo |= 1u; if (nf == 1) lo |= 1u << 16; }
+            if (defi) hi |= 1u;
+            if (critr) hi |= 1u << 16;
+            if (lo) atomicAdd(&T.acc_lo[ea >> kCellBits], lo);
+            if (hi) atomicAdd(&T.acc_hi[ea >> kCellBits], hi);
+            if (hasa && covered) lst[ia] = ea | kCellCov;
+        }
+        __syncwarp();
+    }
+    int out = 0;
+    for (int c = 0; c < n; c += 32) {
+        const int i = c + lane;
+        const uint32_t e = (i < n) ? lst[i] : kEntInvalid;
+        const bool fr = (i < n) && T.st[e >> kCellBits] == ST_FREE;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, fr);
+        __syncwarp();
+        if (fr) lst[out + __popc(m & lt)] = e;
+        out += __popc(m);
+        __syncwarp();
+    }
+    if (lane == 0) { T.rdef[lid] = def; T.rn[lid] = (unsigned short)cfree; }
+}
+
+// one row of the tail, any length: GREEDY row step (see row_greedy); the list is exact (all FREE)
+__device__ void tail_row_greedy(TailSmem& T, int lid) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t* lst = T.ent + T.rptr[lid];
+    const int n = T.rn[lid];
+    if (n == 0) return;
+    const int d = max(0, T.rdef[lid]);
+    // what does this row have to decide?  cells with FREE candidates, and / or a deficit smaller than its FREE count
+    int nfr = 0;
+    bool any_unc = false;
+    for (int c = 0; c < n; c += 32) {
+        const int i = c + lane;
+        const uint32_t e = (i < n) ? lst[i] : kEntInvalid;
+        const bool fr = (i < n) && T.st[e >> kCellBits] == ST_FREE;
+        nfr += __popc(__ballot_sync(0xFFFFFFFFu, fr));
+        any_unc |= __any_sync(0xFFFFFFFFu, fr && (e & kCellCov) != kCellCov) != 0;
+    }
+    const bool rank = d > 0 && nfr > d;
+    if (!any_unc && !rank) {
+        if (d > 0) {
+            for (int i = lane; i < n; i += 32) {
+                const unsigned v = lst[i] >> kCellBits;
+                if (T.st[v] == ST_FREE) atomicOr(&T.acc_lo[v], (uint32_t)FLAG_NOMINATED);
+            }
+        }
+        return;
+    }
+    // (d+1)-th largest key of the row by bisection on the key bits: thr = max x with #{keys >= x} >= d + 1
+    unsigned long long thr = 0ull;
+    if (rank) {
+        if (n <= 32 * kEpt) {
+            unsigned long long k[kEpt];
+#pragma unroll
+            for (int b = 0; b < kEpt; ++b) {
+                const int i = b * 32 + lane;
+                k[b] = 0ull;
+                if (i < n) {
+                    const unsigned v = lst[i] >> kCellBits;
+                    if (T.st[v] == ST_FREE) k[b] = make_key(T.gain[v], T.mp[v]);
+                }
+            }
+            for (int bit = 63; bit >= 0; --bit) {
+                const unsigned long long cand = thr | (1ull << bit);
+                int c = 0;
+#pragma unroll
+                for (int b = 0; b < kEpt; ++b) c += (k[b] >= cand) ? 1 : 0;
+                c = __reduce_add_sync(0xFFFFFFFFu, c);
+                if (c > d) thr = cand;
+            }
+        } else {
+            for (int bit = 63; bit >= 0; --bit) {
+                const unsigned long long cand = thr | (1ull << bit);
+                int c = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const unsigned v = lst[i] >> kCellBits;
+                    c += (T.st[v] == ST_FREE && make_key(T.gain[v], T.mp[v]) >= cand) ? 1 : 0;
+                }
+                c = __reduce_add_sync(0xFFFFFFFFu, c);
+                if (c > d) thr = cand;
+            }
+        }
+    }
+    for (int ca = 0; ca < n; ca += 32) {
+        const int ia = ca + lane;
+        const uint32_t ea = (ia < n) ? lst[ia] : kEntInvalid;
+        const unsigned va = ea >> kCellBits;
+        const bool fra = (ia < n) && T.st[va] == ST_FREE;
+        const unsigned long long keya = fra ? make_key(T.gain[va], T.mp[va]) : 0ull;
+        const unsigned cella = ea & kCellCov;
+        const bool unca = fra && cella != kCellCov;
+        unsigned long long best = 0ull;
+        if (__any_sync(0xFFFFFFFFu, unca)) {
+            const unsigned amin = __reduce_min_sync(0xFFFFFFFFu, unca ? cella : 0xFFFFu);
+            const unsigned amax = __reduce_max_sync(0xFFFFFFFFu, unca ? cella : 0u);
+            for (int cb = 0; cb < n; cb += 32) {
+                const int ib = cb + lane;
+                const uint32_t eb = (ib < n) ? lst[ib] : kEntInvalid;
+                const unsigned vb = eb >> kCellBits;
+                const bool ub = (ib < n) && T.st[vb] == ST_FREE && (eb & kCellCov) != kCellCov;
+                const unsigned cellb = ub ? (eb & kCellCov) : kCellCov;
+                const unsigned bmin = __reduce_min_sync(0xFFFFFFFFu, ub ? cellb : 0xFFFFu);
+                const unsigned bmax = __reduce_max_sync(0xFFFFFFFFu, ub ? cellb : 0u);
+                if (bmin > amax || bmax < amin) continue;
+                const unsigned long long keyb = ub ? make_key(T.gain[vb], T.mp[vb]) : 0ull;
+                for (unsigned rem = __ballot_sync(0xFFFFFFFFu, ub && cellb >= amin && cellb <= amax); rem; rem &= rem - 1u) {
+                    const int j = __ffs(rem) - 1;
+                    const unsigned long long kj = __shfl_sync(0xFFFFFFFFu, keyb, j);
+                    const unsigned cj = __shfl_sync(0xFFFFFFFFu, cellb, j);
+                    if (unca && cj == cella) best = max(best, kj);
+                }
+            }
+        }
+        uint32_t flags = 0u;
+        if (unca && keya != best) flags |= (uint32_t)FLAG_BLOCKED;
+        if (d > 0 && fra) flags |= (uint32_t)((!rank || keya > thr) ? FLAG_NOMINATED : FLAG_BLOCKED);
+        if (flags) atomicOr(&T.acc_lo[va], flags);
+    }
+}
+
+// Runs on CTA 0 of the group.  vprev/nv: FREE list of the state the live lists were written for.  On return the states of
+// those map points are final (IN / OUT) in P.st, and rounds / greedy_steps / status are updated.
+__device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, TailSmem& T, BlockScratch& S, const int* vprev, int nv,
+                           int mode, int drop_mode, int& rounds, int& greedy_steps, int& status, int w, int& tn,
+                           unsigned long long t_win) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rows = D.K + D.H;
+    // ---- gather ----------------------------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < nv; i += kThreads) {
+        const int mp = vprev[i];
+        const int g = D.var_base + mp;
+        T.mp[i] = (uint32_t)mp;
+        T.st[i] = P.st[g];
+        T.cost[i] = ws.n_max - __ldg(D.mp_nobs + mp);
+        T.acc_lo[i] = 0u;
+        T.acc_hi[i] = 0u;
+        T.gain[i] = P.gain[g];
+        P.deg[g] = (unsigned)i;                 // deg is not needed any more: reuse it as the local-id map
+    }
+    int nr = 0, ne = 0;
+    for (int base = 0; base < rows; base += kThreads) {
+        const int r = base + (int)threadIdx.x;
+        const int n = (r < rows) ? P.live_n[D.row_base + r] : 0;
+        int tr, te;
+        const int lid = nr + block_excl_scan(S, n > 0 ? 1 : 0, tr);
+        const int ptr = ne + block_excl_scan(S, n, te);
+        if (n > 0) {
+            T.rptr[lid] = (unsigned short)ptr;
+            T.rn[lid] = (unsigned short)n;
+            T.rsrc[lid] = (unsigned short)r;
+            T.rdef[lid] = P.row_need[D.row_base + r] - P.row_cov[D.row_base + r];
+        }
+        nr += tr;
+        ne += te;
+    }
+    __syncthreads();
+    for (int lid = wid; lid < nr; lid += kWarps) {
+        const uint32_t* src = P.live + P.row_off[D.row_base + T.rsrc[lid]];
+        uint32_t* dst = T.ent + T.rptr[lid];
+        const int n = T.rn[lid];
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t e = src[i];
+            dst[i] = (P.deg[D.var_base + (e >> kCellBits)] << kCellBits) | (e & kCellCov);
+        }
+    }
+    __syncthreads();
+    if (P.trace && threadIdx.x == 0 && tn < kTraceCap - 1) {
+        P.trace[(size_t)w * kTraceCap + tn] = make_uint2((20u << 24) | (unsigned)ne, (unsigned)(globaltimer_ns() - t_win));
+        ++tn;
+    }
+    // ---- rounds ----------------------------------------------------------------------------------------------------
+    while (mode == MODE_PROP || mode == MODE_GREEDY) {
+        const int mode0 = mode;
+        if (mode == MODE_PROP) {
+            if (threadIdx.x < 2) S.tcnt[threadIdx.x] = 0;
+            for (int lid = wid; lid < nr; lid += kWarps) tail_row_prop(T, lid);
+            __syncthreads();
+            int c0 = 0, c1 = 0, c2 = 0;
+            for (int i = threadIdx.x; i < nv; i += kThreads) {
+                if (T.st[i] != ST_FREE) continue;
+                const unsigned long long a = (unsigned long long)T.acc_lo[i] | ((unsigned long long)T.acc_hi[i] << 32);
+                T.acc_lo[i] = 0u;
+                T.acc_hi[i] = 0u;
+                prop_decide(P, a, T.cost[i], &T.st[i], &T.gain[i], 0u, c0, c1, c2);
+            }
+            if (c0) atomicAdd(&S.tcnt[0], c0);
+            if (c1) atomicAdd(&S.tcnt[1], c1);
+            __syncthreads();
+            ++rounds;
+            const unsigned changed = (unsigned)S.tcnt[0], nfree = (unsigned)S.tcnt[1];
+            __syncthreads();                         // everyone has read the counters before they are zeroed again
+            if (changed > 0 && rounds < P.max_rounds) mode = MODE_PROP;
+            else if (nfree == 0) mode = drop_mode;
+            else if (rounds >= P.max_rounds) { status = -5; mode = MODE_FORCE; }
+            else mode = MODE_GREEDY;
+        } else {
+            for (int lid = wid; lid < nr; lid += kWarps) tail_row_greedy(T, lid);
+            __syncthreads();
+            const bool any_rule = greedy_steps >= P.all_rule_steps;
+            for (int i = threadIdx.x; i < nv; i += kThreads) {
+                if (T.st[i] != ST_FREE) continue;
+                const uint32_t a = T.acc_lo[i];
+                T.acc_lo[i] = 0u;
+                const bool sel = (T.gain[i] > 0.0f && !(a & FLAG_BLOCKED)) || (any_rule && (a & FLAG_NOMINATED));
+                if (sel) T.st[i] = ST_IN;
+            }
+            __syncthreads();
+            ++greedy_steps;
+            ++rounds;
+            mode = MODE_PROP;
+        }
+        if (P.trace && threadIdx.x == 0 && tn < kTraceCap - 1) {
+            P.trace[(size_t)w * kTraceCap + tn] = make_uint2(((20u + (unsigned)mode0) << 24) | (unsigned)S.tcnt[1], (unsigned)(globaltimer_ns() - t_win));
+            ++tn;
+        }
+    }
+    // ---- write-back (FORCE: every point still FREE is taken) --------------------------------------------------------------
+    for (int i = threadIdx.x; i < nv; i += kThreads) {
+        uint8_t s = T.st[i];
+        if (s == ST_FREE) s = ST_IN;
+        P.st[D.var_base + T.mp[i]] = s;
+    }
+    if (threadIdx.x == 0) { ws.t_rounds = rounds; ws.t_greedy = greedy_steps; ws.t_status = status; }
+}
+
+// Row phase of PROP / GREEDY over the rows of this CTA: the rows are classified by list length in chunks of 256; long
+// lists are processed by the whole CTA one after the other, short ones by one warp each.
+__device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc, const GroupCtx& G, int mode, bool from_csr,
+                                unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
+    const int rows = D.K + D.H;
+    const int mine = (rows - G.cta + G.ncta - 1) / G.ncta;          // rows G.cta, G.cta + ncta, ...
+    const int* listn = from_csr ? P.ent_n : P.live_n;
+    const int wid = threadIdx.x >> 5;
+    unsigned rows_live = 0;
+    if (threadIdx.x == 0) { S.rows_live = 0u; S.maxlive = 0u; }
+    for (int base = 0; base < mine; base += kThreads) {
+        if (threadIdx.x < 2) S.qn[threadIdx.x] = 0;
+        __syncthreads();
+        const int i = base + (int)threadIdx.x;
+        if (i < mine) {
+            const int n = listn[D.row_base + G.cta + i * G.ncta];
+            S.rown[threadIdx.x] = n;
+            if (n > kWarpRow) S.rowq[atomicAdd(&S.qn[0], 1)] = (unsigned short)threadIdx.x;
+            else if (n > 0) S.rowq[kThreads - 1 - atomicAdd(&S.qn[1], 1)] = (unsigned short)threadIdx.x;
+        }
+        __syncthreads();
+        const int nlong = S.qn[0], nshort = S.qn[1];
+        for (int q = 0; q < nlong; ++q) {
+            const int slot = S.rowq[q];
+            const int R = D.row_base + G.cta + (base + slot) * G.ncta;
+            if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], from_csr, tab, S);
+            else row_greedy(P, D, R, S.rown[slot], keytab, S);
+            __syncthreads();
+        }
+        for (int q = wid; q < nshort; q += kWarps) {
+            const int slot = S.rowq[kThreads - 1 - q];
+            const int R = D.row_base + G.cta + (base + slot) * G.ncta;
+            if (mode == MODE_PROP) warp_row_prop(P, D, R, S.rown[slot], from_csr, rows_live);
+            else warp_row_greedy(P, D, R, S.rown[slot]);
+        }
+        __syncthreads();
+    }
+    if (mode == MODE_PROP) {
+        if ((threadIdx.x & 31) == 0 && rows_live) atomicAdd(&S.rows_live, rows_live);
+        __syncthreads();
+        if (threadIdx.x == 0 && S.rows_live) atomicAdd(&rc.rows_live, S.rows_live);
+        if (threadIdx.x == 0 && S.maxlive > (unsigned)kWarpRow) atomicMax(&rc.maxlive, S.maxlive);
+    }
+}
+
+__device__ __forceinline__ void trace_mark(const Params& P, const GroupCtx& G, int w, int& tn, int mode, unsigned info,
+                                           unsigned long long t_win) {
+    if (P.trace && G.cta == 0 && threadIdx.x == 0 && tn < kTraceCap - 1) {
+        P.trace[(size_t)w * kTraceCap + tn] = make_uint2(((unsigned)mode << 24) | min(info, 0xFFFFFFu),
+                                                        (unsigned)(globaltimer_ns() - t_win));
+        ++tn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // one window, solved by the CTAs of one group
 // ---------------------------------------------------------------------------------------------------------------
-__device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
+__device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab, unsigned long long* keytab, TailSmem& T,
+                             BlockScratch& S) {
     const WinDesc D = P.win[w];
     WinState& ws = P.ws[w];
     const int rows = D.K + D.H;
     const int tiles = (D.M + kVarTile - 1) / kVarTile;
     const int gt = G.cta * kThreads + (int)threadIdx.x, gsz = G.ncta * kThreads;
+    const unsigned long long t_win = globaltimer_ns();
+    int tn = 0;
 
     // ---- W0: state init ------------------------------------------------------------------------------------------
     {
         const int mpad = ((max(D.M, 1) + kVarTile - 1) / kVarTile) * kVarTile;
-        uint32_t* st32 = reinterpret_cast<uint32_t*>(P.st + D.var_base);
-        for (int i = gt; i < mpad / 4; i += gsz) st32[i] = 0x03030303u;            // ST_NOTVAR
+        uint32_t* seen32 = reinterpret_cast<uint32_t*>(P.seen + D.var_base);
+        for (int i = gt; i < mpad / 4; i += gsz) seen32[i] = 0u;
         for (int i = gt; i < mpad; i += gsz) P.acc[D.var_base + i] = 0ull;
         for (int j = gt; j < D.H; j += gsz) P.ent_n[D.row_base + D.K + j] = 0;
         if (G.cta == 0) {
@@ -950,19 +1618,24 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         }
     }
     if (!group_sync(P, G)) return false;
+    trace_mark(P, G, w, tn, 10, 0, t_win);
     // ---- W1: keyframe rows ---------------------------------------------------------------------------------------
     for (int k = G.cta; k < D.K; k += G.ncta) {
-        w1_build_row(P, D, ws, k, tab, reinterpret_cast<unsigned*>(keytab), S);
+        w1_build_row(P, D, ws, k, tab, S);
         __syncthreads();
     }
     if (!group_sync(P, G)) return false;
+    trace_mark(P, G, w, tn, 11, 0, t_win);
     // ---- W2..W4: outside rows + round 1 ----------------------------------------------------------------------------
-    for (int t = G.cta; t < tiles; t += G.ncta) w2_count_outside(P, D, ws, t, S);
+    ObsTile& OT = *reinterpret_cast<ObsTile*>(keytab);             // shared scratch of the variable passes
+    const int stiles = (D.M + kSuper - 1) / kSuper;
+    for (int t = G.cta; t < stiles; t += G.ncta) w2_vars_and_outside_counts(P, D, ws, t, OT, S);
     if (!group_sync(P, G)) return false;
     if (G.cta == 0) w3_scan_outside(P, D, S);
     if (!group_sync(P, G)) return false;
+    trace_mark(P, G, w, tn, 13, 0, t_win);
     if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
-    for (int t = G.cta; t < tiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, S);
+    for (int t = G.cta; t < stiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, OT);
     if (!group_sync(P, G)) return false;
     if (w == P.gwin[P.grp[0].wbeg] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();
 
@@ -971,6 +1644,8 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     int rounds = 1, greedy_steps = 0, drop_rounds = 0, status = 0;
     int seq = 0, mode;
     bool from_csr = true;
+    int vbuf = 0, vcnt = (int)ws.rc[0].nfree;           // FREE list written by the last PROP phase
+    unsigned prev_sumdeg = ws.rc[0].sumdeg;             // its total number of row entries
     unsigned unc_final = 0, slack_final = 0;
     auto after_prop = [&](unsigned changed, unsigned nfree) {
         if (changed > 0 && rounds < P.max_rounds) return (int)MODE_PROP;
@@ -979,18 +1654,20 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         return (int)MODE_GREEDY;
     };
     mode = after_prop(ws.rc[0].changed, ws.rc[0].nfree);
+    trace_mark(P, G, w, tn, 14, ws.rc[0].nfree, t_win);
     while (mode != MODE_DONE) {
         ++seq;
         RoundCnt& rc = ws.rc[seq % 3];
         if (G.cta == 0 && threadIdx.x < (int)(sizeof(RoundCnt) / 4))
             reinterpret_cast<uint32_t*>(&ws.rc[(seq + 1) % 3])[threadIdx.x] = 0u;     // used by phase seq + 1
         // row phase
-        if (mode != MODE_FORCE && mode != MODE_EVALV) {
+        if (mode == MODE_PROP || mode == MODE_GREEDY) {
+            row_phase_lists(P, D, rc, G, mode, from_csr, tab, keytab, S);
+            if (!group_sync(P, G)) return false;
+        } else if (mode != MODE_FORCE && mode != MODE_EVALV) {
             for (int r = G.cta; r < rows; r += G.ncta) {
                 const int R = D.row_base + r;
                 switch (mode) {
-                case MODE_PROP: row_prop(P, D, rc, R, from_csr, tab, S); break;
-                case MODE_GREEDY: row_greedy(P, D, R, keytab, S); break;
                 case MODE_D1: row_d1_eval(P, D, rc, R, true, tab, S); break;
                 case MODE_D2: row_d2(P, D, R, tab, keytab, S); break;
                 case MODE_EVAL: row_d1_eval(P, D, rc, R, false, tab, S); break;
@@ -1002,11 +1679,37 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         }
         if (mode == MODE_PROP) from_csr = false;
         // variable phase
-        for (int t = G.cta; t < tiles; t += G.ncta) var_phase(P, D, ws, rc, mode, greedy_steps, t, S);
+        if (mode == MODE_PROP || mode == MODE_GREEDY || mode == MODE_FORCE) {
+            var_list_phase(P, D, ws, rc, mode, greedy_steps, P.vlist + (size_t)vbuf * P.Mpad + D.var_base, vcnt,
+                           P.vlist + (size_t)(vbuf ^ 1) * P.Mpad + D.var_base, G);
+        } else {
+            for (int t = G.cta; t < tiles; t += G.ncta) var_tile_phase(P, D, ws, rc, mode, t, S);
+        }
         if (!group_sync(P, G)) return false;
+        trace_mark(P, G, w, tn, mode, rc.nfree, t_win);
         // transition
         switch (mode) {
-        case MODE_PROP: ++rounds; mode = after_prop(rc.changed, rc.nfree); break;
+        case MODE_PROP: {
+            // the live lists written by this round's row phase are exact for the state BEFORE its variable phase, whose
+            // FREE list is the source list of that variable phase
+            const int src_buf = vbuf, src_cnt = vcnt;
+            const unsigned src_deg = prev_sumdeg;
+            ++rounds;
+            vbuf ^= 1;
+            vcnt = (int)rc.nfree;
+            prev_sumdeg = rc.sumdeg;
+            mode = after_prop(rc.changed, rc.nfree);
+            if ((mode == MODE_PROP || mode == MODE_GREEDY) && src_cnt <= P.tail_vars && src_deg <= (unsigned)P.tail_ents &&
+                rc.rows_live <= (unsigned)kTailRows && rc.maxlive <= (unsigned)kTailRowMax) {
+                if (G.cta == 0)
+                    tail_solve(P, D, ws, T, S, P.vlist + (size_t)src_buf * P.Mpad + D.var_base, src_cnt, mode, drop_mode, rounds,
+                               greedy_steps, status, w, tn, t_win);
+                if (!group_sync(P, G)) return false;
+                rounds = ws.t_rounds; greedy_steps = ws.t_greedy; status = ws.t_status;
+                mode = drop_mode;
+                trace_mark(P, G, w, tn, 8, (unsigned)rounds, t_win);
+            }
+        } break;
         case MODE_GREEDY: ++greedy_steps; ++rounds; mode = MODE_PROP; break;
         case MODE_FORCE: mode = drop_mode; break;
         case MODE_D1:
@@ -1035,6 +1738,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
                 hdr[13] = (uint32_t)drop_rounds;
                 hdr[14] = 0x4D535331u;      // "MSS1": slot written
                 hdr[15] = (uint32_t)w;
+                if (P.trace) P.trace[(size_t)w * kTraceCap + kTraceCap - 1] = make_uint2((unsigned)tn, (unsigned)(globaltimer_ns() - t_win));
             }
             mode = MODE_DONE;
         } break;
@@ -1047,11 +1751,17 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
 // ---------------------------------------------------------------------------------------------------------------
 // the persistent cooperative kernel
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) mss_persistent_kernel(const Params P) {
-    __shared__ unsigned tab[kCells];
-    __shared__ unsigned long long keytab[kCells];
-    __shared__ BlockScratch S;
-    __shared__ int s_abort;
+constexpr size_t kRowSmem = (size_t)kCells * 12;                                   // tab (u32) + keytab (u64)
+constexpr size_t kUnionSmem = ((kRowSmem > sizeof(TailSmem) ? kRowSmem : sizeof(TailSmem)) + 15) & ~(size_t)15;
+constexpr size_t kSmemBytes = kUnionSmem + ((sizeof(BlockScratch) + 15) & ~(size_t)15) + 16;
+
+__global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* tab = reinterpret_cast<unsigned*>(smem_raw);
+    unsigned long long* keytab = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kCells * 4);
+    TailSmem& T = *reinterpret_cast<TailSmem*>(smem_raw);                        // aliases tab / keytab
+    BlockScratch& S = *reinterpret_cast<BlockScratch*>(smem_raw + kUnionSmem);
+    int& s_abort = *reinterpret_cast<int*>(smem_raw + kSmemBytes - 16);
 
     if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl->t_start = globaltimer_ns();
     const int gi = P.cta_grp[blockIdx.x];
@@ -1066,7 +1776,7 @@ __global__ void __launch_bounds__(kThreads) mss_persistent_kernel(const Params P
     if (threadIdx.x == 0) s_abort = 0;
     __syncthreads();
     for (int wi = gd.wbeg; wi < gd.wend; ++wi) {
-        if (!solve_window(P, G, P.gwin[wi], tab, keytab, S)) break;
+        if (!solve_window(P, G, P.gwin[wi], tab, keytab, T, S)) break;
     }
     if (G.cta == 0 && threadIdx.x == 0) atomicMax(&P.ctrl->t_end, globaltimer_ns());
 }

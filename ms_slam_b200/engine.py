@@ -58,7 +58,7 @@ class mss_stats(C.Structure):
 SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_set_params", "mss_solve",
            "mss_solve_batch", "mss_comm_unique_id", "mss_comm_init", "mss_comm_destroy", "mss_host_alloc",
            "mss_host_free", "mss_device_alloc", "mss_device_free", "mss_memcpy_h2d", "mss_memcpy_d2h",
-           "mss_get_stats", "mss_stream"]
+           "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace"]
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load_library(path: str = LIB_PATH):
     lib.mss_get_stats.argtypes = [C.c_void_p, C.POINTER(mss_stats)]
     lib.mss_stream.argtypes = [C.c_void_p]
     lib.mss_stream.restype = C.c_void_p
+    lib.mss_debug_trace.argtypes = [C.c_void_p, C.c_int32]
+    lib.mss_debug_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
     _lib = lib
     return lib
 
@@ -238,6 +240,18 @@ class Engine:
 
     def pinned(self, shape, dtype) -> _Pinned:
         return _Pinned(self.lib, shape, dtype)
+
+    def trace(self, enable=True):
+        self._check(self.lib.mss_debug_trace(self.handle, 1 if enable else 0))
+
+    def get_trace(self, local_window=0):
+        """[(phase, free_left, ns)] of one window of the last call (phase: 10..14 build steps, 1 PROP, 2 GREEDY, 3 FORCE,
+        4 D1, 5 D2, 6/7 EVAL)"""
+        buf = np.zeros(2 * 255, np.uint32)
+        n = self.lib.mss_debug_get_trace(self.handle, local_window, buf.ctypes.data, 255)
+        if n < 0:
+            raise MssError(n, "no trace (call trace(True) before solving)")
+        return [(int(buf[2 * i] >> 24), int(buf[2 * i] & 0xFFFFFF), int(buf[2 * i + 1])) for i in range(n)]
 
     # -- multi-GPU ------------------------------------------------------------------------------------------
     def unique_id(self) -> bytes:
