@@ -102,6 +102,7 @@ struct mss_handle {
     int rank = 0, nranks = 1;
     unsigned long long watchdog_ns = 20000000000ull;
     int tail_vars = 64, tail_ents = 256;
+    int group_ctas = 0;              // CTAs per window group; 0 = heuristic
     // stats
     mss_stats stats{};
     int64_t device_bytes = 0;
@@ -232,41 +233,20 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
     const int Rtot = (int)(Ktot + Htot);
 
-    // ---- groups: CTAs are split among the windows in proportion to their size; with more windows than CTAs every CTA
-    //      is a group of its own and works through a queue of windows (largest first, least-loaded group next) ----------
+    // ---- groups: the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest first), so a
+    //      group that draws a short solve simply takes the next window.  One window -> one group with the whole grid. ------
     const int max_grid = std::max(1, h->max_ctas_per_sm * h->sm_count);
-    const int ngroups = std::max(1, std::min(nl, max_grid));
-    std::vector<std::vector<int>> gw(ngroups);
-    std::vector<double> gload(ngroups, 0.0);
     auto work = [&](int i) { const mss_window_view& v = views[local[i]]; return 1.0 + (double)v.F + (double)v.O + 0.25 * (double)v.M; };
-    {
-        std::vector<int> order(nl);
-        for (int i = 0; i < nl; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
-        for (int i : order) {
-            int best = 0;
-            for (int g = 1; g < ngroups; ++g) if (gload[g] < gload[best]) best = g;
-            gw[best].push_back(i);
-            gload[best] += work(i);
-        }
-    }
-    std::vector<int> gcta(ngroups, 1);
-    if (nl > 0 && ngroups < max_grid) {
-        double total = 0.0;
-        for (double x : gload) total += x;
-        int used = ngroups;
-        for (int g = 0; g < ngroups; ++g) {
-            // a window cannot use more CTAs than it has rows or variable tiles
-            int cap = 1;
-            for (int i : gw[g]) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
-            const int want = (int)((double)(max_grid - ngroups) * gload[g] / std::max(total, 1.0));
-            gcta[g] = std::min(cap, 1 + want);
-            used += gcta[g] - 1;
-        }
-        (void)used;
-    }
-    int grid = 0;
-    for (int g = 0; g < ngroups; ++g) grid += gcta[g];
+    std::vector<int> order(nl);
+    for (int i = 0; i < nl; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
+    int cap = 1;        // a window cannot use more CTAs than it has rows or variable tiles
+    for (int i = 0; i < nl; ++i) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
+    int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(nl, 1));
+    gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
+    const int ngroups = std::max(1, std::min(std::max(nl, 1), max_grid / gsize));
+    std::vector<int> gcta(ngroups, gsize);
+    int grid = ngroups * gsize;
 
     int rc;
     const size_t off_grp = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16);
@@ -332,14 +312,12 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         var_base += (int)align_up((size_t)std::max(v.M, 1), mss::kVarTile);
     }
     {
-        int cta = 0, wpos = 0;
+        int cta = 0;
         for (int g = 0; g < ngroups; ++g) {
-            h_grp[g].cta0 = cta; h_grp[g].ncta = gcta[g];
-            h_grp[g].wbeg = wpos;
-            for (int i : gw[g]) h_gwin[wpos++] = i;
-            h_grp[g].wend = wpos;
+            h_grp[g].cta0 = cta; h_grp[g].ncta = gcta[g]; h_grp[g].pad_[0] = h_grp[g].pad_[1] = 0;
             for (int c = 0; c < gcta[g]; ++c) h_cta_grp[cta++] = g;
         }
+        for (int i = 0; i < nl; ++i) h_gwin[i] = order[i];
     }
     MSS_CUDA(h, cudaGetLastError());
     MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -513,6 +491,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if (const char* gc = getenv("MSS_GROUP_CTAS")) h->group_ctas = atoi(gc);
     if (const char* tv = getenv("MSS_TAIL_VARS")) h->tail_vars = atoi(tv);
     if (const char* te = getenv("MSS_TAIL_ENTS")) h->tail_ents = atoi(te);
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }

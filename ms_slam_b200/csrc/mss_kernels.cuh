@@ -94,14 +94,14 @@ struct WinState {
 };
 
 struct GroupDesc {
-    int cta0, ncta;      // CTAs [cta0, cta0 + ncta) work on this group's windows
-    int wbeg, wend;      // windows gwin[wbeg .. wend), solved one after the other
+    int cta0, ncta;      // CTAs [cta0, cta0 + ncta) form the group; groups pull windows from one queue (gwin order)
+    int pad_[2];
 };
 
 struct Ctrl {
     unsigned long long t_start, t_build, t_end;
     int abort;           // set by the watchdog: a barrier waited longer than watchdog_ns
-    int pad_;
+    unsigned queue;      // next position of gwin[] to hand out
 };
 
 struct Params {
@@ -1637,7 +1637,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
     for (int t = G.cta; t < stiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, OT);
     if (!group_sync(P, G)) return false;
-    if (w == P.gwin[P.grp[0].wbeg] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();
+    if (w == P.gwin[0] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();
 
     // ---- phase machine (every CTA of the group takes the same decisions from the same counters) ----------------------
     const int drop_mode = (P.max_drop_rounds > 0) ? MODE_D1 : MODE_EVAL;
@@ -1775,7 +1775,12 @@ __global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Param
     G.t0 = globaltimer_ns();
     if (threadIdx.x == 0) s_abort = 0;
     __syncthreads();
-    for (int wi = gd.wbeg; wi < gd.wend; ++wi) {
+    // dynamic window queue: a group that finishes early takes the next window (largest windows are queued first)
+    while (true) {
+        if (G.cta == 0 && threadIdx.x == 0) G.bar[1] = atomicAdd(&P.ctrl->queue, 1u);
+        if (!group_sync(P, G)) break;
+        const unsigned wi = *(volatile unsigned*)&G.bar[1];
+        if (wi >= (unsigned)P.nwin) break;
         if (!solve_window(P, G, P.gwin[wi], tab, keytab, T, S)) break;
     }
     if (G.cta == 0 && threadIdx.x == 0) atomicMax(&P.ctrl->t_end, globaltimer_ns());

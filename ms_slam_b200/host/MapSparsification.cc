@@ -1,0 +1,334 @@
+// MapSparsification.cc -- the sparsifier thread of MS-SLAM on the B200 engine.
+//
+// Behaviour kept from the reference (/root/reference/src/MapSparsification.cc), by line:
+//   :4-21    constructor reads Sparsification.N / Lambda / GridLambda / WindowLength and starts the solver environment
+//   :23-56   Run(): poll every 3 ms; when more than 10 keyframes wait, take the oldest <= WindowLength and sparsify them;
+//            mbStopped is false only while a window is being processed; on finish, sparsify every keyframe that is not
+//            sparsified yet and call EraseBadDescriptor on each
+//   :159-166 every variable map point whose solution value is 0 gets SetBadFlag()
+//   :168-170 every window keyframe is forwarded to LoopClosing::InsertSparsifiedKeyFrame
+//   :173-199 FIFO queue under mMutexNewKFs, trigger size > 10, inertial gate on Map::GetIniertialBA2
+//   :205-241 stop / release / finish handshakes under mMutexStop / mMutexFinish
+// New: Sparsifying() = FlattenWindow (one walk of the pointer graph) -> mss_solve (libmss, CUDA) -> apply the bitmask.
+// Fail-safe: if the engine is unavailable or a solve fails, no map point is deleted (deleting is irreversible) and the
+// keyframes are still forwarded, so the SLAM pipeline keeps running with an unsparsified window.
+#include "MapSparsification.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <thread>
+#include <unordered_map>
+
+namespace ORB_SLAM3 {
+
+using std::shared_ptr;
+using std::vector;
+typedef std::chrono::steady_clock Clock;
+static double MsSince(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// settings
+// ---------------------------------------------------------------------------------------------------------------------
+bool ReadSparsificationSettings(const std::string& path, SparsificationSettings& s) {
+    std::ifstream in(path.c_str());
+    if (!in) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line.erase(hash);
+        const size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        auto trim = [](std::string t) {
+            const char* ws = " \t\r\n\"";
+            const size_t a = t.find_first_not_of(ws), b = t.find_last_not_of(ws);
+            return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
+        };
+        const std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+        if (val.empty()) continue;
+        const double v = std::atof(val.c_str());
+        if (key == "Sparsification.N") s.N = (int)v;
+        else if (key == "Sparsification.Lambda") s.Lambda = (float)v;
+        else if (key == "Sparsification.GridLambda") s.GridLambda = (float)v;
+        else if (key == "Sparsification.WindowLength") s.WindowLength = (int)v;
+        else if (key == "Sparsification.NonLocalKF") s.NonLocalKF = (int)v;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// flatten: pointer graph -> mss_window_view
+// ---------------------------------------------------------------------------------------------------------------------
+mss_window_view WindowSnapshot::View() const {
+    mss_window_view v;
+    v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)mp_obs_kf.size();
+    v.memory = MSS_MEM_HOST;
+    v.feat_ptr = feat_ptr.data(); v.feat_mp = feat_mp.data(); v.feat_cell = feat_cell.data();
+    v.mp_nobs = mp_nobs.data(); v.mp_obs_ptr = mp_obs_ptr.data(); v.mp_obs_kf = mp_obs_kf.data();
+    v.okf_total = okf_total.data();
+    return v;
+}
+
+void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int nId, WindowSnapshot& out) {
+    const Clock::time_point t0 = Clock::now();
+    const int K = (int)vpKFs.size();
+    out.K = K; out.H = 0;
+    out.feat_ptr.assign(1, 0);
+    out.feat_mp.clear(); out.feat_cell.clear(); out.mp_nobs.clear(); out.is_var.clear();
+    out.mp_obs_ptr.assign(1, 0); out.mp_obs_kf.clear(); out.okf_total.clear();
+    out.vpMapPoints.clear(); out.vpOutsideKFs.clear();
+
+    // window membership first (the reference stamps inside its second pass, :81; observations are classified with it, :132)
+    std::unordered_map<const KeyFrame*, int> windowIndex;
+    windowIndex.reserve((size_t)K * 2);
+    for (int k = 0; k < K; ++k) {
+        vpKFs[k]->mnMapSaprsificationId = nId;
+        windowIndex.emplace(vpKFs[k].get(), k);          // a keyframe queued twice keeps its first position
+    }
+
+    // keyframe side: slots and cells (passes 1 and 2, :67-123)
+    for (int k = 0; k < K; ++k) {
+        const vector<shared_ptr<MapPoint>> vMPs = vpKFs[k]->GetMapPointMatches();
+        const size_t base = out.feat_mp.size(), n = vMPs.size();
+        out.feat_mp.resize(base + n, -1);
+        out.feat_cell.resize(base + n, (uint16_t)MSS_CELL_NONE);
+        for (size_t i = 0; i < n; ++i) {
+            const shared_ptr<MapPoint>& pMP = vMPs[i];
+            if (!pMP || pMP->isBad()) continue;
+            if (pMP->mnMapSparsificationId != nId) {
+                pMP->mnMapSparsificationId = nId;
+                pMP->mnIndexForSparsification = out.vpMapPoints.size();
+                out.vpMapPoints.push_back(pMP);
+                out.mp_nobs.push_back(pMP->Observations());
+                out.is_var.push_back(0);
+            }
+            out.feat_mp[base + i] = (int32_t)pMP->mnIndexForSparsification;
+        }
+        const auto& grid = vpKFs[k]->GetFeatureGrids();
+        for (size_t col = 0; col < grid.size(); ++col)
+            for (size_t row = 0; row < grid[col].size(); ++row)
+                for (size_t i : grid[col][row]) {
+                    if (i >= n) continue;
+                    out.feat_cell[base + i] = (uint16_t)(col * MSS_GRID_ROWS + row);
+                    if (out.feat_mp[base + i] >= 0) out.is_var[out.feat_mp[base + i]] = 1;
+                }
+        out.feat_ptr.push_back((int32_t)out.feat_mp.size());
+    }
+
+    // map-point side: observations of the variables (pass 3, :125-142); outside keyframes in discovery order for now
+    std::unordered_map<const KeyFrame*, int> outsideIndex;
+    const size_t M = out.vpMapPoints.size();
+    for (size_t p = 0; p < M; ++p) {
+        if (out.is_var[p]) {
+            const auto obs = out.vpMapPoints[p]->GetObservations();
+            for (const auto& kv : obs) {
+                const KeyFrame* pKF = kv.first.get();
+                if (kv.first->mnMapSaprsificationId == nId) {
+                    const auto it = windowIndex.find(pKF);
+                    if (it != windowIndex.end()) out.mp_obs_kf.push_back(it->second);
+                } else {
+                    auto it = outsideIndex.find(pKF);
+                    if (it == outsideIndex.end()) {
+                        it = outsideIndex.emplace(pKF, (int)out.vpOutsideKFs.size()).first;
+                        out.vpOutsideKFs.push_back(kv.first);
+                    }
+                    out.mp_obs_kf.push_back(K + it->second);
+                }
+            }
+        }
+        out.mp_obs_ptr.push_back((int32_t)out.mp_obs_kf.size());
+    }
+    // deterministic order of the outside rows: by keyframe id (the reference orders by pointer value, :125-126)
+    const int H = (int)out.vpOutsideKFs.size();
+    vector<int> order(H), rank(H);
+    for (int j = 0; j < H; ++j) order[j] = j;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return out.vpOutsideKFs[a]->mnId < out.vpOutsideKFs[b]->mnId; });
+    vector<shared_ptr<KeyFrame>> sorted(H);
+    for (int j = 0; j < H; ++j) { rank[order[j]] = j; sorted[j] = out.vpOutsideKFs[order[j]]; }
+    out.vpOutsideKFs.swap(sorted);
+    for (int32_t& kf : out.mp_obs_kf) if (kf >= K) kf = K + rank[kf - K];
+    out.H = H;
+    out.okf_total.resize(H);
+    for (int j = 0; j < H; ++j) out.okf_total[j] = out.vpOutsideKFs[j]->GetNumberMPs();      // :146
+    out.flatten_ms = MsSince(t0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the thread object
+// ---------------------------------------------------------------------------------------------------------------------
+MapSparsification::MapSparsification(const std::string& strSettingsFile, Atlas* pAtlas, bool bInertial)
+    : mnMinNum(0), mbFinishRequested(false), mbFinished(true), mnId(0), mbStopRequested(false), mbStopped(true),
+      mpEngine(nullptr), mfLambda(0.f), mfGridLambda(0.f), mnWindowLength(0), mpLoopClosing(nullptr), mpAtlas(pAtlas),
+      mbInertial(bInertial) {
+    SparsificationSettings s;
+    if (!ReadSparsificationSettings(strSettingsFile, s))
+        std::cerr << "MapSparsification: cannot read settings file " << strSettingsFile << std::endl;
+    mnMinNum = s.N;
+    mfLambda = s.Lambda;
+    mfGridLambda = s.GridLambda;
+    mnWindowLength = s.WindowLength;
+    std::cout << std::endl << "*****************************************" << std::endl;
+    std::cout << "Map Sparsification settings: " << std::endl;
+    std::cout << "Sparsification.N: " << mnMinNum << std::endl;
+    std::cout << "Sparsification.Lambda: " << mfLambda << std::endl;
+    std::cout << "Sparsification.GridLambda: " << mfGridLambda << std::endl;
+    std::cout << "Sparsification.WindowLength: " << mnWindowLength << std::endl;
+    std::cout << "*****************************************" << std::endl;
+    mss_config cfg{};
+    const char* dev = std::getenv("MSS_DEVICE");
+    cfg.device = dev ? std::atoi(dev) : 0;
+    cfg.min_points = mnMinNum;
+    cfg.lambda = mfLambda;
+    cfg.grid_lambda = mfGridLambda;
+    const int rc = mss_create(&cfg, &mpEngine);
+    if (rc != MSS_OK) {
+        mpEngine = nullptr;
+        std::cerr << "MapSparsification: mss_create failed (" << rc << "): no usable CUDA device; windows will be forwarded "
+                     "unsparsified (there is no CPU solver)" << std::endl;
+    }
+}
+
+MapSparsification::~MapSparsification() {
+    if (mpEngine) mss_destroy(mpEngine);
+}
+
+void MapSparsification::Run() {
+    {
+        std::unique_lock<std::mutex> lock(mMutexFinish);
+        mbFinished = false;
+    }
+    while (true) {
+        if (CheckNewKeyFrames()) {
+            {
+                std::unique_lock<std::mutex> lock(mMutexStop);
+                mbStopped = false;
+            }
+            vector<shared_ptr<KeyFrame>> vpKFs = GetLastestKeyFrames();
+            Sparsifying(vpKFs);
+            {
+                std::unique_lock<std::mutex> lock(mMutexStop);
+                mbStopped = true;
+            }
+        }
+        if (CheckFinish()) {
+            // final flush: one window with every keyframe that has not been sparsified yet
+            vector<shared_ptr<KeyFrame>> vRemain;
+            for (const shared_ptr<KeyFrame>& pKF : mpAtlas->GetAllKeyFrames())
+                if (!pKF->mbSparsified) vRemain.push_back(pKF);
+            Sparsifying(vRemain);
+            for (const shared_ptr<KeyFrame>& pKF : vRemain) pKF->EraseBadDescriptor();
+            break;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(3000));
+    }
+    SetFinish();
+}
+
+void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
+    mnId++;
+    WindowReport rep;
+    FlattenWindow(vpKFs, mnId, mLast);
+    const size_t M = mLast.vpMapPoints.size();
+    rep.K = mLast.K; rep.H = mLast.H; rep.M = (int)M; rep.flatten_ms = mLast.flatten_ms;
+    mKeepBits.assign((M + 31) / 32, 0xFFFFFFFFu);
+
+    Clock::time_point t0 = Clock::now();
+    int rc = MSS_E_CUDA;
+    mss_result res{};
+    if (mpEngine) {
+        // the yaml values can be changed through the public member between windows, like upstream
+        mss_set_params(mpEngine, mnMinNum, mfLambda, mfGridLambda);
+        const mss_window_view view = mLast.View();
+        res.keep_bits = mKeepBits.data();
+        rc = mss_solve(mpEngine, &view, &res);
+        if (rc != MSS_OK && rc != MSS_E_NOCONVERGE) {
+            std::cerr << "MapSparsification: window " << mnId << " not sparsified: " << mss_last_error(mpEngine) << std::endl;
+            std::fill(mKeepBits.begin(), mKeepBits.end(), 0xFFFFFFFFu);
+        }
+    }
+    rep.status = rc; rep.solve_ms = MsSince(t0);
+    rep.n_vars = res.n_vars; rep.n_kept = res.n_kept; rep.rounds = res.rounds; rep.objective = res.objective;
+
+    // hand-back: delete what the selection dropped (only variables can have a 0 bit)
+    t0 = Clock::now();
+    for (size_t p = 0; p < M; ++p) {
+        if (!mLast.is_var[p]) continue;
+        if (!((mKeepBits[p >> 5] >> (p & 31)) & 1u)) {
+            mLast.vpMapPoints[p]->SetBadFlag();
+            ++rep.n_deleted;
+        }
+    }
+    if (mpLoopClosing)
+        for (const shared_ptr<KeyFrame>& pKF : vpKFs) mpLoopClosing->InsertSparsifiedKeyFrame(pKF);
+    rep.apply_ms = MsSince(t0);
+    std::unique_lock<std::mutex> lock(mMutexReports);
+    mReports.push_back(rep);
+}
+
+vector<MapSparsification::WindowReport> MapSparsification::GetReports() {
+    std::unique_lock<std::mutex> lock(mMutexReports);
+    return mReports;
+}
+
+vector<shared_ptr<KeyFrame>> MapSparsification::GetLastestKeyFrames() {
+    std::unique_lock<std::mutex> lock(mMutexNewKFs);
+    const size_t take = std::min(mvpNewKeyFrames.size(), (size_t)std::max(mnWindowLength, 0));
+    vector<shared_ptr<KeyFrame>> vKFs(mvpNewKeyFrames.begin(), mvpNewKeyFrames.begin() + take);
+    mvpNewKeyFrames.erase(mvpNewKeyFrames.begin(), mvpNewKeyFrames.begin() + take);
+    return vKFs;
+}
+
+void MapSparsification::InsertKeyFrame(shared_ptr<KeyFrame> pKF) {
+    std::unique_lock<std::mutex> lock(mMutexNewKFs);
+    mvpNewKeyFrames.push_back(pKF);
+}
+
+bool MapSparsification::CheckNewKeyFrames() {
+    std::unique_lock<std::mutex> lock2(mMutexStop);
+    std::unique_lock<std::mutex> lock(mMutexNewKFs);
+    return mvpNewKeyFrames.size() > 10 && !mbStopRequested &&
+           (!mbInertial || mvpNewKeyFrames[0]->GetMap()->GetIniertialBA2());
+}
+
+void MapSparsification::SetLoopClosing(LoopClosing* pLoopClosing) { mpLoopClosing = pLoopClosing; }
+
+void MapSparsification::RequestStop() {
+    std::unique_lock<std::mutex> lock2(mMutexStop);
+    mbStopRequested = true;
+    std::cout << "Map Sparsification STOP" << std::endl;
+}
+
+void MapSparsification::Release() {
+    std::unique_lock<std::mutex> lock2(mMutexStop);
+    mbStopRequested = false;
+    std::cout << "Map Sparsification RELEASE" << std::endl;
+}
+
+bool MapSparsification::isStopped() {
+    std::unique_lock<std::mutex> lock2(mMutexStop);
+    return mbStopped;
+}
+
+void MapSparsification::RequestFinish() {
+    std::unique_lock<std::mutex> lock(mMutexFinish);
+    mbFinishRequested = true;
+}
+
+bool MapSparsification::CheckFinish() {
+    std::unique_lock<std::mutex> lock(mMutexFinish);
+    return mbFinishRequested;
+}
+
+void MapSparsification::SetFinish() {
+    std::unique_lock<std::mutex> lock(mMutexFinish);
+    mbFinished = true;
+}
+
+bool MapSparsification::isFinished() {
+    std::unique_lock<std::mutex> lock(mMutexFinish);
+    return mbFinished;
+}
+
+}  // namespace ORB_SLAM3

@@ -1,0 +1,113 @@
+// MapSparsification.h -- host-side mirror of MS-SLAM's sparsifier thread, B200 engine underneath.
+//
+// Same class, same namespace, same public members as /root/reference/include/MapSparsification.h:26-70, so the call
+// sites in System (src/System.cc:159-162,460-466), LocalMapping (src/LocalMapping.cc:264), Tracking
+// (src/Tracking.cc:3626) and LoopClosing (src/LoopClosing.cc:930,955,1162,2441) compile unchanged.  What differs is
+// private: the GUROBI environment member (`GRBEnv mGRBEnv`, :59) is an opaque `mss_handle*` of libmss (include/mss.h),
+// and Sparsifying() snapshots the window into a flat view, calls mss_solve and applies the returned keep-bitmask instead
+// of building a GRBModel.
+#pragma once
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mss.h"
+#ifdef MSS_WITH_ORBSLAM3_HEADERS      // building inside an MS-SLAM checkout
+#include "KeyFrame.h"
+#include "Map.h"
+#include "Atlas.h"
+#include "LoopClosing.h"
+#else
+#include "SlamShims.h"
+#endif
+
+namespace ORB_SLAM3 {
+
+// Flat snapshot of one window: exactly the arrays of mss_window_view plus the objects the bits refer to.
+struct WindowSnapshot {
+    std::vector<int32_t> feat_ptr, feat_mp, mp_nobs, mp_obs_ptr, mp_obs_kf, okf_total;
+    std::vector<uint16_t> feat_cell;
+    std::vector<uint8_t> is_var;                              // map point reachable through a grid cell (an ILP variable)
+    std::vector<std::shared_ptr<MapPoint>> vpMapPoints;       // table order = mnIndexForSparsification = bit position
+    std::vector<std::shared_ptr<KeyFrame>> vpOutsideKFs;      // ordered by KeyFrame::mnId
+    int K = 0, H = 0;
+    double flatten_ms = 0.0;
+    mss_window_view View() const;
+};
+
+// Passes 1-3 of the reference (MapSparsification.cc:66-151) as ONE walk over the pointer graph that only records what it
+// sees; stamps mnMapSaprsificationId / mnMapSparsificationId / mnIndexForSparsification like the reference (:81,93,98).
+void FlattenWindow(const std::vector<std::shared_ptr<KeyFrame>>& vpKFs, long unsigned int nId, WindowSnapshot& out);
+
+struct SparsificationSettings {
+    int N = 0, WindowLength = 0, NonLocalKF = 0;
+    float Lambda = 0.f, GridLambda = 0.f;
+};
+// Reads the `Sparsification.*` keys of an ORB-SLAM3 settings file (OpenCV-YAML subset: `key: value` lines); missing keys
+// stay 0 exactly like cv::FileNode -> int/float does upstream (MapSparsification.cc:8-12).
+bool ReadSparsificationSettings(const std::string& path, SparsificationSettings& s);
+
+class MapSparsification {
+public:
+    MapSparsification(const std::string& strSettingsFile, Atlas* pAtlas, bool bInertial);
+    ~MapSparsification();
+
+    void Run();
+
+    bool CheckNewKeyFrames();
+
+    void InsertKeyFrame(std::shared_ptr<KeyFrame> pKF);
+
+    void SetLoopClosing(LoopClosing* pLoopClosing);
+
+    std::vector<std::shared_ptr<KeyFrame>> GetLastestKeyFrames();
+
+    bool isStopped();
+    void RequestStop();
+    void Release();
+    void RequestFinish();
+    bool isFinished();
+    int mnMinNum;
+
+    // ---- additions (not in the reference; read-only diagnostics) -------------------------------------------------------
+    struct WindowReport {
+        int status = 0;                 // mss_status of the solve (0 ok); on error every map point was kept
+        int K = 0, H = 0, M = 0, n_vars = 0, n_kept = 0, n_deleted = 0, rounds = 0;
+        double objective = 0.0, flatten_ms = 0.0, solve_ms = 0.0, apply_ms = 0.0;
+    };
+    std::vector<WindowReport> GetReports();
+    const WindowSnapshot& LastSnapshot() const { return mLast; }      // valid while the thread is stopped
+    bool EngineReady() const { return mpEngine != nullptr; }
+
+private:
+    void Sparsifying(std::vector<std::shared_ptr<KeyFrame>>& vpKFs);
+    bool CheckFinish();
+    void SetFinish();
+
+    bool mbFinishRequested;
+    bool mbFinished;
+    std::mutex mMutexFinish;
+
+    long unsigned int mnId;
+    bool mbStopRequested;
+    bool mbStopped;
+
+    mss_handle* mpEngine;               // replaces GRBEnv mGRBEnv (include/MapSparsification.h:59)
+    float mfLambda;
+    float mfGridLambda;
+    int mnWindowLength;
+    std::vector<std::shared_ptr<KeyFrame>> mvpNewKeyFrames;
+    std::mutex mMutexNewKFs;
+    std::mutex mMutexStop;
+    LoopClosing* mpLoopClosing;
+    Atlas* mpAtlas;
+    bool mbInertial;
+
+    WindowSnapshot mLast;
+    std::vector<uint32_t> mKeepBits;
+    std::vector<WindowReport> mReports;
+    std::mutex mMutexReports;
+};
+
+}  // namespace ORB_SLAM3

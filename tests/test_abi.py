@@ -69,3 +69,11 @@ def test_product_code_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_host_mirror_library_exports(build_native):
+    """libmss_host.so (C++ MapSparsification mirror + harness) builds, loads next to libmss.so and exports its harness."""
+    from ms_slam_b200 import host_mirror
+    lib = host_mirror.load_library()
+    for name in host_mirror.SYMBOLS:
+        assert hasattr(lib, name), f"libmss_host.so does not export {name}"

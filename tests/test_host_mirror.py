@@ -1,0 +1,198 @@
+"""The C++ MapSparsification mirror (ms_slam_b200/host/): drop-in boundary of SURVEY.md section 8b.
+
+CPU tests: the pointer-graph -> flat-view walk (FlattenWindow = passes 1-3 of /root/reference/src/MapSparsification.cc:66-151)
+reproduces the view the graph was built from; settings reader; non-local counter; fail-safe behaviour without a GPU.
+GPU tests: the sparsifier thread driven like System / LocalMapping / LoopClosing drive it upstream deletes exactly the map
+points the engine's bitmask says, forwards every keyframe, honours the stop / finish handshakes."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import LAM, GLAM
+from ms_slam_b200 import make_view, msgen, CELL_NONE
+
+
+@pytest.fixture(scope="module")
+def hm(build_native):
+    from ms_slam_b200 import host_mirror
+    host_mirror.load_library()
+    return host_mirror
+
+
+def check_roundtrip(view, flat, mp_ids, okf_ids, is_var):
+    """flat view == original view up to the renumbering of the map-point table / outside keyframes"""
+    K = view.K
+    assert flat.K == K and np.array_equal(flat.feat_ptr, view.feat_ptr)
+    valid = view.feat_mp >= 0
+    assert np.array_equal(flat.feat_mp >= 0, valid)
+    assert np.array_equal(mp_ids[flat.feat_mp[valid]], view.feat_mp[valid])
+    assert np.array_equal(flat.feat_cell, view.feat_cell)
+    assert np.unique(mp_ids).size == mp_ids.size                       # each map point has exactly one table entry
+    assert set(mp_ids.tolist()) == set(view.feat_mp[valid].tolist())   # and the table holds exactly the points seen in valid slots
+    assert np.array_equal(flat.mp_nobs, view.mp_nobs[mp_ids])
+    # discovery order: keyframes in window order, slots in index order
+    first = {}
+    for s in np.nonzero(valid)[0]:
+        first.setdefault(int(view.feat_mp[s]), len(first))
+    assert [first[int(p)] for p in mp_ids] == list(range(mp_ids.size))
+    grid = valid & (view.feat_cell != CELL_NONE)
+    var_orig = np.zeros(view.M, bool)
+    var_orig[view.feat_mp[grid]] = True
+    assert np.array_equal(is_var, var_orig[mp_ids])
+    # observations: complete for variables, omitted for the rest (the engine only reads those of variables)
+    cnt_all = np.zeros(view.H, np.int64)
+    for p in range(view.M):
+        for kf in view.mp_obs_kf[view.mp_obs_ptr[p]:view.mp_obs_ptr[p + 1]]:
+            if kf >= K:
+                cnt_all[kf - K] += 1
+    seen_outside = set()
+    for q, p in enumerate(mp_ids):
+        got = flat.mp_obs_kf[flat.mp_obs_ptr[q]:flat.mp_obs_ptr[q + 1]]
+        if not is_var[q]:
+            assert got.size == 0
+            continue
+        got = sorted(int(k) if k < K else int(okf_ids[k - K]) for k in got)      # outside keyframe ids are K + original j
+        exp = sorted(int(k) for k in view.mp_obs_kf[view.mp_obs_ptr[p]:view.mp_obs_ptr[p + 1]])
+        assert got == exp
+        seen_outside.update(k for k in got if k >= K)
+    assert sorted(okf_ids.tolist()) == sorted(seen_outside) and list(okf_ids) == sorted(okf_ids)    # ordered by keyframe id
+    for j, kid in enumerate(okf_ids):
+        jj = int(kid) - K
+        assert flat.okf_total[j] == max(int(view.okf_total[jj]), int(cnt_all[jj]))              # GetNumberMPs() of that keyframe
+
+
+@pytest.mark.parametrize("name,seed,over", [("c1", 0, {}), ("live", 0, {}), ("live", 3, dict(M=1500, H=20)), ("c4", 1000, dict(M=3000))])
+def test_flatten_roundtrip(hm, name, seed, over):
+    view, N = msgen.make_config(name, seed, **over)
+    w = hm.World(view, N=N)
+    try:
+        flat, mp_ids, okf_ids, is_var = w.flatten_only()
+        flat.validate()
+        check_roundtrip(view, flat, mp_ids, okf_ids, is_var)
+    finally:
+        w.close()
+
+
+def test_flatten_quirks(hm):
+    # empty / bad slots, keypoints outside the grid, a point in two slots of one keyframe, an outside keyframe
+    view = make_view(2, [[(0, 0), (None, 3), (1, None), (2, 7), (2, 9)], [(2, 100), (3, 3071), (None, None)]],
+                     [4, 6, 8, 5], outside=[[2, 3], [1]], okf_total=[5, 2])
+    w = hm.World(view, N=2)
+    try:
+        flat, mp_ids, okf_ids, is_var = w.flatten_only()
+        check_roundtrip(view, flat, mp_ids, okf_ids, is_var)
+        assert mp_ids.tolist() == [0, 1, 2, 3] and is_var.tolist() == [True, False, True, True]
+        assert okf_ids.tolist() == [2]                 # the second outside keyframe is only seen by a non-variable: no row
+    finally:
+        w.close()
+
+
+def test_settings_reader_and_nonlocal_counter(hm):
+    view, N = msgen.make_config("c1", 0)
+    w = hm.World(view, N=75, lam=437.5, grid_lam=9.5, window_length=30, non_local=15)
+    try:
+        assert w.nonlocal_after(0) == 15              # KeyFrame::UpdateCountInLocalMapping (src/KeyFrame.cc:980-997)
+        assert w.nonlocal_after(1) == 15
+    finally:
+        w.close()
+
+
+def test_without_gpu_keeps_every_point(hm):
+    """No CUDA device -> no engine -> fail-safe: nothing is deleted, keyframes are still forwarded (SURVEY 8b error row)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    view, N = msgen.make_config("c1", 1)
+    w = hm.World(view, N=N)
+    try:
+        assert not w.engine_ready()
+        w.start()
+        w.feed(0, view.K)
+        assert w.wait_forwarded(view.K) == 0
+        assert w.forwarded_ids() == list(range(view.K))
+        assert not w.bad_flags().any()
+        assert w.reports()[0]["status"] < 0 and w.reports()[0]["n_deleted"] == 0
+        w.consume()
+        assert w.finish() == 0
+    finally:
+        w.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed,over", [("c1", 0, {}), ("live", 0, {}), ("live", 5, dict(M=1500, H=20))])
+def test_thread_flow_matches_engine(hm, name, seed, over):
+    from ms_slam_b200.engine import Engine
+    from oracle import ilp_model as om
+    view, N = msgen.make_config(name, seed, **over)
+    w = hm.World(view, N=N)
+    eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    try:
+        assert w.engine_ready()
+        w.start()
+        w.feed(0, 10)                                   # trigger is "more than 10 queued" (MapSparsification.cc:197)
+        assert w.wait_forwarded(1, timeout_ms=200) == -1 and w.forwarded_ids() == []
+        w.feed(10, view.K - 10)
+        assert w.wait_forwarded(view.K) == 0
+        assert w.forwarded_ids() == list(range(view.K))                  # every window keyframe, in window order (:168-170)
+        flat, mp_ids, okf_ids, is_var = w.snapshot(1)
+        check_roundtrip(view, flat, mp_ids, okf_ids, is_var)
+        ref = eng.solve(flat)                                            # the engine called directly on the same snapshot
+        bad = w.bad_flags()
+        exp_bad = np.zeros(view.M, bool)
+        exp_bad[mp_ids[~ref.keep]] = True
+        assert np.array_equal(bad, exp_bad)                              # SetBadFlag exactly where the bit is 0 (:159-166)
+        rep = w.reports()[0]
+        assert rep["status"] == 0 and rep["objective"] == ref.objective and rep["n_deleted"] == int((~ref.keep).sum())
+        # quality on the ORIGINAL view: rows satisfied, within 1 % of the LP bound of the reference ILP
+        model = om.build_model(view, N)
+        x = om.keep_to_x(model, ~bad)
+        assert om.rows_satisfied(model, x, N)[0]
+        assert om.objective(model, x, N, LAM, GLAM) <= 1.01 * om.solve_lp(view, N, LAM, GLAM, model=model).objective
+        # deleted points are gone from their keyframes and from the map (MapPoint.cc:227-255)
+        st = w.keyframe_state()
+        kept_slots = np.array([int((~bad[view.feat_mp[view.feat_ptr[k]:view.feat_ptr[k + 1]][view.feat_mp[view.feat_ptr[k]:view.feat_ptr[k + 1]] >= 0]]).sum())
+                               for k in range(view.K)])
+        assert np.array_equal(st[:view.K, 0], kept_slots)
+        # stop handshake of LoopClosing::CorrectLoop, consumer step, shutdown flush
+        assert w.stop_handshake() == 1
+        w.consume()
+        st = w.keyframe_state()
+        assert st[:view.K, 1].all() and (st[:view.K, 2] == 1).all()      # EraseBadDescriptor ran once per keyframe, mbSparsified
+        assert w.map_counts()["sparsified_keyframes"] == view.K
+        assert w.finish() == 0
+        assert len(w.reports()) == 2 and w.reports()[1]["K"] == 0        # nothing left for the final flush
+    finally:
+        eng.close()
+        w.close()
+
+
+@pytest.mark.gpu
+def test_final_flush_takes_all_unsparsified_keyframes(hm):
+    """RequestFinish with keyframes still queued: one window over every keyframe with !mbSparsified, then EraseBadDescriptor
+    (MapSparsification.cc:38-52); the outside keyframes of the fixture are already sparsified and stay outside."""
+    from ms_slam_b200.engine import Engine
+    view, N = msgen.make_config("live", 2)
+    w = hm.World(view, N=N, window_length=8)
+    eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    try:
+        w.start()
+        w.feed(0, 5)                                    # below the trigger: nothing happens until shutdown
+        assert w.finish() == 0
+        reps = w.reports()
+        assert len(reps) == 1 and reps[0]["K"] == view.K and reps[0]["H"] > 0
+        flat, mp_ids, okf_ids, is_var = w.snapshot(1)
+        ref = eng.solve(flat)
+        exp_bad = np.zeros(view.M, bool)
+        exp_bad[mp_ids[~ref.keep]] = True
+        assert np.array_equal(w.bad_flags(), exp_bad)
+        st = w.keyframe_state()
+        assert st[:view.K, 1].all() and (st[:view.K, 2] == 1).all()
+        assert w.forwarded_ids() == list(range(view.K))
+        w.consume()                                     # quirk A.5.5: the same keyframes reach LoopClosing too -> second call
+        assert (w.keyframe_state()[:view.K, 2] == 2).all()
+    finally:
+        eng.close()
+        w.close()
