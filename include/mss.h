@@ -114,6 +114,8 @@ typedef struct mss_stats {
     int64_t device_bytes;      /* device scratch currently owned */
     int32_t grid_ctas;         /* CTAs of the persistent kernel in the last call */
     int32_t sm_count;
+    int64_t last_row_entries;  /* work accounting of the last call: CSR / live-list entries read by all row phases after the build */
+    int64_t last_var_visits;   /* ... and map points visited by all variable phases after round 1 */
 } mss_stats;
 
 int         mss_version(void);

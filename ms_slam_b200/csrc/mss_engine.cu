@@ -440,6 +440,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     h->stats.last_d2h_bytes = d2h;
     h->stats.device_bytes = h->device_bytes;
     h->stats.grid_ctas = grid;
+    h->stats.last_row_entries = nl > 0 ? (int64_t)h->h_ctrl->row_entries : 0;
+    h->stats.last_var_visits = nl > 0 ? (int64_t)h->h_ctrl->var_visits : 0;
     h->stats.last_total_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
     return ret;
 }

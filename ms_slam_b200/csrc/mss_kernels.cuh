@@ -102,6 +102,8 @@ struct Ctrl {
     unsigned long long t_start, t_build, t_end;
     int abort;           // set by the watchdog: a barrier waited longer than watchdog_ns
     unsigned queue;      // next position of gwin[] to hand out
+    unsigned long long row_entries;   // list / CSR entries read by the row phases of this launch (work accounting)
+    unsigned long long var_visits;    // map points visited by the variable phases of this launch
 };
 
 struct Params {
@@ -174,6 +176,7 @@ struct BlockScratch {
     int rown[kThreads];
     int qn[2];
     unsigned rows_live, maxlive;
+    unsigned long long work;   // entries read by this CTA in the current row phase
     int tcnt[4];             // tail: changed, nfree
 };
 
@@ -1546,7 +1549,7 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
     const int* listn = from_csr ? P.ent_n : P.live_n;
     const int wid = threadIdx.x >> 5;
     unsigned rows_live = 0;
-    if (threadIdx.x == 0) { S.rows_live = 0u; S.maxlive = 0u; }
+    if (threadIdx.x == 0) { S.rows_live = 0u; S.maxlive = 0u; S.work = 0ull; }
     for (int base = 0; base < mine; base += kThreads) {
         if (threadIdx.x < 2) S.qn[threadIdx.x] = 0;
         __syncthreads();
@@ -1559,6 +1562,12 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
         }
         __syncthreads();
         const int nlong = S.qn[0], nshort = S.qn[1];
+        if (threadIdx.x == 0) {
+            unsigned long long wsum = 0;
+            for (int q = 0; q < nlong; ++q) wsum += (unsigned long long)S.rown[S.rowq[q]];
+            for (int q = 0; q < nshort; ++q) wsum += (unsigned long long)S.rown[S.rowq[kThreads - 1 - q]];
+            S.work += wsum;
+        }
         for (int q = 0; q < nlong; ++q) {
             const int slot = S.rowq[q];
             const int R = D.row_base + G.cta + (base + slot) * G.ncta;
@@ -1574,6 +1583,7 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0 && S.work) atomicAdd(&P.ctrl->row_entries, S.work);
     if (mode == MODE_PROP) {
         if ((threadIdx.x & 31) == 0 && rows_live) atomicAdd(&S.rows_live, rows_live);
         __syncthreads();
@@ -1665,8 +1675,10 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
             row_phase_lists(P, D, rc, G, mode, from_csr, tab, keytab, S);
             if (!group_sync(P, G)) return false;
         } else if (mode != MODE_FORCE && mode != MODE_EVALV) {
+            unsigned long long wsum = 0;
             for (int r = G.cta; r < rows; r += G.ncta) {
                 const int R = D.row_base + r;
+                wsum += (unsigned long long)P.ent_n[R];
                 switch (mode) {
                 case MODE_D1: row_d1_eval(P, D, rc, R, true, tab, S); break;
                 case MODE_D2: row_d2(P, D, R, tab, keytab, S); break;
@@ -1675,10 +1687,13 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
                 }
                 __syncthreads();
             }
+            if (threadIdx.x == 0 && wsum) atomicAdd(&P.ctrl->row_entries, wsum);
             if (!group_sync(P, G)) return false;
         }
         if (mode == MODE_PROP) from_csr = false;
         // variable phase
+        if (G.cta == 0 && threadIdx.x == 0)
+            atomicAdd(&P.ctrl->var_visits, (unsigned long long)((mode == MODE_PROP || mode == MODE_GREEDY || mode == MODE_FORCE) ? vcnt : D.M));
         if (mode == MODE_PROP || mode == MODE_GREEDY || mode == MODE_FORCE) {
             var_list_phase(P, D, ws, rc, mode, greedy_steps, P.vlist + (size_t)vbuf * P.Mpad + D.var_base, vcnt,
                            P.vlist + (size_t)(vbuf ^ 1) * P.Mpad + D.var_base, G);

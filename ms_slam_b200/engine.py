@@ -51,7 +51,8 @@ class mss_result(C.Structure):
 class mss_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("solves", C.c_int64), ("last_device_ms", C.c_double),
                 ("last_total_ms", C.c_double), ("last_h2d_bytes", C.c_int64), ("last_d2h_bytes", C.c_int64),
-                ("device_bytes", C.c_int64), ("grid_ctas", C.c_int32), ("sm_count", C.c_int32)]
+                ("device_bytes", C.c_int64), ("grid_ctas", C.c_int32), ("sm_count", C.c_int32),
+                ("last_row_entries", C.c_int64), ("last_var_visits", C.c_int64)]
 
 
 # every symbol include/mss.h declares (tests check the library exports all of them)
