@@ -226,7 +226,9 @@ def main():
     mine = msd.local_windows(nwin, rank, world)
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # numpy releases the GIL in the heavy parts
-        views = dict(zip(mine, pool.map(lambda w: msgen.make_config(args.workload, seed=w)[0], mine)))
+        # transport form: what the C++ FlattenWindow emits (empty slots and window-keyframe observations left out; the
+        # window, the model and the result are the same -- tests/test_gpu_parity.py::test_compact_view_same_result)
+        views = dict(zip(mine, pool.map(lambda w: msgen.make_config(args.workload, seed=w)[0].compact(), mine)))
     K, H, M = cfg["K"], cfg["H"], cfg["M"]
     words, rows = (M + 31) // 32, K + H
     in_bytes = sum(v.input_bytes() for v in views.values())
@@ -328,7 +330,8 @@ def main():
             "metric": METRIC, "value": nwin * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {K} KF x {M} MP KITTI-00-shaped windows (msgen-v1 seeds 0..{nwin-1})",
+            "config": {"workload": f"{args.workload}: {K} KF x {M} MP KITTI-00-shaped windows (msgen-v1 seeds 0..{nwin-1}), compact "
+                                   "transport form (valid slots + outside observations only, as FlattenWindow emits)",
                        "windows_per_gpu_per_step": B, "global_windows_per_step": nwin,
                        "N": N, "lambda": msgen.LAMBDA, "grid_lambda": msgen.GRID_LAMBDA,
                        "parallelism": f"window w -> rank w % {world}; one NCCL all-gather of result slots" if world > 1 else "single GPU",

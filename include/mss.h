@@ -73,12 +73,14 @@ typedef struct mss_window_view {
     int32_t F;                 /* feature slots = feat_ptr[K] */
     int32_t O;                 /* observations  = mp_obs_ptr[M] */
     int32_t memory;            /* mss_memory of every pointer below */
-    const int32_t*  feat_ptr;  /* [K+1] slot range of each window keyframe */
+    const int32_t*  feat_ptr;  /* [K+1] slot range of each window keyframe (a caller may leave empty slots out altogether) */
     const int32_t*  feat_mp;   /* [F]   map-point table index, -1 = empty slot or bad map point (MapSparsification.cc:70,90) */
     const uint16_t* feat_cell; /* [F]   col*48+row in the 64x48 grid, MSS_CELL_NONE = not in mGrid */
     const int32_t*  mp_nobs;   /* [M]   MapPoint::Observations() */
     const int32_t*  mp_obs_ptr;/* [M+1] */
-    const int32_t*  mp_obs_kf; /* [O]   KF-table index of each observation; >= K means outside keyframe (value - K) */
+    const int32_t*  mp_obs_kf; /* [O]   KF-table index of each observation; >= K means outside keyframe (value - K); entries < K
+                                        (window keyframes) are ignored and may be left out, as may the lists of map points
+                                        that are not variables */
     const int32_t*  okf_total; /* [H]   GetNumberMPs() of each outside keyframe */
 } mss_window_view;
 

@@ -18,6 +18,7 @@
 
 namespace {
 
+constexpr int kMaxChunks = 8;
 using mss::Ctrl;
 using mss::Params;
 using mss::WinDesc;
@@ -71,7 +72,9 @@ struct mss_handle {
     int device = 0;
     int sm_count = 0;
     int max_ctas_per_sm = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[8] = {};
+    int chunk_windows = 8;           // host views are copied / solved in chunks of about this many windows (0 = one chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     // device arena
@@ -233,27 +236,45 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
     const int Rtot = (int)(Ktot + Htot);
 
-    // ---- groups: the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest first), so a
-    //      group that draws a short solve simply takes the next window.  One window -> one group with the whole grid. ------
+    // ---- chunks: host views are handed to the device in chunks, so that the H2D copy of chunk c+1 (copy stream) overlaps
+    //      the solve of chunk c (one cooperative launch per chunk on the compute stream).  Device-resident views: one chunk.
+    bool any_host = false;
+    for (int w : local) any_host = any_host || views[w].memory == MSS_MEM_HOST;
+    int nchunks = 1;
+    if (any_host && h->chunk_windows > 0 && nl >= 2 * h->chunk_windows) nchunks = std::min(kMaxChunks, nl / h->chunk_windows);
+    const int csize = (std::max(nl, 1) + nchunks - 1) / nchunks;
+    nchunks = (std::max(nl, 1) + csize - 1) / csize;
+
+    // ---- groups (per chunk): the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest
+    //      first), so a group that draws a short solve simply takes the next window.  One window -> one group, whole grid. --
     const int max_grid = std::max(1, h->max_ctas_per_sm * h->sm_count);
     auto work = [&](int i) { const mss_window_view& v = views[local[i]]; return 1.0 + (double)v.F + (double)v.O + 0.25 * (double)v.M; };
-    std::vector<int> order(nl);
-    for (int i = 0; i < nl; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
-    int cap = 1;        // a window cannot use more CTAs than it has rows or variable tiles
-    for (int i = 0; i < nl; ++i) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
-    int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(nl, 1));
-    gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
-    const int ngroups = std::max(1, std::min(std::max(nl, 1), max_grid / gsize));
-    std::vector<int> gcta(ngroups, gsize);
-    int grid = ngroups * gsize;
+    struct Chunk { int first, count, gsize, ngroups, grid; size_t off_grp, off_cta, off_gwin, sync_off; std::vector<int> order; };
+    std::vector<Chunk> chunks(nchunks);
+    size_t meta_bytes = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16), sync_words = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        Chunk& ch = chunks[c];
+        ch.first = c * csize;
+        ch.count = std::max(0, std::min(csize, nl - ch.first));
+        ch.order.resize(ch.count);
+        for (int i = 0; i < ch.count; ++i) ch.order[i] = ch.first + i;
+        std::stable_sort(ch.order.begin(), ch.order.end(), [&](int x, int y) { return work(x) > work(y); });
+        int cap = 1;        // a window cannot use more CTAs than it has rows or variable tiles
+        for (int i : ch.order) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
+        int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(ch.count, 1));
+        ch.gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
+        ch.ngroups = std::max(1, std::min(std::max(ch.count, 1), max_grid / ch.gsize));
+        ch.grid = ch.ngroups * ch.gsize;
+        ch.off_grp = meta_bytes;
+        ch.off_cta = ch.off_grp + align_up((size_t)ch.ngroups * sizeof(mss::GroupDesc), 16);
+        ch.off_gwin = ch.off_cta + align_up((size_t)ch.grid * 4, 16);
+        meta_bytes = ch.off_gwin + align_up((size_t)std::max(ch.count, 1) * 4, 16);
+        ch.sync_off = sync_words;
+        sync_words += 32 + (size_t)ch.ngroups * 32;
+    }
+    int grid = chunks[0].grid;
 
     int rc;
-    const size_t off_grp = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16);
-    const size_t off_cta = off_grp + align_up((size_t)ngroups * sizeof(mss::GroupDesc), 16);
-    const size_t off_gwin = off_cta + align_up((size_t)std::max(grid, 1) * 4, 16);
-    const size_t meta_bytes = off_gwin + align_up((size_t)std::max(nl, 1) * 4, 16);
-    const size_t sync_words = 32 + (size_t)ngroups * 32;
     if ((rc = ensure(h, h->meta, meta_bytes))) return rc;
     if ((rc = ensure(h, h->ws, (size_t)std::max(nl, 1)))) return rc;
     if ((rc = ensure(h, h->st, (size_t)Mpad + 16))) return rc;
@@ -273,16 +294,15 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if ((rc = ensure_pinned(h, (void**)&h->h_meta, &h->h_meta_cap, meta_bytes))) return rc;
     if ((rc = ensure_pinned(h, (void**)&h->h_out, &h->h_out_cap, (out_words + 16) * 4))) return rc;
 
-    // ---- stage host views, build descriptors ------------------------------------------------------------------------
+    // ---- descriptors -----------------------------------------------------------------------------------------------------
+    // with one chunk everything runs on the compute stream; with several, copies go to the copy stream and each launch
+    // waits for the event recorded after its chunk's copies
+    cudaStream_t cstream = nchunks > 1 ? h->copy_stream : h->stream;
     WinDesc* hd = reinterpret_cast<WinDesc*>(h->h_meta);
-    mss::GroupDesc* h_grp = reinterpret_cast<mss::GroupDesc*>(h->h_meta + off_grp);
-    int* h_cta_grp = reinterpret_cast<int*>(h->h_meta + off_cta);
-    int* h_gwin = reinterpret_cast<int*>(h->h_meta + off_gwin);
     int64_t h2d = 0;
     size_t soff = 0;
     auto stage = [&](const void* src, size_t bytes) -> const void* {
         uint8_t* dst = h->stage.p + soff;
-        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
         soff += align_up(bytes, 16);
         h2d += (int64_t)bytes;
         return dst;
@@ -311,27 +331,44 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         row_base += v.K + v.H; slot_base += v.F; obs_base += v.O;
         var_base += (int)align_up((size_t)std::max(v.M, 1), mss::kVarTile);
     }
-    {
+    for (const Chunk& ch : chunks) {
+        mss::GroupDesc* h_grp = reinterpret_cast<mss::GroupDesc*>(h->h_meta + ch.off_grp);
+        int* h_cta_grp = reinterpret_cast<int*>(h->h_meta + ch.off_cta);
+        int* h_gwin = reinterpret_cast<int*>(h->h_meta + ch.off_gwin);
         int cta = 0;
-        for (int g = 0; g < ngroups; ++g) {
-            h_grp[g].cta0 = cta; h_grp[g].ncta = gcta[g]; h_grp[g].pad_[0] = h_grp[g].pad_[1] = 0;
-            for (int c = 0; c < gcta[g]; ++c) h_cta_grp[cta++] = g;
+        for (int g = 0; g < ch.ngroups; ++g) {
+            h_grp[g].cta0 = cta; h_grp[g].ncta = ch.gsize; h_grp[g].pad_[0] = h_grp[g].pad_[1] = 0;
+            for (int k = 0; k < ch.gsize; ++k) h_cta_grp[cta++] = g;
         }
-        for (int i = 0; i < nl; ++i) h_gwin[i] = order[i];
+        for (int i = 0; i < ch.count; ++i) h_gwin[i] = ch.order[i];
+    }
+    MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, cstream));
+    h2d += (int64_t)meta_bytes;
+    // ---- staging copies, chunk by chunk ------------------------------------------------------------------------------------
+    for (int c = 0; c < nchunks; ++c) {
+        const Chunk& ch = chunks[c];
+        for (int i = ch.first; i < ch.first + ch.count; ++i) {
+            const mss_window_view& v = views[local[i]];
+            if (v.memory != MSS_MEM_HOST) continue;
+            const WinDesc& d = hd[i];
+            auto put = [&](const void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream); };
+            put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
+            put(d.feat_mp, v.feat_mp, (size_t)v.F * 4);
+            put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
+            put(d.mp_nobs, v.mp_nobs, (size_t)v.M * 4);
+            put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
+            put(d.mp_obs_kf, v.mp_obs_kf, (size_t)v.O * 4);
+            put(d.okf_total, v.okf_total, (size_t)v.H * 4);
+        }
+        if (nchunks > 1) MSS_CUDA(h, cudaEventRecord(h->ev_copy[c], cstream));
     }
     MSS_CUDA(h, cudaGetLastError());
-    MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
-    h2d += (int64_t)meta_bytes;
 
-    // ---- launch -------------------------------------------------------------------------------------------------------
+    // ---- launches -----------------------------------------------------------------------------------------------------
     Params P;
     memset(&P, 0, sizeof(P));
     P.win = reinterpret_cast<const WinDesc*>(h->meta.p);
     P.ws = h->ws.p;
-    P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + off_grp);
-    P.cta_grp = reinterpret_cast<const int*>(h->meta.p + off_cta);
-    P.gwin = reinterpret_cast<const int*>(h->meta.p + off_gwin);
-    P.gbar = h->sync.p + 32;
     P.st = h->st.p; P.acc = h->acc.p; P.gain = h->gain.p; P.deg = h->deg.p; P.seen = h->seen.p;
     P.vlist = h->vlist.p; P.Mpad = (int)Mpad;
     P.trace = h->trace_on ? h->trace.p : nullptr;
@@ -341,8 +378,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         P.row_off = h->rows.p; P.ent_n = h->rows.p + rs; P.live_n = h->rows.p + 2 * rs; P.row_need = h->rows.p + 3 * rs;
         P.row_cov = h->rows.p + 4 * rs; P.row_ncell = h->rows.p + 5 * rs; P.ocursor = h->rows.p + 6 * rs;
     }
-    P.out = h->out.p; P.ctrl = h->ctrl;
-    P.nwin = nl; P.ngroups = ngroups; P.Ftot = (int)Ftot;
+    P.out = h->out.p;
+    P.Ftot = (int)Ftot;
     P.N = h->cfg.min_points;
     P.max_rounds = h->cfg.max_rounds; P.all_rule_steps = h->cfg.all_rule_steps; P.max_drop_rounds = h->cfg.max_drop_rounds;
     P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
@@ -351,13 +388,25 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
 
     float dev_ms = 0.f;
     if (nl > 0) {
-        void* args[] = {(void*)&P};
         MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
         if (h->trace_on) MSS_CUDA(h, cudaMemsetAsync(h->trace.p, 0, (size_t)nl * mss::kTraceCap * sizeof(uint2), h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
+        for (int c = 0; c < nchunks; ++c) {
+            const Chunk& ch = chunks[c];
+            if (ch.count == 0) continue;
+            P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + ch.off_grp);
+            P.cta_grp = reinterpret_cast<const int*>(h->meta.p + ch.off_cta);
+            P.gwin = reinterpret_cast<const int*>(h->meta.p + ch.off_gwin);
+            P.ctrl = reinterpret_cast<Ctrl*>(h->sync.p + ch.sync_off);
+            P.gbar = h->sync.p + ch.sync_off + 32;
+            P.nwin = ch.count; P.ngroups = ch.ngroups;
+            void* args[] = {(void*)&P};
+            if (nchunks > 1) MSS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
+            MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(ch.grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
+            h->stats.kernel_launches += 1;
+            grid = std::max(grid, ch.grid);
+        }
         MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-        h->stats.kernel_launches += 1;
     } else {
         grid = 0;
     }
@@ -369,8 +418,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     }
     // ---- hand-back ------------------------------------------------------------------------------------------------------
     MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
-    MSS_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
-    int64_t d2h = (int64_t)(out_words * 4 + sizeof(Ctrl));
+    for (int c = 0; c < nchunks; ++c)
+        MSS_CUDA(h, cudaMemcpyAsync(&h->h_ctrl[c], h->sync.p + chunks[c].sync_off, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    int64_t d2h = (int64_t)(out_words * 4 + (size_t)nchunks * sizeof(Ctrl));
     bool aborted = false;
     for (int w = 0; w < nwin; ++w) {       // device-resident result buffers are filled device-to-device
         const mss_window_view& v = views[w];
@@ -384,7 +434,12 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     }
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
-    aborted = nl > 0 && h->h_ctrl->abort != 0;
+    unsigned long long row_entries = 0, var_visits = 0;
+    for (int c = 0; c < nchunks && nl > 0; ++c) {
+        aborted = aborted || h->h_ctrl[c].abort != 0;
+        row_entries += h->h_ctrl[c].row_entries;
+        var_visits += h->h_ctrl[c].var_visits;
+    }
     if (h->trace_on && nl > 0) {
         h->h_trace.resize((size_t)nl * mss::kTraceCap);
         h->h_trace_nwin = nl;
@@ -440,8 +495,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     h->stats.last_d2h_bytes = d2h;
     h->stats.device_bytes = h->device_bytes;
     h->stats.grid_ctas = grid;
-    h->stats.last_row_entries = nl > 0 ? (int64_t)h->h_ctrl->row_entries : 0;
-    h->stats.last_var_visits = nl > 0 ? (int64_t)h->h_ctrl->var_visits : 0;
+    h->stats.last_row_entries = (int64_t)row_entries;
+    h->stats.last_var_visits = (int64_t)var_visits;
     h->stats.last_total_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
     return ret;
 }
@@ -497,7 +552,11 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if (const char* tv = getenv("MSS_TAIL_VARS")) h->tail_vars = atoi(tv);
     if (const char* te = getenv("MSS_TAIL_ENTS")) h->tail_ents = atoi(te);
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
-    if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc((void**)&h->h_ctrl, kMaxChunks * sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (int c = 0; c < kMaxChunks; ++c)
+        if ((e = cudaEventCreateWithFlags(&h->ev_copy[c], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if (const char* cw = getenv("MSS_CHUNK_WINDOWS")) h->chunk_windows = atoi(cw);
     h->stats.sm_count = h->sm_count;
     *out = h;
     return MSS_OK;
@@ -514,6 +573,8 @@ void mss_destroy(mss_handle* h) {
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int c = 0; c < kMaxChunks; ++c) if (h->ev_copy[c]) cudaEventDestroy(h->ev_copy[c]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -81,19 +81,15 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     out.vpMapPoints.clear(); out.vpOutsideKFs.clear();
 
     // window membership first (the reference stamps inside its second pass, :81; observations are classified with it, :132)
-    std::unordered_map<const KeyFrame*, int> windowIndex;
-    windowIndex.reserve((size_t)K * 2);
-    for (int k = 0; k < K; ++k) {
-        vpKFs[k]->mnMapSaprsificationId = nId;
-        windowIndex.emplace(vpKFs[k].get(), k);          // a keyframe queued twice keeps its first position
-    }
+    for (int k = 0; k < K; ++k) vpKFs[k]->mnMapSaprsificationId = nId;
 
-    // keyframe side: slots and cells (passes 1 and 2, :67-123)
+    // keyframe side: slots and cells (passes 1 and 2, :67-123).  Only valid slots are emitted (empty slots and bad points
+    // contribute nothing to the model, :70,90), which keeps the transport to the GPU small.
+    vector<int32_t> slotPos;
     for (int k = 0; k < K; ++k) {
         const vector<shared_ptr<MapPoint>> vMPs = vpKFs[k]->GetMapPointMatches();
-        const size_t base = out.feat_mp.size(), n = vMPs.size();
-        out.feat_mp.resize(base + n, -1);
-        out.feat_cell.resize(base + n, (uint16_t)MSS_CELL_NONE);
+        const size_t n = vMPs.size();
+        slotPos.assign(n, -1);
         for (size_t i = 0; i < n; ++i) {
             const shared_ptr<MapPoint>& pMP = vMPs[i];
             if (!pMP || pMP->isBad()) continue;
@@ -104,38 +100,37 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
                 out.mp_nobs.push_back(pMP->Observations());
                 out.is_var.push_back(0);
             }
-            out.feat_mp[base + i] = (int32_t)pMP->mnIndexForSparsification;
+            slotPos[i] = (int32_t)out.feat_mp.size();
+            out.feat_mp.push_back((int32_t)pMP->mnIndexForSparsification);
+            out.feat_cell.push_back((uint16_t)MSS_CELL_NONE);
         }
         const auto& grid = vpKFs[k]->GetFeatureGrids();
         for (size_t col = 0; col < grid.size(); ++col)
             for (size_t row = 0; row < grid[col].size(); ++row)
                 for (size_t i : grid[col][row]) {
-                    if (i >= n) continue;
-                    out.feat_cell[base + i] = (uint16_t)(col * MSS_GRID_ROWS + row);
-                    if (out.feat_mp[base + i] >= 0) out.is_var[out.feat_mp[base + i]] = 1;
+                    if (i >= n || slotPos[i] < 0) continue;
+                    out.feat_cell[slotPos[i]] = (uint16_t)(col * MSS_GRID_ROWS + row);
+                    out.is_var[out.feat_mp[slotPos[i]]] = 1;
                 }
         out.feat_ptr.push_back((int32_t)out.feat_mp.size());
     }
 
-    // map-point side: observations of the variables (pass 3, :125-142); outside keyframes in discovery order for now
+    // map-point side: observations of the variables by keyframes OUTSIDE the window (pass 3, :125-142); observations by
+    // window keyframes are not emitted (the engine only needs the outside rows); outside keyframes in discovery order for now
     std::unordered_map<const KeyFrame*, int> outsideIndex;
     const size_t M = out.vpMapPoints.size();
     for (size_t p = 0; p < M; ++p) {
         if (out.is_var[p]) {
             const auto obs = out.vpMapPoints[p]->GetObservations();
             for (const auto& kv : obs) {
+                if (kv.first->mnMapSaprsificationId == nId) continue;
                 const KeyFrame* pKF = kv.first.get();
-                if (kv.first->mnMapSaprsificationId == nId) {
-                    const auto it = windowIndex.find(pKF);
-                    if (it != windowIndex.end()) out.mp_obs_kf.push_back(it->second);
-                } else {
-                    auto it = outsideIndex.find(pKF);
-                    if (it == outsideIndex.end()) {
-                        it = outsideIndex.emplace(pKF, (int)out.vpOutsideKFs.size()).first;
-                        out.vpOutsideKFs.push_back(kv.first);
-                    }
-                    out.mp_obs_kf.push_back(K + it->second);
+                auto it = outsideIndex.find(pKF);
+                if (it == outsideIndex.end()) {
+                    it = outsideIndex.emplace(pKF, (int)out.vpOutsideKFs.size()).first;
+                    out.vpOutsideKFs.push_back(kv.first);
                 }
+                out.mp_obs_kf.push_back(K + it->second);
             }
         }
         out.mp_obs_ptr.push_back((int32_t)out.mp_obs_kf.size());

@@ -76,6 +76,24 @@ class WindowView:
         return int(self.feat_ptr.nbytes + self.feat_mp.nbytes + self.feat_cell.nbytes + self.mp_nobs.nbytes
                    + self.mp_obs_ptr.nbytes + self.mp_obs_kf.nbytes + self.okf_total.nbytes)
 
+    def compact(self) -> "WindowView":
+        """The same window in the compact transport form the C++ FlattenWindow emits: empty / bad slots (feat_mp == -1) and
+        observations by window keyframes (mp_obs_kf < K, which the engine never reads) are omitted.  Map-point and keyframe
+        numbering is unchanged, so results are directly comparable (and bit-identical)."""
+        keep = self.feat_mp >= 0
+        kf = np.repeat(np.arange(self.K, dtype=np.int64), np.diff(self.feat_ptr))
+        feat_ptr = np.zeros(self.K + 1, np.int64)
+        feat_ptr[1:] = np.cumsum(np.bincount(kf[keep], minlength=self.K))
+        out = self.mp_obs_kf >= self.K
+        mp = np.repeat(np.arange(self.M, dtype=np.int64), np.diff(self.mp_obs_ptr))
+        obs_ptr = np.zeros(self.M + 1, np.int64)
+        obs_ptr[1:] = np.cumsum(np.bincount(mp[out], minlength=self.M))
+        v = WindowView(K=self.K, H=self.H, feat_ptr=feat_ptr, feat_mp=self.feat_mp[keep], feat_cell=self.feat_cell[keep],
+                       mp_nobs=self.mp_nobs, mp_obs_ptr=obs_ptr, mp_obs_kf=self.mp_obs_kf[out], okf_total=self.okf_total,
+                       kf_gid=self.kf_gid, mp_gid=self.mp_gid)
+        v.meta = dict(self.meta, compact=True)
+        return v
+
     def validate(self) -> None:
         K, H, F, M, O = self.K, self.H, self.F, self.M, self.O
         if K < 0 or H < 0:

@@ -122,6 +122,43 @@ def test_batch_equals_singles_and_device_views(eng):
     assert eng.stats()["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("name,seed", [("live", 4), ("c3", 1), ("c1", 2)])
+def test_compact_view_same_result(eng, name, seed):
+    """The compact transport form (empty slots and window-keyframe observations omitted, what FlattenWindow emits and what
+    bench.py ships) is the same window: bit-identical selection, coverage and objective."""
+    view, N = msgen.make_config(name, seed)
+    eng.set_params(N, LAM, GLAM)
+    full = eng.solve(view)
+    comp = eng.solve(view.compact())
+    assert np.array_equal(full.keep_bits, comp.keep_bits) and np.array_equal(full.kf_cov, comp.kf_cov)
+    assert (full.objective, full.rounds, full.n_vars, full.n_cells, full.nnz, full.n_max) == \
+           (comp.objective, comp.rounds, comp.n_vars, comp.n_cells, comp.nnz, comp.n_max)
+    check_against_cpu(view, N, comp)
+
+
+def test_chunked_host_batch_equals_single_launch(build_native):
+    """Host views are copied and solved in chunks (copy of chunk c+1 overlaps the solve of chunk c): same results."""
+    import os
+    from ms_slam_b200.engine import Engine
+    views = [msgen.make_config("live", 20 + i)[0] for i in range(12)]
+    N = 100
+    os.environ["MSS_CHUNK_WINDOWS"] = "3"
+    try:
+        e1 = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    finally:
+        os.environ["MSS_CHUNK_WINDOWS"] = "0"
+    try:
+        e2 = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    finally:
+        del os.environ["MSS_CHUNK_WINDOWS"]
+    r1, r2 = e1.solve_batch(views), e2.solve_batch(views)
+    assert e1.stats()["kernel_launches"] == 4 and e2.stats()["kernel_launches"] == 1
+    for v, a, b in zip(views, r1, r2):
+        assert np.array_equal(a.keep_bits, b.keep_bits) and a.objective == b.objective and a.rounds == b.rounds
+        check_against_cpu(v, N, a)
+    e1.close(); e2.close()
+
+
 def test_edge_cases(eng):
     N = 3
     eng.set_params(N, LAM, GLAM)

@@ -24,11 +24,12 @@ def hm(build_native):
 def check_roundtrip(view, flat, mp_ids, okf_ids, is_var):
     """flat view == original view up to the renumbering of the map-point table / outside keyframes"""
     K = view.K
-    assert flat.K == K and np.array_equal(flat.feat_ptr, view.feat_ptr)
+    comp = view.compact()                  # FlattenWindow emits valid slots only and outside observations only
+    assert flat.K == K and np.array_equal(flat.feat_ptr, comp.feat_ptr)
     valid = view.feat_mp >= 0
-    assert np.array_equal(flat.feat_mp >= 0, valid)
-    assert np.array_equal(mp_ids[flat.feat_mp[valid]], view.feat_mp[valid])
-    assert np.array_equal(flat.feat_cell, view.feat_cell)
+    assert (flat.feat_mp >= 0).all()
+    assert np.array_equal(mp_ids[flat.feat_mp], comp.feat_mp)
+    assert np.array_equal(flat.feat_cell, comp.feat_cell)
     assert np.unique(mp_ids).size == mp_ids.size                       # each map point has exactly one table entry
     assert set(mp_ids.tolist()) == set(view.feat_mp[valid].tolist())   # and the table holds exactly the points seen in valid slots
     assert np.array_equal(flat.mp_nobs, view.mp_nobs[mp_ids])
@@ -53,8 +54,9 @@ def check_roundtrip(view, flat, mp_ids, okf_ids, is_var):
         if not is_var[q]:
             assert got.size == 0
             continue
-        got = sorted(int(k) if k < K else int(okf_ids[k - K]) for k in got)      # outside keyframe ids are K + original j
-        exp = sorted(int(k) for k in view.mp_obs_kf[view.mp_obs_ptr[p]:view.mp_obs_ptr[p + 1]])
+        assert (got >= K).all()
+        got = sorted(int(okf_ids[k - K]) for k in got)                           # outside keyframe ids are K + original j
+        exp = sorted(int(k) for k in comp.mp_obs_kf[comp.mp_obs_ptr[p]:comp.mp_obs_ptr[p + 1]])
         assert got == exp
         seen_outside.update(k for k in got if k >= K)
     assert sorted(okf_ids.tolist()) == sorted(seen_outside) and list(okf_ids) == sorted(okf_ids)    # ordered by keyframe id
