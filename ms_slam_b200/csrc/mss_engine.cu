@@ -262,8 +262,16 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         int cap = 1;        // a window cannot use more CTAs than it has rows or variable tiles
         for (int i : ch.order) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
         int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(ch.count, 1));
-        ch.gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
-        ch.ngroups = std::max(1, std::min(std::max(ch.count, 1), max_grid / ch.gsize));
+        gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
+        int ngroups = std::max(1, std::min(std::max(ch.count, 1), max_grid / gsize));
+        if (h->group_ctas <= 0 && ch.count > ngroups) {
+            // several windows per group: even out the number of windows per group, then give the groups all the CTAs
+            const int waves = (ch.count + ngroups - 1) / ngroups;
+            ngroups = (ch.count + waves - 1) / waves;
+            gsize = std::max(1, std::min(cap, max_grid / ngroups));
+        }
+        ch.gsize = gsize;
+        ch.ngroups = ngroups;
         ch.grid = ch.ngroups * ch.gsize;
         ch.off_grp = meta_bytes;
         ch.off_cta = ch.off_grp + align_up((size_t)ch.ngroups * sizeof(mss::GroupDesc), 16);

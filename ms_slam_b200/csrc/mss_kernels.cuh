@@ -174,6 +174,9 @@ struct BlockScratch {
     // row queue of the current chunk of this CTA's rows: long rows from the front, short rows from the back
     unsigned short rowq[kThreads];
     int rown[kThreads];
+    int rowoff[kThreads];
+    int pred[2][2][kWarps];  // parity-buffered partial sums / warp counts of the row phases (saves the protective barriers)
+    int pscan[2][kWarps];
     int qn[2];
     unsigned rows_live, maxlive;
     unsigned long long work;   // entries read by this CTA in the current row phase
@@ -332,23 +335,26 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
 
 // A row's entries held in registers: warp w owns a contiguous chunk of the list, lane-strided inside it, so global
 // accesses are coalesced and (warp, b, lane) order is list order (needed for the stable compaction).
+template <int EPT>
 struct RowRegs {
-    uint32_t e[kEpt];
-    uint8_t s[kEpt];
+    uint32_t e[EPT];
+    uint8_t s[EPT];
     int per, nb;
 };
 
-__device__ __forceinline__ void load_row(RowRegs& X, const uint32_t* __restrict__ src, int n, const uint8_t* __restrict__ st_w) {
+// EPT = entries per thread: 1, 2, 4 or 8, the smallest that covers the list (short lists must not pay for eight slots)
+template <int EPT>
+__device__ __forceinline__ void load_row(RowRegs<EPT>& X, const uint32_t* __restrict__ src, int n, const uint8_t* __restrict__ st_w) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     X.per = (((n + kWarps - 1) / kWarps) + 31) & ~31;
     X.nb = X.per >> 5;
 #pragma unroll
-    for (int b = 0; b < kEpt; ++b) {
+    for (int b = 0; b < EPT; ++b) {
         const int idx = wid * X.per + b * 32 + lane;
         X.e[b] = (b < X.nb && idx < n) ? src[idx] : kEntInvalid;
     }
 #pragma unroll
-    for (int b = 0; b < kEpt; ++b) X.s[b] = (X.e[b] != kEntInvalid) ? st_w[X.e[b] >> kCellBits] : (uint8_t)ST_NOTVAR;
+    for (int b = 0; b < EPT; ++b) X.s[b] = (X.e[b] != kEntInvalid) ? st_w[X.e[b] >> kCellBits] : (uint8_t)ST_NOTVAR;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -713,71 +719,95 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
 // PROP: counts on the current state, contributions to the FREE variables, and the row's new live list.
 // Source list: the CSR (first PROP row phase of the window) or the previous live list.  Entries found IN are added to the
 // running coverage exactly once (they are not copied to the new list); entries found OUT are dropped.
-__device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, bool from_csr, unsigned* tab, BlockScratch& S) {
+// PROP on a list held in registers (EPT entries per thread): three block barriers per row; the scratch is double-buffered
+// by row parity, so no protective barriers are needed
+template <int EPT>
+__device__ __forceinline__ void row_prop_regs(const Params& P, const WinDesc& D, int R, int n, const uint32_t* src, uint32_t* dst,
+                                              int need, int cov0, int par, unsigned* tab, BlockScratch& S) {
+    const uint8_t* st_w = P.st + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    // three block barriers per row; the scratch is double-buffered by row parity, so no protective barriers are needed
+    RowRegs<EPT> X;
+    load_row(X, src, n, st_w);
+#pragma unroll
+    for (int b = 0; b < EPT; ++b)
+        if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
+    __syncthreads();
+    int cin = 0, cfree = 0;
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if (X.e[b] == kEntInvalid) continue;
+        const unsigned cell = X.e[b] & kCellCov;
+        if (X.s[b] == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
+        else if (X.s[b] == ST_FREE) { ++cfree; if (cell != kCellCov) atomicAdd(&tab[cell], 1u); }
+    }
+    cin = __reduce_add_sync(0xFFFFFFFFu, cin);
+    cfree = __reduce_add_sync(0xFFFFFFFFu, cfree);
+    if (lane == 0) { S.pred[par][0][wid] = cin; S.pred[par][1][wid] = cfree; }
+    __syncthreads();                                    // publishes the cell table and the partial sums
+    cin = 0; cfree = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) { cin += S.pred[par][0][q]; cfree += S.pred[par][1][q]; }
+    const int cov = cov0 + cin;
+    const int d = max(0, need - cov);
+    const bool defi = d > 0, critr = defi && d >= cfree;
+    int wcnt = 0;
+    unsigned m[EPT];
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        const bool fr = (X.e[b] != kEntInvalid) && X.s[b] == ST_FREE;
+        if (fr) {
+            const unsigned cell = X.e[b] & kCellCov;
+            unsigned long long add = 0;
+            bool covered = true;
+            if (cell != kCellCov) {
+                const unsigned t = tab[cell];
+                covered = (t & kTabCov) != 0u;
+                if (!covered) { add |= 1ull; if ((t & 0xFFFFu) == 1u) add |= 1ull << 16; }
+            }
+            if (defi) add |= 1ull << 32;
+            if (critr) add |= 1ull << 48;
+            if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
+            if (covered) X.e[b] |= kCellCov;
+        }
+        m[b] = __ballot_sync(0xFFFFFFFFu, fr);
+        wcnt += __popc(m[b]);
+    }
+    if (lane == 0) S.pscan[par][wid] = wcnt;
+    __syncthreads();                                    // every read of src and of the cell table precedes what follows
+    int pos = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) if (q < wid) pos += S.pscan[par][q];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if ((m[b] >> lane) & 1u) dst[pos + __popc(m[b] & lt)] = X.e[b];
+        pos += __popc(m[b]);
+    }
+    if (threadIdx.x == 0) {
+        P.row_cov[R] = cov;
+        P.live_n[R] = cfree;
+        if (cfree) { S.rows_live += 1u; if (R - D.row_base < D.K) S.maxlive = max(S.maxlive, (unsigned)cfree); }   // thread 0 only
+    }
+}
+
+__device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, int off, int par, bool from_csr, unsigned* tab,
+                         BlockScratch& S) {
     if (n == 0) return;                                     // live_n[R] is already 0 (W1 / W3 / previous round)
-    const int off = P.row_off[R];
     const uint32_t* src = (from_csr ? P.ent : P.live) + off;
     uint32_t* dst = P.live + off;
     const uint8_t* st_w = P.st + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
     const int cov0 = P.row_cov[R];
-    const int lane = threadIdx.x & 31;
-    if (n <= kRegRow) {
-        RowRegs X;
-        load_row(X, src, n, st_w);
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b)
-            if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
-        __syncthreads();
-        int cin = 0, cfree = 0, z = 0;
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            if (X.e[b] == kEntInvalid) continue;
-            const unsigned cell = X.e[b] & kCellCov;
-            if (X.s[b] == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
-            else if (X.s[b] == ST_FREE) { ++cfree; if (cell != kCellCov) atomicAdd(&tab[cell], 1u); }
-        }
-        block_sum3(S, cin, cfree, z);                       // barriers publish tab
-        const int cov = cov0 + cin;
-        const int d = max(0, need - cov);
-        const bool defi = d > 0, critr = defi && d >= cfree;
-        int wcnt = 0;
-        unsigned m[kEpt];
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            const bool fr = (X.e[b] != kEntInvalid) && X.s[b] == ST_FREE;
-            if (fr) {
-                const unsigned cell = X.e[b] & kCellCov;
-                unsigned long long add = 0;
-                bool covered = true;
-                if (cell != kCellCov) {
-                    const unsigned t = tab[cell];
-                    covered = (t & kTabCov) != 0u;
-                    if (!covered) { add |= 1ull; if ((t & 0xFFFFu) == 1u) add |= 1ull << 16; }
-                }
-                if (defi) add |= 1ull << 32;
-                if (critr) add |= 1ull << 48;
-                if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
-                if (covered) X.e[b] |= kCellCov;
-            }
-            m[b] = __ballot_sync(0xFFFFFFFFu, fr);
-            wcnt += __popc(m[b]);
-        }
-        int total;
-        int pos = warp_excl_scan(S, wcnt, total);           // barrier: every read of src precedes the in-place writes
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            if ((m[b] >> lane) & 1u) dst[pos + __popc(m[b] & lt)] = X.e[b];
-            pos += __popc(m[b]);
-        }
-        if (threadIdx.x == 0) {
-            P.row_cov[R] = cov;
-            P.live_n[R] = cfree;
-            if (cfree) { S.rows_live += 1u; if (R - D.row_base < D.K) S.maxlive = max(S.maxlive, (unsigned)cfree); }   // thread 0 only
-        }
-    } else {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (n <= kThreads) row_prop_regs<1>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 2 * kThreads) row_prop_regs<2>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 4 * kThreads) row_prop_regs<4>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= kRegRow) row_prop_regs<8>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else {
         // long row: two passes over the list in global memory
         zero_tab(tab);
         __syncthreads();
@@ -831,6 +861,50 @@ __device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, bool f
 
 // GREEDY: runs right after a PROP round that changed nothing, so the live list is exact (all FREE, cell field = covered
 // flag, row_cov current).
+template <int EPT>
+__device__ __forceinline__ void row_greedy_regs(const Params& P, const WinDesc& D, int n, const uint32_t* src, int d,
+                                                unsigned long long* keytab, BlockScratch& S) {
+    const uint8_t* st_w = P.st + D.var_base;
+    const float* gain_w = P.gain + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+
+    RowRegs<EPT> X;
+    load_row(X, src, n, st_w);
+    unsigned long long key[EPT];
+    int nfree = 0;
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        const bool fr = X.e[b] != kEntInvalid && X.s[b] == ST_FREE;
+        key[b] = fr ? make_key(gain_w[X.e[b] >> kCellBits], X.e[b] >> kCellBits) : 0ull;
+        if (fr) { ++nfree; if ((X.e[b] & kCellCov) != kCellCov) keytab[X.e[b] & kCellCov] = 0ull; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < EPT; ++b)
+        if (key[b] && (X.e[b] & kCellCov) != kCellCov) atomicMax(&keytab[X.e[b] & kCellCov], key[b]);
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < EPT; ++b)
+        if (key[b] && (X.e[b] & kCellCov) != kCellCov && keytab[X.e[b] & kCellCov] != key[b])
+            atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_BLOCKED);
+    if (d > 0) {
+        int z0 = 0, z1 = 0;
+        block_sum3(S, nfree, z0, z1);
+        if (nfree > d) {
+            const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
+#pragma unroll
+                for (int b = 0; b < EPT; ++b) if (key[b]) sink(key[b]);
+            });
+#pragma unroll
+            for (int b = 0; b < EPT; ++b)
+                if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], key[b] > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
+        } else {
+#pragma unroll
+            for (int b = 0; b < EPT; ++b) if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_NOMINATED);
+        }
+    }
+}
+
 __device__ void row_greedy(const Params& P, const WinDesc& D, int R, int n, unsigned long long* keytab, BlockScratch& S) {
     if (n == 0) return;
     const uint32_t* src = P.live + P.row_off[R];
@@ -838,43 +912,10 @@ __device__ void row_greedy(const Params& P, const WinDesc& D, int R, int n, unsi
     const float* gain_w = P.gain + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int d = max(0, P.row_need[R] - P.row_cov[R]);
-    if (n <= kRegRow) {
-        RowRegs X;
-        load_row(X, src, n, st_w);
-        unsigned long long key[kEpt];
-        int nfree = 0;
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            const bool fr = X.e[b] != kEntInvalid && X.s[b] == ST_FREE;
-            key[b] = fr ? make_key(gain_w[X.e[b] >> kCellBits], X.e[b] >> kCellBits) : 0ull;
-            if (fr) { ++nfree; if ((X.e[b] & kCellCov) != kCellCov) keytab[X.e[b] & kCellCov] = 0ull; }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b)
-            if (key[b] && (X.e[b] & kCellCov) != kCellCov) atomicMax(&keytab[X.e[b] & kCellCov], key[b]);
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b)
-            if (key[b] && (X.e[b] & kCellCov) != kCellCov && keytab[X.e[b] & kCellCov] != key[b])
-                atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_BLOCKED);
-        if (d > 0) {
-            int z0 = 0, z1 = 0;
-            block_sum3(S, nfree, z0, z1);
-            if (nfree > d) {
-                const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
-#pragma unroll
-                    for (int b = 0; b < kEpt; ++b) if (key[b]) sink(key[b]);
-                });
-#pragma unroll
-                for (int b = 0; b < kEpt; ++b)
-                    if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], key[b] > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
-            } else {
-#pragma unroll
-                for (int b = 0; b < kEpt; ++b) if (key[b]) atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_NOMINATED);
-            }
-        }
-    } else {
+    if (n <= kThreads) row_greedy_regs<1>(P, D, n, src, d, keytab, S);
+    else if (n <= 4 * kThreads) row_greedy_regs<4>(P, D, n, src, d, keytab, S);
+    else if (n <= kRegRow) row_greedy_regs<8>(P, D, n, src, d, keytab, S);
+    else {
         for (int c = threadIdx.x; c < kCells; c += kThreads) keytab[c] = 0ull;
         __syncthreads();
         int nfree = 0;
@@ -1002,41 +1043,60 @@ __device__ __forceinline__ void warp_row_greedy(const Params& P, const WinDesc& 
 // D1 (and EVAL): one sweep of the row's CSR segment: IN counts per cell and per row; D1 adds the criticality counters
 // of the IN points; both write the row's coverage / slack and the uncovered-cell count (the read-out uses the values of
 // the last sweep, which is the one that found nothing left to drop).
-__device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int R, bool accumulate, unsigned* tab, BlockScratch& S) {
-    const int n = P.ent_n[R];
-    const uint32_t* src = P.ent + P.row_off[R];
+template <int EPT>
+__device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, int n, const uint32_t* src, int need, int par,
+                                            bool accumulate, unsigned* tab, BlockScratch& S, int& cin, int& ccells) {
+    const uint8_t* st_w = P.st + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    RowRegs<EPT> X;
+    load_row(X, src, n, st_w);
+#pragma unroll
+    for (int b = 0; b < EPT; ++b)
+        if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
+        ++cin;
+        const unsigned cell = X.e[b] & kCellCov;
+        if (cell != kCellCov && atomicAdd(&tab[cell], 1u) == 0u) ++ccells;
+    }
+    cin = __reduce_add_sync(0xFFFFFFFFu, cin);
+    ccells = __reduce_add_sync(0xFFFFFFFFu, ccells);
+    if (lane == 0) { S.pred[par][0][wid] = cin; S.pred[par][1][wid] = ccells; }
+    __syncthreads();
+    cin = 0; ccells = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) { cin += S.pred[par][0][q]; ccells += S.pred[par][1][q]; }
+    if (accumulate && cin > 0) {
+        const bool critr = cin <= need;
+#pragma unroll
+        for (int b = 0; b < EPT; ++b) {
+            if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
+            const unsigned cell = X.e[b] & kCellCov;
+            unsigned long long add = 0;
+            if (cell != kCellCov && tab[cell] == 1u) add |= 1ull;
+            if (critr) add |= 1ull << 32;
+            if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
+        }
+    }
+}
+
+__device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int R, int n, int off, int par, bool accumulate,
+                            unsigned* tab, BlockScratch& S) {
+    const uint32_t* src = P.ent + off;
     const uint8_t* st_w = P.st + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int cin = 0, ccells = 0, z = 0;
-    if (n > 0 && n <= kRegRow) {
-        RowRegs X;
-        load_row(X, src, n, st_w);
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b)
-            if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
-            ++cin;
-            const unsigned cell = X.e[b] & kCellCov;
-            if (cell != kCellCov && atomicAdd(&tab[cell], 1u) == 0u) ++ccells;
-        }
-        block_sum3(S, cin, ccells, z);
-        if (accumulate && cin > 0) {
-            const bool critr = cin <= need;
-#pragma unroll
-            for (int b = 0; b < kEpt; ++b) {
-                if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
-                const unsigned cell = X.e[b] & kCellCov;
-                unsigned long long add = 0;
-                if (cell != kCellCov && tab[cell] == 1u) add |= 1ull;
-                if (critr) add |= 1ull << 32;
-                if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
-            }
-        }
-    } else if (n > 0) {
+    if (n > 0 && n <= kThreads) row_d1_regs<1>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 2 * kThreads) row_d1_regs<2>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 4 * kThreads) row_d1_regs<4>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= kRegRow) row_d1_regs<8>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0) {
         zero_tab(tab);
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -1540,13 +1600,19 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
     if (threadIdx.x == 0) { ws.t_rounds = rounds; ws.t_greedy = greedy_steps; ws.t_status = status; }
 }
 
-// Row phase of PROP / GREEDY over the rows of this CTA: the rows are classified by list length in chunks of 256; long
-// lists are processed by the whole CTA one after the other, short ones by one warp each.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Row phase of PROP / GREEDY / D1 / EVAL over the rows of this CTA: the rows are classified by list length in chunks of
+// 256; long lists are processed by the whole CTA one after the other (the next row's entries are prefetched into L1 while
+// the current one is processed), short PROP / GREEDY lists by one warp each.
 __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc, const GroupCtx& G, int mode, bool from_csr,
                                 unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
     const int rows = D.K + D.H;
     const int mine = (rows - G.cta + G.ncta - 1) / G.ncta;          // rows G.cta, G.cta + ncta, ...
-    const int* listn = from_csr ? P.ent_n : P.live_n;
+    const bool sweep = mode == MODE_D1 || mode == MODE_EVAL;        // whole CSR rows, every row (also empty ones) reports
+    const bool csr = from_csr || sweep;
+    const int* listn = csr ? P.ent_n : P.live_n;
+    const uint32_t* lists = csr ? P.ent : P.live;
     const int wid = threadIdx.x >> 5;
     unsigned rows_live = 0;
     if (threadIdx.x == 0) { S.rows_live = 0u; S.maxlive = 0u; S.work = 0ull; }
@@ -1555,9 +1621,11 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
         __syncthreads();
         const int i = base + (int)threadIdx.x;
         if (i < mine) {
-            const int n = listn[D.row_base + G.cta + i * G.ncta];
+            const int R = D.row_base + G.cta + i * G.ncta;
+            const int n = listn[R];
             S.rown[threadIdx.x] = n;
-            if (n > kWarpRow) S.rowq[atomicAdd(&S.qn[0], 1)] = (unsigned short)threadIdx.x;
+            S.rowoff[threadIdx.x] = P.row_off[R];
+            if (n > kWarpRow || sweep) S.rowq[atomicAdd(&S.qn[0], 1)] = (unsigned short)threadIdx.x;
             else if (n > 0) S.rowq[kThreads - 1 - atomicAdd(&S.qn[1], 1)] = (unsigned short)threadIdx.x;
         }
         __syncthreads();
@@ -1571,9 +1639,13 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
         for (int q = 0; q < nlong; ++q) {
             const int slot = S.rowq[q];
             const int R = D.row_base + G.cta + (base + slot) * G.ncta;
-            if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], from_csr, tab, S);
-            else row_greedy(P, D, R, S.rown[slot], keytab, S);
-            __syncthreads();
+            if (q + 1 < nlong) {                                    // one 128-byte line per thread covers 8192 entries
+                const int ns = S.rowq[q + 1];
+                if ((int)threadIdx.x * 32 < S.rown[ns]) prefetch_l1(lists + S.rowoff[ns] + threadIdx.x * 32);
+            }
+            if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], S.rowoff[slot], q & 1, from_csr, tab, S);
+            else if (sweep) { row_d1_eval(P, D, rc, R, S.rown[slot], S.rowoff[slot], q & 1, mode == MODE_D1, tab, S); __syncthreads(); }
+            else { row_greedy(P, D, R, S.rown[slot], keytab, S); __syncthreads(); }
         }
         for (int q = wid; q < nshort; q += kWarps) {
             const int slot = S.rowq[kThreads - 1 - q];
@@ -1671,20 +1743,15 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         if (G.cta == 0 && threadIdx.x < (int)(sizeof(RoundCnt) / 4))
             reinterpret_cast<uint32_t*>(&ws.rc[(seq + 1) % 3])[threadIdx.x] = 0u;     // used by phase seq + 1
         // row phase
-        if (mode == MODE_PROP || mode == MODE_GREEDY) {
+        if (mode == MODE_PROP || mode == MODE_GREEDY || mode == MODE_D1 || mode == MODE_EVAL) {
             row_phase_lists(P, D, rc, G, mode, from_csr, tab, keytab, S);
             if (!group_sync(P, G)) return false;
-        } else if (mode != MODE_FORCE && mode != MODE_EVALV) {
+        } else if (mode == MODE_D2) {
             unsigned long long wsum = 0;
             for (int r = G.cta; r < rows; r += G.ncta) {
                 const int R = D.row_base + r;
                 wsum += (unsigned long long)P.ent_n[R];
-                switch (mode) {
-                case MODE_D1: row_d1_eval(P, D, rc, R, true, tab, S); break;
-                case MODE_D2: row_d2(P, D, R, tab, keytab, S); break;
-                case MODE_EVAL: row_d1_eval(P, D, rc, R, false, tab, S); break;
-                default: break;
-                }
+                row_d2(P, D, R, tab, keytab, S);
                 __syncthreads();
             }
             if (threadIdx.x == 0 && wsum) atomicAdd(&P.ctrl->row_entries, wsum);
