@@ -6,9 +6,9 @@
 //
 // What it replaces in the reference (/root/reference/src/MapSparsification.cc):
 //   :66-76   nMaxObservation scan            -> W1 (per keyframe row: block max -> atomicMax)
-//   :78-123  variables + cell rows + KF rows -> W1 marks variables and writes the keyframe rows as a CSR of packed
-//                                               (map point, cell) entries, counting-sorted by cell in shared memory, so the
-//                                               entries of one cell row are a contiguous run of its keyframe row
+//   :78-123  variables + cell rows + KF rows -> W1 writes the keyframe rows as a CSR of packed (map point, cell) entries
+//                                               (slot order, coalesced); a cell row is the set of entries of one keyframe
+//                                               row with the same cell id and is never materialised
 //   :125-151 outside-keyframe rows           -> W2 count / W3 scan + rhs / W4 fill (CSR of the outside rows)
 //   :153-157 GUROBI optimize()               -> per-window phase machine PROP / GREEDY / DROP on F(x)
 //   :159-166 read-out of GRB_DoubleAttr_X    -> EVAL: ballot-packed keep bits + row coverage + F(x)
@@ -156,6 +156,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ unsigned f32_orderable(float g) {
     unsigned b = __float_as_uint(g);
@@ -1346,8 +1348,8 @@ __device__ void tail_row_prop(TailSmem& T, int lid) {
         bool covered = false;
         int nf = 0;
         if (__any_sync(0xFFFFFFFFu, hasa)) {
-            // lists are cell-sorted (counting sort in W1, stable compactions since), so the entries of one cell sit next to
-            // each other: only chunks whose cell range overlaps this chunk's range can hold a match
+            // only chunks whose cell range overlaps this chunk's range can hold a match (a cheap filter; it prunes most
+            // pairs when neighbouring slots fall into neighbouring cells and is harmless otherwise)
             const unsigned amin = __reduce_min_sync(0xFFFFFFFFu, hasa ? cella : 0xFFFFu);
             const unsigned amax = __reduce_max_sync(0xFFFFFFFFu, hasa ? cella : 0u);
             for (int cb = 0; cb < n; cb += 32) {
@@ -1600,8 +1602,6 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
     if (threadIdx.x == 0) { ws.t_rounds = rounds; ws.t_greedy = greedy_steps; ws.t_status = status; }
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // Row phase of PROP / GREEDY / D1 / EVAL over the rows of this CTA: the rows are classified by list length in chunks of
 // 256; long lists are processed by the whole CTA one after the other (the next row's entries are prefetched into L1 while
 // the current one is processed), short PROP / GREEDY lists by one warp each.
@@ -1703,6 +1703,13 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     trace_mark(P, G, w, tn, 10, 0, t_win);
     // ---- W1: keyframe rows ---------------------------------------------------------------------------------------
     for (int k = G.cta; k < D.K; k += G.ncta) {
+        if (k + G.ncta < D.K) {                  // next row of this CTA: pull its slots towards L1 while this one is processed
+            const int nb = __ldg(D.feat_ptr + k + G.ncta), ne = __ldg(D.feat_ptr + k + G.ncta + 1);
+            if (nb >= 0 && ne <= D.F) {
+                for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
+                for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
+            }
+        }
         w1_build_row(P, D, ws, k, tab, S);
         __syncthreads();
     }
