@@ -100,6 +100,11 @@ def floor_bytes(K, H, M, F, O):
     return b_in + b_out
 
 
+def view_floor_bytes(v):
+    """floor_bytes for a view object in either layout: its arrays read once + the result slot written once"""
+    return v.input_bytes() + 4 * ((v.M + 31) // 32) + 8 * (v.K + v.H) + 64
+
+
 def kernel_alg_bytes(views, results, row_entries, var_visits):
     """Algorithmic bytes of one launch of the implemented kernel, a LOWER bound of what it has to move:
          view arrays read once, observations streamed a second time by the fill pass     6F + 4(K+1) + 8M + 8O + 4H (+ 4(M+1))
@@ -111,7 +116,8 @@ def kernel_alg_bytes(views, results, row_entries, var_visits):
        not counted: 64-bit reductions of the PROP / GREEDY / D1 row phases, live-list and FREE-list writes."""
     total = 0
     for v, r in zip(views, results):
-        total += floor_bytes(v.K, v.H, v.M, v.F, v.O) + 4 * v.O + 4 * (v.M + 1) + 39 * v.M + 12 * int(r.nnz)
+        obs_elt = 2 if hasattr(v, "mp_obs_kf16") else 4
+        total += view_floor_bytes(v) + obs_elt * v.O + 4 * (v.M + 1) + 39 * v.M + 12 * int(r.nnz)
     return total + 5 * int(row_entries) + 17 * int(var_visits)
 
 
@@ -213,10 +219,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="c2 windows per GPU per step")
+    ap.add_argument("--batch", type=int, default=128, help="c2 windows per GPU per step")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--order", default="discovery", choices=["generated", "discovery"],
+                    help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
+                         "(mnIndexForSparsification, MapSparsification.cc:91-99) or as msgen draws them (random)")
+    ap.add_argument("--layout", default="packed", choices=["packed", "soa"], help="transport layout of the views (include/mss.h mss_layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -230,6 +240,7 @@ def main():
     import torch.distributed as dist
     from ms_slam_b200 import msgen, dist as msd
     from ms_slam_b200 import engine as E
+    from ms_slam_b200.window import pack_view
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
@@ -252,7 +263,11 @@ def main():
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # numpy releases the GIL in the heavy parts
         # transport form: what the C++ FlattenWindow emits (empty slots and window-keyframe observations left out; the
         # window, the model and the result are the same -- tests/test_gpu_parity.py::test_compact_view_same_result)
-        views = dict(zip(mine, pool.map(lambda w: msgen.make_config(args.workload, seed=w)[0].compact(), mine)))
+        def make(w):
+            v = msgen.make_config(args.workload, seed=w)[0].compact()
+            v = v.discovery_order() if args.order == "discovery" else v
+            return pack_view(v) if args.layout == "packed" else v
+        views = dict(zip(mine, pool.map(make, mine)))
     K, H, M = cfg["K"], cfg["H"], cfg["M"]
     words, rows = (M + 31) // 32, K + H
     in_bytes = sum(v.input_bytes() for v in views.values())
@@ -282,11 +297,28 @@ def main():
         pins.append(p)
         return p.array.ctypes.data
 
+    def pin_blob(arrays):
+        """one pinned blob per window, arrays back to back at 16-byte boundaries (what FlattenWindow lays out): the engine
+        moves such a view with a single copy"""
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 15) // 16 * 16
+        p = eng.pinned((max(total, 16),), np.uint8)
+        pins.append(p)
+        for a, o in zip(arrays, offs):
+            p.array[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+        return [p.array.ctypes.data + o for o in offs]
+
     for w in range(nwin):
         if w in views and not args.no_e2e:
             v = views[w]
-            hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST, pin(v.feat_ptr), pin(v.feat_mp), pin(v.feat_cell),
-                                      pin(v.mp_nobs), pin(v.mp_obs_ptr), pin(v.mp_obs_kf), pin(v.okf_total))
+            if args.layout == "packed":
+                hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
+                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.mp_obs_ptr, v.mp_obs_kf16, v.okf_total]))
+            else:
+                hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
+                                          *pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr, v.mp_obs_kf, v.okf_total]))
         else:
             hv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
         hr[w].keep_bits = pin(np.zeros(words, np.uint32))
@@ -343,7 +375,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        fb = sum(floor_bytes(v.K, v.H, v.M, v.F, v.O) for v in views.values())       # per launch on this rank
+        fb = sum(view_floor_bytes(v) for v in views.values())       # per launch on this rank
         sb = sum(survey_alg_bytes(views[w].K, views[w].H, views[w].M, views[w].F, views[w].O, cr[w].nnz, cr[w].n_cells, cr[w].rounds)
                  for w in mine)
         ab = kernel_alg_bytes([views[w] for w in mine], [cr[w] for w in mine], st_dev["last_row_entries"], st_dev["last_var_visits"])
@@ -354,8 +386,10 @@ def main():
             "metric": METRIC, "value": nwin * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {K} KF x {M} MP KITTI-00-shaped windows (msgen-v1 seeds 0..{nwin-1}), compact "
-                                   "transport form (valid slots + outside observations only, as FlattenWindow emits)",
+            "config": {"workload": f"{args.workload}: {K} KF x {M} MP KITTI-00-shaped windows (msgen-v1 seeds 0..{nwin-1}) in the transport "
+                                   "form FlattenWindow emits: valid slots + outside observations only, map points numbered "
+                                   + ("in discovery order (mnIndexForSparsification)" if args.order == "discovery" else "as generated (random)")
+                                   + f", {args.layout} layout",
                        "windows_per_gpu_per_step": B, "global_windows_per_step": nwin,
                        "N": N, "lambda": msgen.LAMBDA, "grid_lambda": msgen.GRID_LAMBDA,
                        "parallelism": f"window w -> rank w % {world}; one NCCL all-gather of result slots" if world > 1 else "single GPU",

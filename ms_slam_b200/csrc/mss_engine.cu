@@ -73,8 +73,8 @@ struct mss_handle {
     int sm_count = 0;
     int max_ctas_per_sm = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copy[8] = {};
-    int chunk_windows = 8;           // host views are copied / solved in chunks of about this many windows (0 = one chunk)
+    cudaEvent_t ev_ready = nullptr;  // compute stream -> copy stream: the ready flags of this call have been zeroed
+    int overlap_copy = 1;            // host views: copy on the copy stream while the kernel runs (per-window ready flags); 0 = copy first
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     // device arena
@@ -94,7 +94,8 @@ struct mss_handle {
     DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
     DevBuf<uint32_t> out;
     DevBuf<uint8_t> stage;           // host views staged here
-    DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart
+    DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart | ready flags
+    unsigned* h_one = nullptr;       // pinned constant 1: source of the ready-flag copies
     Ctrl* ctrl = nullptr;            // = sync.p
     // pinned host mirrors
     uint8_t* h_meta = nullptr; size_t h_meta_cap = 0;
@@ -181,9 +182,12 @@ int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
     if (!owned) return MSS_OK;
     if (v.F < 0 || v.O < 0) { h->err = "view: negative F/O"; return MSS_E_BADARG; }
     if (v.memory != MSS_MEM_HOST && v.memory != MSS_MEM_DEVICE) { h->err = "view: bad memory kind"; return MSS_E_BADARG; }
+    if (v.layout != MSS_LAYOUT_SOA && v.layout != MSS_LAYOUT_PACKED) { h->err = "view: bad layout"; return MSS_E_BADARG; }
     if (!v.feat_ptr || !v.mp_obs_ptr) { h->err = "view: feat_ptr / mp_obs_ptr is NULL"; return MSS_E_BADARG; }
-    if ((v.F > 0 && (!v.feat_mp || !v.feat_cell)) || (v.M > 0 && !v.mp_nobs) || (v.O > 0 && !v.mp_obs_kf) ||
-        (v.H > 0 && !v.okf_total)) { h->err = "view: NULL array with non-zero size"; return MSS_E_BADARG; }
+    const bool null_arr = v.layout == MSS_LAYOUT_PACKED
+        ? ((v.F > 0 && !v.slots) || (v.M > 0 && !v.mp_nobs16) || (v.O > 0 && !v.mp_obs_kf16))
+        : ((v.F > 0 && (!v.feat_mp || !v.feat_cell)) || (v.M > 0 && !v.mp_nobs) || (v.O > 0 && !v.mp_obs_kf));
+    if (null_arr || (v.H > 0 && !v.okf_total)) { h->err = "view: NULL array with non-zero size"; return MSS_E_BADARG; }
     if (v.memory == MSS_MEM_HOST) {
         if (v.feat_ptr[0] != 0 || v.feat_ptr[v.K] != v.F) { h->err = "view: feat_ptr must start at 0 and end at F"; return MSS_E_BADARG; }
         if (v.mp_obs_ptr[0] != 0 || v.mp_obs_ptr[v.M] != v.O) { h->err = "view: mp_obs_ptr must start at 0 and end at O"; return MSS_E_BADARG; }
@@ -228,23 +232,22 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         if (v.K + v.H > mss::kMaxWindowRows) { h->err = "view: more than 65535 keyframe rows in one window"; return MSS_E_BADARG; }
         Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ftot += v.F; Otot += v.O;
         if (v.memory == MSS_MEM_HOST) {
-            stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + align_up((size_t)v.F * 2, 16) +
-                           align_up((size_t)v.M * 4, 16) + align_up((size_t)(v.M + 1) * 4, 16) + align_up((size_t)v.O * 4, 16) +
-                           align_up((size_t)v.H * 4, 16);
+            const bool pk = v.layout == MSS_LAYOUT_PACKED;
+            stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
+                           align_up((size_t)v.M * (pk ? 2 : 4), 16) + align_up((size_t)(v.M + 1) * 4, 16) +
+                           align_up((size_t)v.O * (pk ? 2 : 4), 16) + align_up((size_t)v.H * 4, 16);
         }
     }
     if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
     const int Rtot = (int)(Ktot + Htot);
 
-    // ---- chunks: host views are handed to the device in chunks, so that the H2D copy of chunk c+1 (copy stream) overlaps
-    //      the solve of chunk c (one cooperative launch per chunk on the compute stream).  Device-resident views: one chunk.
+    // ---- host views travel while the kernel runs: the copies go to the copy stream in queue order, each window followed
+    //      by a 4-byte copy that sets its ready flag; the persistent kernel is launched at once and a group waits for the flag
+    //      of the window it draws.  Device-resident views: no flags.
     bool any_host = false;
     for (int w : local) any_host = any_host || views[w].memory == MSS_MEM_HOST;
-    int nchunks = 1;
-    if (any_host && h->chunk_windows > 0 && nl >= 2 * h->chunk_windows) nchunks = std::min(kMaxChunks, nl / h->chunk_windows);
-    const int csize = (std::max(nl, 1) + nchunks - 1) / nchunks;
-    nchunks = (std::max(nl, 1) + csize - 1) / csize;
-
+    const bool gated = any_host && h->overlap_copy && nl > 1;
+    const int nchunks = 1, csize = std::max(nl, 1);
     // ---- groups (per chunk): the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest
     //      first), so a group that draws a short solve simply takes the next window.  One window -> one group, whole grid. --
     const int max_grid = std::max(1, h->max_ctas_per_sm * h->sm_count);
@@ -280,6 +283,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         ch.sync_off = sync_words;
         sync_words += 32 + (size_t)ch.ngroups * 32;
     }
+    const size_t ready_off = sync_words;
+    sync_words += align_up((size_t)std::max(nl, 1), 32);
     int grid = chunks[0].grid;
 
     int rc;
@@ -305,7 +310,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     // ---- descriptors -----------------------------------------------------------------------------------------------------
     // with one chunk everything runs on the compute stream; with several, copies go to the copy stream and each launch
     // waits for the event recorded after its chunk's copies
-    cudaStream_t cstream = nchunks > 1 ? h->copy_stream : h->stream;
+    cudaStream_t cstream = gated ? h->copy_stream : h->stream;
     WinDesc* hd = reinterpret_cast<WinDesc*>(h->h_meta);
     int64_t h2d = 0;
     size_t soff = 0;
@@ -320,14 +325,19 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         const mss_window_view& v = views[local[i]];
         WinDesc d;
         memset(&d, 0, sizeof(d));
+        const bool pk = v.layout == MSS_LAYOUT_PACKED;
+        d.packed = pk ? 1 : 0;
         if (v.memory == MSS_MEM_HOST) {
             d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
-            d.feat_mp = (const int*)stage(v.feat_mp, (size_t)v.F * 4);
-            d.feat_cell = (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
-            d.mp_nobs = (const int*)stage(v.mp_nobs, (size_t)v.M * 4);
+            d.feat_mp = (const int*)stage(pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
+            d.feat_cell = pk ? nullptr : (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
+            d.mp_nobs = (const int*)stage(pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
             d.mp_obs_ptr = (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
-            d.mp_obs_kf = (const int*)stage(v.mp_obs_kf, (size_t)v.O * 4);
+            d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, (size_t)v.O * (pk ? 2 : 4));
             d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
+        } else if (pk) {
+            d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)v.slots; d.feat_cell = nullptr; d.mp_nobs = (const int*)v.mp_nobs16;
+            d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = (const int*)v.mp_obs_kf16; d.okf_total = v.okf_total;
         } else {
             d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
             d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
@@ -350,29 +360,53 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         }
         for (int i = 0; i < ch.count; ++i) h_gwin[i] = ch.order[i];
     }
-    MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, cstream));
+    // descriptors first, on the compute stream (the kernel needs them at once)
+    MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
     h2d += (int64_t)meta_bytes;
-    // ---- staging copies, chunk by chunk ------------------------------------------------------------------------------------
-    for (int c = 0; c < nchunks; ++c) {
-        const Chunk& ch = chunks[c];
-        for (int i = ch.first; i < ch.first + ch.count; ++i) {
-            const mss_window_view& v = views[local[i]];
-            if (v.memory != MSS_MEM_HOST) continue;
-            const WinDesc& d = hd[i];
-            auto put = [&](const void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream); };
-            put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
-            put(d.feat_mp, v.feat_mp, (size_t)v.F * 4);
-            put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
-            put(d.mp_nobs, v.mp_nobs, (size_t)v.M * 4);
-            put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
-            put(d.mp_obs_kf, v.mp_obs_kf, (size_t)v.O * 4);
-            put(d.okf_total, v.okf_total, (size_t)v.H * 4);
-        }
-        if (nchunks > 1) MSS_CUDA(h, cudaEventRecord(h->ev_copy[c], cstream));
+    MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
+    if (gated) {
+        MSS_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
+        MSS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
     }
+    // ---- staging copies, in queue order ------------------------------------------------------------------------------------
+    auto copy_window = [&](int i) {
+        const mss_window_view& v = views[local[i]];
+        if (v.memory != MSS_MEM_HOST) return;
+        const WinDesc& d = hd[i];
+        const bool pk = v.layout == MSS_LAYOUT_PACKED;
+        auto put = [&](const void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream); };
+        // a view whose arrays lie back to back on the host, in staging order and each at the next 16-byte boundary (one
+        // pinned blob per window, as FlattenWindow lays them out), travels with ONE copy
+        {
+            const void* src[7] = {v.feat_ptr, pk ? (const void*)v.slots : (const void*)v.feat_mp, pk ? nullptr : (const void*)v.feat_cell,
+                                  pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, v.mp_obs_ptr,
+                                  pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, v.okf_total};
+            const size_t len[7] = {(size_t)(v.K + 1) * 4, (size_t)v.F * 4, pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+                                   (size_t)(v.M + 1) * 4, (size_t)v.O * (pk ? 2 : 4), (size_t)v.H * 4};
+            const uint8_t* base = static_cast<const uint8_t*>(src[0]);
+            size_t off = 0, end = 0;
+            bool blob = (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
+            for (int a = 0; a < 7 && blob; ++a) {
+                if (pk && a == 2) continue;
+                if (len[a]) { if (static_cast<const uint8_t*>(src[a]) != base + off) blob = false; end = off + len[a]; }
+                off += align_up(len[a], 16);
+            }
+            if (blob) { put(d.feat_ptr, base, end); return; }
+        }
+        put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
+        put(d.feat_mp, pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
+        if (!pk) put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
+        put(d.mp_nobs, pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
+        put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
+        put(d.mp_obs_kf, pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, (size_t)v.O * (pk ? 2 : 4));
+        put(d.okf_total, v.okf_total, (size_t)v.H * 4);
+    };
+    const Chunk& ch0 = chunks[0];
+    unsigned* d_ready = h->sync.p + ready_off;
+    if (!gated) for (int q = 0; q < ch0.count; ++q) copy_window(ch0.order[q]);
     MSS_CUDA(h, cudaGetLastError());
 
-    // ---- launches -----------------------------------------------------------------------------------------------------
+    // ---- launch -----------------------------------------------------------------------------------------------------------
     Params P;
     memset(&P, 0, sizeof(P));
     P.win = reinterpret_cast<const WinDesc*>(h->meta.p);
@@ -393,28 +427,31 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
     P.watchdog_ns = h->watchdog_ns;
     P.tail_vars = std::min(h->tail_vars, mss::kTailVars); P.tail_ents = std::min(h->tail_ents, mss::kTailEnts);
+    P.ready = gated ? d_ready : nullptr;
 
     float dev_ms = 0.f;
     if (nl > 0) {
-        MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
         if (h->trace_on) MSS_CUDA(h, cudaMemsetAsync(h->trace.p, 0, (size_t)nl * mss::kTraceCap * sizeof(uint2), h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        for (int c = 0; c < nchunks; ++c) {
-            const Chunk& ch = chunks[c];
-            if (ch.count == 0) continue;
-            P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + ch.off_grp);
-            P.cta_grp = reinterpret_cast<const int*>(h->meta.p + ch.off_cta);
-            P.gwin = reinterpret_cast<const int*>(h->meta.p + ch.off_gwin);
-            P.ctrl = reinterpret_cast<Ctrl*>(h->sync.p + ch.sync_off);
-            P.gbar = h->sync.p + ch.sync_off + 32;
-            P.nwin = ch.count; P.ngroups = ch.ngroups;
-            void* args[] = {(void*)&P};
-            if (nchunks > 1) MSS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
-            MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(ch.grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
-            h->stats.kernel_launches += 1;
-            grid = std::max(grid, ch.grid);
-        }
+        P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + ch0.off_grp);
+        P.cta_grp = reinterpret_cast<const int*>(h->meta.p + ch0.off_cta);
+        P.gwin = reinterpret_cast<const int*>(h->meta.p + ch0.off_gwin);
+        P.ctrl = reinterpret_cast<Ctrl*>(h->sync.p + ch0.sync_off);
+        P.gbar = h->sync.p + ch0.sync_off + 32;
+        P.nwin = ch0.count; P.ngroups = ch0.ngroups;
+        void* args[] = {(void*)&P};
+        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(ch0.grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
+        h->stats.kernel_launches += 1;
+        grid = ch0.grid;
         MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        if (gated) {
+            // the kernel is running (or queued); feed it: window after window in queue order, flag after data
+            for (int q = 0; q < ch0.count; ++q) {
+                copy_window(ch0.order[q]);
+                MSS_CUDA(h, cudaMemcpyAsync(d_ready + q, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream));
+            }
+            h2d += 4ll * ch0.count;
+        }
     } else {
         grid = 0;
     }
@@ -441,6 +478,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         if (r.kf_slack && s.rows) MSS_CUDA(h, cudaMemcpyAsync(r.kf_slack, slot + mss::kHdrWords + s.words_keep + s.rows, (size_t)s.rows * 4, cudaMemcpyDeviceToDevice, h->stream));
     }
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (gated) MSS_CUDA(h, cudaStreamSynchronize(h->copy_stream));     // (only an aborted launch can finish before its copies)
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
     unsigned long long row_entries = 0, var_visits = 0;
     for (int c = 0; c < nchunks && nl > 0; ++c) {
@@ -562,9 +600,10 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
     if ((e = cudaHostAlloc((void**)&h->h_ctrl, kMaxChunks * sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    for (int c = 0; c < kMaxChunks; ++c)
-        if ((e = cudaEventCreateWithFlags(&h->ev_copy[c], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if (const char* cw = getenv("MSS_CHUNK_WINDOWS")) h->chunk_windows = atoi(cw);
+    if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaHostAlloc((void**)&h->h_one, 64, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    *h->h_one = 1u;
+    if (const char* oc = getenv("MSS_OVERLAP_COPY")) h->overlap_copy = atoi(oc);
     h->stats.sm_count = h->sm_count;
     *out = h;
     return MSS_OK;
@@ -581,7 +620,8 @@ void mss_destroy(mss_handle* h) {
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    for (int c = 0; c < kMaxChunks; ++c) if (h->ev_copy[c]) cudaEventDestroy(h->ev_copy[c]);
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+    if (h->h_one) cudaFreeHost(h->h_one);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -74,7 +74,8 @@ struct WinDesc {
     int obs_base;    // first entry of this window's outside rows in ent[] / live[] (after all keyframe segments)
     int var_base;    // global variable index of map point 0 (multiple of kVarTile)
     int out_off;     // u32 word offset of this window's result slot
-    int pad_[3];
+    int packed;      // MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs / mp_obs_kf are u16 arrays
+    int pad_[2];
 };
 
 // per-phase counters; three copies rotate so that a copy is zeroed two phases before it is used again
@@ -138,6 +139,8 @@ struct Params {
     double lam, glam;
     unsigned long long watchdog_ns;
     int tail_vars, tail_ents;    // residual size handed to the shared-memory tail (<= kTailVars / kTailEnts; 0 = never)
+    const unsigned* ready;       // optional [nwin] (queue order): set to 1 by a stream-ordered host->device copy once the views
+                                 // of that window have landed in the staging buffer; nullptr = everything is resident
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,6 +161,11 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ unsigned f32_orderable(float g) {
     unsigned b = __float_as_uint(g);
@@ -335,6 +343,28 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
     return (int)ceil((double)r - 1e-5);
 }
 
+// View accessors: the SoA layout carries i32 / u16 arrays, the packed transport layout u32 slots and u16 tables
+// (include/mss.h, mss_layout); the branch is uniform per window.
+__device__ __forceinline__ int ld_nobs(const WinDesc& D, int mp) {
+    return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : __ldg(D.mp_nobs + mp);
+}
+__device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) {
+    return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_obs_kf) + o) : __ldg(D.mp_obs_kf + o);
+}
+// slot i of the view -> (map point or -1, cell or kCellNone)
+__device__ __forceinline__ void ld_slot(const WinDesc& D, int i, int& mp, unsigned& c) {
+    if (D.packed) {
+        const uint32_t s = __ldg(reinterpret_cast<const uint32_t*>(D.feat_mp) + i);
+        if (s == kEntInvalid) { mp = -1; c = kCellNone; return; }
+        mp = (int)(s >> kCellBits);
+        c = s & kCellCov;
+        if (c == kCellCov) c = kCellNone;
+    } else {
+        mp = __ldg(D.feat_mp + i);
+        c = __ldg(D.feat_cell + i);
+    }
+}
+
 // A row's entries held in registers: warp w owns a contiguous chunk of the list, lane-strided inside it, so global
 // accesses are coalesced and (warp, b, lane) order is list order (needed for the stable compaction).
 template <int EPT>
@@ -393,7 +423,7 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
             const int idx = wid * per + b * 32 + lane;
             int mp = -1;
             unsigned c = kCellNone;
-            if (b < nb && idx < nslots) { mp = __ldg(D.feat_mp + beg + idx); c = __ldg(D.feat_cell + beg + idx); }
+            if (b < nb && idx < nslots) ld_slot(D, beg + idx, mp, c);
             e[b] = kEntInvalid;
             if (mp < -1 || mp >= D.M) err |= ERR_INDEX;
             else if (mp >= 0) {
@@ -447,10 +477,11 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
         __syncthreads();
         int nz = 0, ncell = 0, z = 0;
         for (int i = threadIdx.x; i < nslots; i += kThreads) {
-            const int mp = __ldg(D.feat_mp + beg + i);
+            int mp;
+            unsigned c;
+            ld_slot(D, beg + i, mp, c);
             if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
             if (mp >= D.M) { err |= ERR_INDEX; continue; }
-            const unsigned c = __ldg(D.feat_cell + beg + i);
             if (c == kCellNone) { seen_w[mp] = 1; continue; }
             if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
             ++nz;
@@ -463,8 +494,9 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
             const int i = base + (int)threadIdx.x;
             uint32_t e = kEntInvalid;
             if (i < nslots) {
-                const int mp = __ldg(D.feat_mp + beg + i);
-                const unsigned c = __ldg(D.feat_cell + beg + i);
+                int mp;
+                unsigned c;
+                ld_slot(D, beg + i, mp, c);
                 if (mp >= 0 && mp < D.M && c < (unsigned)kCells) e = ((uint32_t)mp << kCellBits) | c;
             }
             int total;
@@ -550,7 +582,7 @@ __device__ void w2_vars_and_outside_counts(const Params& P, const WinDesc& D, Wi
         const int mp = base + j * kVarTile + (int)threadIdx.x;
         isvar[j] = a[j] != 0ull;
         if (mp < D.M || mp < ((D.M + kVarTile - 1) / kVarTile) * kVarTile) P.st[D.var_base + mp] = isvar[j] ? (uint8_t)ST_FREE : (uint8_t)ST_NOTVAR;
-        if (isvar[j] || sn[j]) nmax = max(nmax, __ldg(D.mp_nobs + mp));
+        if (isvar[j] || sn[j]) nmax = max(nmax, ld_nobs(D, mp));
         nv += isvar[j] ? 1 : 0;
     }
     nmax = block_max(S, nmax);
@@ -571,7 +603,7 @@ __device__ void w2_vars_and_outside_counts(const Params& P, const WinDesc& D, Wi
 #pragma unroll
         for (int j = 0; j < kVpt; ++j) {
             const int o = o0 + j * kThreads + (int)threadIdx.x;
-            kf[j] = o < p1 ? __ldg(D.mp_obs_kf + o) : 0;
+            kf[j] = o < p1 ? ld_obs_kf(D, o) : 0;
         }
 #pragma unroll
         for (int j = 0; j < kVpt; ++j) {
@@ -655,7 +687,7 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
         const int mp = base + j * kVarTile + (int)threadIdx.x;
         a[j] = 0ull;
         nobs[j] = 0;
-        if (isvar[j]) { a[j] = P.acc[D.var_base + mp]; nobs[j] = __ldg(D.mp_nobs + mp); any = true; }
+        if (isvar[j]) { a[j] = P.acc[D.var_base + mp]; nobs[j] = ld_nobs(D, mp); any = true; }
     }
     unsigned nout[kVpt] = {0u, 0u, 0u, 0u};
     if (D.H > 0 && __syncthreads_or(any)) {
@@ -672,7 +704,7 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
 #pragma unroll
                 for (int j = 0; j < kVpt; ++j) {
                     const int o = o0 + j * kThreads + (int)threadIdx.x;
-                    kf[j] = o < p1 ? __ldg(D.mp_obs_kf + o) : 0;
+                    kf[j] = o < p1 ? ld_obs_kf(D, o) : 0;
                 }
 #pragma unroll
                 for (int j = 0; j < kVpt; ++j) {
@@ -1205,7 +1237,7 @@ __device__ void var_list_phase(const Params& P, const WinDesc& D, WinState& ws, 
             if (s == ST_FREE) {
                 const unsigned long long a = P.acc[g];
                 if (a) P.acc[g] = 0ull;
-                prop_decide(P, a, ws.n_max - __ldg(D.mp_nobs + mp), &P.st[g], &P.gain[g], P.deg[g], c0, c1, c2);
+                prop_decide(P, a, ws.n_max - ld_nobs(D, mp), &P.st[g], &P.gain[g], P.deg[g], c0, c1, c2);
             }
             prop_commit(rc, vdst, mp, c0, c1, c2);
         } else if (mode == MODE_GREEDY) {
@@ -1234,7 +1266,7 @@ __device__ void var_tile_phase(const Params& P, const WinDesc& D, WinState& ws, 
             const unsigned long long a = P.acc[g];
             if (a) P.acc[g] = 0ull;
             const double critc = (double)(a & 0xFFFFu), critr = (double)((a >> 32) & 0xFFFFu);
-            const double cost = (double)(ws.n_max - __ldg(D.mp_nobs + mp));
+            const double cost = (double)(ws.n_max - ld_nobs(D, mp));
             const double dF = __dadd_rn(__dadd_rn(-cost, __dmul_rn(P.glam, critc)), __dmul_rn(P.lam, critr));
             if (dF < 0.0) { P.st[g] = ST_CAND; P.gain[g] = (float)(-dF); c0 = 1; }
         }
@@ -1259,7 +1291,7 @@ __device__ void var_tile_phase(const Params& P, const WinDesc& D, WinState& ws, 
         const int widx = mp >> 5;
         if ((threadIdx.x & 31) == 0 && widx < words) P.out[D.out_off + kHdrWords + widx] = word;
         int kept = (s == ST_IN) ? 1 : 0;
-        int cost = kept ? (ws.n_max - __ldg(D.mp_nobs + mp)) : 0;    // < 2^31 per block: 256 * nMax
+        int cost = kept ? (ws.n_max - ld_nobs(D, mp)) : 0;    // < 2^31 per block: 256 * nMax
         block_sum3(S, kept, cost, c2);
         if (threadIdx.x == 0 && kept) {
             atomicAdd(&rc.nkept, (unsigned)kept);
@@ -1510,7 +1542,7 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
         const int g = D.var_base + mp;
         T.mp[i] = (uint32_t)mp;
         T.st[i] = P.st[g];
-        T.cost[i] = ws.n_max - __ldg(D.mp_nobs + mp);
+        T.cost[i] = ws.n_max - ld_nobs(D, mp);
         T.acc_lo[i] = 0u;
         T.acc_hi[i] = 0u;
         T.gain[i] = P.gain[g];
@@ -1707,7 +1739,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
             const int nb = __ldg(D.feat_ptr + k + G.ncta), ne = __ldg(D.feat_ptr + k + G.ncta + 1);
             if (nb >= 0 && ne <= D.F) {
                 for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
-                for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
+                if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
             }
         }
         w1_build_row(P, D, ws, k, tab, S);
@@ -1866,7 +1898,22 @@ __global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Param
     __syncthreads();
     // dynamic window queue: a group that finishes early takes the next window (largest windows are queued first)
     while (true) {
-        if (G.cta == 0 && threadIdx.x == 0) G.bar[1] = atomicAdd(&P.ctrl->queue, 1u);
+        if (G.cta == 0 && threadIdx.x == 0) {
+            const unsigned q = atomicAdd(&P.ctrl->queue, 1u);
+            if (P.ready && q < (unsigned)P.nwin) {
+                // host views are copied while the kernel runs: wait for this window's flag (written by a copy that is
+                // stream-ordered after the copies of its arrays); the group barrier publishes it to the other CTAs
+                unsigned spins = 0;
+                while (ld_acquire_sys_u32(P.ready + q) == 0u) {
+                    __nanosleep(200);
+                    if ((++spins & 0x3FFu) == 0u) {
+                        if (*(volatile int*)&P.ctrl->abort) break;
+                        if (globaltimer_ns() - G.t0 > P.watchdog_ns) { atomicExch(&P.ctrl->abort, 1); break; }
+                    }
+                }
+            }
+            G.bar[1] = q;
+        }
         if (!group_sync(P, G)) break;
         const unsigned wi = *(volatile unsigned*)&G.bar[1];
         if (wi >= (unsigned)P.nwin) break;

@@ -10,13 +10,14 @@ import os
 from dataclasses import dataclass
 import numpy as np
 
-from .window import WindowView
+from .window import WindowView, PackedView
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmss.so")
 
 MSS_OK, MSS_E_BADARG, MSS_E_CUDA, MSS_E_NCCL, MSS_E_NOMEM, MSS_E_NOCONVERGE, MSS_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
+LAYOUT_SOA, LAYOUT_PACKED = 0, 1
 UNIQUE_ID_BYTES = 128
 
 
@@ -36,7 +37,15 @@ class mss_window_view(C.Structure):
     _fields_ = [("K", C.c_int32), ("H", C.c_int32), ("M", C.c_int32), ("F", C.c_int32), ("O", C.c_int32),
                 ("memory", C.c_int32),
                 ("feat_ptr", C.c_void_p), ("feat_mp", C.c_void_p), ("feat_cell", C.c_void_p), ("mp_nobs", C.c_void_p),
-                ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p)]
+                ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
+                ("layout", C.c_int32), ("reserved", C.c_int32),
+                ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("mp_obs_kf16", C.c_void_p)]
+
+
+def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, mp_obs_ptr, mp_obs_kf16, okf_total) -> "mss_window_view":
+    """MSS_LAYOUT_PACKED view from raw addresses"""
+    return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, mp_obs_ptr, None, okf_total,
+                           LAYOUT_PACKED, 0, slots, mp_nobs16, mp_obs_kf16)
 
 
 class mss_result(C.Structure):
@@ -155,9 +164,13 @@ class DeviceView:
     """A window view resident in device memory (inputs already in HBM: bench `value`, MSS_MEM_DEVICE)."""
 
     _ARR = ("feat_ptr", "feat_mp", "feat_cell", "mp_nobs", "mp_obs_ptr", "mp_obs_kf", "okf_total")
+    _ARR_PACKED = ("feat_ptr", "slots", "mp_nobs16", "mp_obs_ptr", "mp_obs_kf16", "okf_total")
 
-    def __init__(self, engine: "Engine", view: WindowView):
+    def __init__(self, engine: "Engine", view):
         self.engine = engine
+        self.packed = isinstance(view, PackedView)
+        if self.packed:
+            self._ARR = self._ARR_PACKED
         self.K, self.H, self.M, self.F, self.O = view.K, view.H, view.M, view.F, view.O
         self.ptrs = {}
         lib, h = engine.lib, engine.handle
@@ -175,6 +188,8 @@ class DeviceView:
         self.d_slack = lib.mss_device_alloc(h, max(rows * 4, 4))
 
     def c_view(self) -> mss_window_view:
+        if self.packed:
+            return packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR])
         return mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR])
 
     def fetch(self):
@@ -267,7 +282,11 @@ class Engine:
 
     # -- solve ------------------------------------------------------------------------------------------------
     @staticmethod
-    def _host_view(v: WindowView) -> mss_window_view:
+    def _host_view(v) -> mss_window_view:
+        if isinstance(v, PackedView):
+            return packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
+                                 v.mp_nobs16.ctypes.data, v.mp_obs_ptr.ctypes.data, v.mp_obs_kf16.ctypes.data,
+                                 v.okf_total.ctypes.data)
         return mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
                                v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
                                v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data)

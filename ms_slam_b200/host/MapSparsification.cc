@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <thread>
@@ -61,8 +62,65 @@ bool ReadSparsificationSettings(const std::string& path, SparsificationSettings&
 // ---------------------------------------------------------------------------------------------------------------------
 // flatten: pointer graph -> mss_window_view
 // ---------------------------------------------------------------------------------------------------------------------
+WindowSnapshot::Blob::~Blob() {
+    if (!p) return;
+    if (pinned) mss_host_free(p); else std::free(p);
+}
+
+void WindowSnapshot::Blob::Reserve(size_t bytes) {
+    if (bytes <= cap && p) return;
+    if (p) { if (pinned) mss_host_free(p); else std::free(p); p = nullptr; cap = 0; }
+    const size_t ncap = bytes + bytes / 2 + 4096;
+    p = static_cast<uint8_t*>(mss_host_alloc(ncap));          // NULL without a CUDA device: plain memory still works
+    pinned = p != nullptr;
+    if (!p) p = static_cast<uint8_t*>(std::malloc(ncap));
+    cap = p ? ncap : 0;
+}
+
+void WindowSnapshot::Pack() {
+    packed = false;
+    const size_t M = mp_nobs.size(), F = feat_mp.size(), O = mp_obs_kf.size();
+    if (M > (1u << 20) || K + H > 65535) return;
+    for (int32_t n : mp_nobs) if (n < 0 || n > 65535) return;
+    auto up = [](size_t x) { return (x + 15) / 16 * 16; };
+    off_slots = up((size_t)(K + 1) * 4);
+    off_nobs = off_slots + up(F * 4);
+    off_obs_ptr = off_nobs + up(M * 2);
+    off_obs_kf = off_obs_ptr + up((M + 1) * 4);
+    off_okf = off_obs_kf + up(O * 2);
+    const size_t total = off_okf + up((size_t)H * 4);
+    if (!blob) blob = std::make_shared<Blob>();
+    blob->Reserve(total);
+    if (!blob->p) return;
+    memcpy(blob->p, feat_ptr.data(), (size_t)(K + 1) * 4);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(blob->p + off_slots);
+    for (size_t i = 0; i < F; ++i) {
+        const uint32_t cell = feat_cell[i] == (uint16_t)MSS_CELL_NONE ? MSS_SLOT_CELL_NONE : (uint32_t)feat_cell[i];
+        slots[i] = feat_mp[i] < 0 ? MSS_SLOT_EMPTY : (((uint32_t)feat_mp[i] << 12) | cell);
+    }
+    uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
+    for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
+    memcpy(blob->p + off_obs_ptr, mp_obs_ptr.data(), (M + 1) * 4);
+    uint16_t* okf = reinterpret_cast<uint16_t*>(blob->p + off_obs_kf);
+    for (size_t o = 0; o < O; ++o) okf[o] = (uint16_t)mp_obs_kf[o];
+    if (H) memcpy(blob->p + off_okf, okf_total.data(), (size_t)H * 4);
+    packed = true;
+}
+
 mss_window_view WindowSnapshot::View() const {
-    mss_window_view v;
+    mss_window_view v{};
+    if (packed && blob && blob->p) {
+        v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)mp_obs_kf.size();
+        v.memory = MSS_MEM_HOST;
+        v.layout = MSS_LAYOUT_PACKED;
+        v.feat_ptr = reinterpret_cast<const int32_t*>(blob->p);
+        v.slots = reinterpret_cast<const uint32_t*>(blob->p + off_slots);
+        v.mp_nobs16 = reinterpret_cast<const uint16_t*>(blob->p + off_nobs);
+        v.mp_obs_ptr = reinterpret_cast<const int32_t*>(blob->p + off_obs_ptr);
+        v.mp_obs_kf16 = reinterpret_cast<const uint16_t*>(blob->p + off_obs_kf);
+        v.okf_total = reinterpret_cast<const int32_t*>(blob->p + off_okf);
+        return v;
+    }
     v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)mp_obs_kf.size();
     v.memory = MSS_MEM_HOST;
     v.feat_ptr = feat_ptr.data(); v.feat_mp = feat_mp.data(); v.feat_cell = feat_cell.data();
@@ -147,6 +205,7 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     out.H = H;
     out.okf_total.resize(H);
     for (int j = 0; j < H; ++j) out.okf_total[j] = out.vpOutsideKFs[j]->GetNumberMPs();      // :146
+    out.Pack();
     out.flatten_ms = MsSince(t0);
 }
 

@@ -94,6 +94,30 @@ class WindowView:
         v.meta = dict(self.meta, compact=True)
         return v
 
+    def discovery_order(self) -> "WindowView":
+        """The same window with the map-point table renumbered the way the C++ FlattenWindow (and the reference, through
+        mnIndexForSparsification, /root/reference/src/MapSparsification.cc:91-99) numbers it: in order of first appearance
+        when the keyframes are walked in window order and their slots in slot order.  Map points that sit in no slot of a
+        window keyframe (they cannot be reached by that walk) keep their relative order behind all others.  Returns a new
+        view; `meta["mp_perm"][new] = old` maps results back."""
+        valid = self.feat_mp >= 0
+        first = np.full(self.M, np.iinfo(np.int64).max, np.int64)
+        pos = np.nonzero(valid)[0]
+        np.minimum.at(first, self.feat_mp[pos], pos)
+        perm = np.argsort(first, kind="stable")             # new -> old
+        inv = np.empty(self.M, np.int64)
+        inv[perm] = np.arange(self.M)
+        feat_mp = np.where(valid, inv[np.maximum(self.feat_mp, 0)], -1).astype(self.feat_mp.dtype)
+        cnt = np.diff(self.mp_obs_ptr)[perm]
+        obs_ptr = np.zeros(self.M + 1, self.mp_obs_ptr.dtype)
+        obs_ptr[1:] = np.cumsum(cnt)
+        src = np.repeat(self.mp_obs_ptr[:-1][perm] - obs_ptr[:-1], cnt) + np.arange(int(obs_ptr[-1]))
+        v = WindowView(K=self.K, H=self.H, feat_ptr=self.feat_ptr, feat_mp=feat_mp, feat_cell=self.feat_cell,
+                       mp_nobs=self.mp_nobs[perm], mp_obs_ptr=obs_ptr, mp_obs_kf=self.mp_obs_kf[src], okf_total=self.okf_total,
+                       kf_gid=self.kf_gid, mp_gid=self.mp_gid[perm] if self.mp_gid is not None and len(self.mp_gid) == self.M else self.mp_gid)
+        v.meta = dict(self.meta, discovery_order=True, mp_perm=perm)
+        return v
+
     def validate(self) -> None:
         K, H, F, M, O = self.K, self.H, self.F, self.M, self.O
         if K < 0 or H < 0:
@@ -129,6 +153,53 @@ class WindowView:
     def load(cls, path: str) -> "WindowView":
         z = np.load(path)
         return cls(K=int(z["K"]), H=int(z["H"]), **{n: z[n] for n in cls._ARRAYS})
+
+
+SLOT_CELL_NONE = 0xFFF        # include/mss.h MSS_SLOT_CELL_NONE
+SLOT_EMPTY = 0xFFFFFFFF       # include/mss.h MSS_SLOT_EMPTY
+
+
+@dataclass
+class PackedView:
+    """MSS_LAYOUT_PACKED form of a window (include/mss.h): u32 slots = (map point << 12) | cell, u16 tables.  Same window,
+    same map-point numbering, about 0.6x the bytes of the SoA form."""
+    K: int
+    H: int
+    M: int
+    feat_ptr: np.ndarray      # int32 [K+1]
+    slots: np.ndarray         # uint32 [F]
+    mp_nobs16: np.ndarray     # uint16 [M]
+    mp_obs_ptr: np.ndarray    # int32 [M+1]
+    mp_obs_kf16: np.ndarray   # uint16 [O]
+    okf_total: np.ndarray     # int32 [H]
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def F(self) -> int:
+        return int(self.slots.shape[0])
+
+    @property
+    def O(self) -> int:
+        return int(self.mp_obs_kf16.shape[0])
+
+    def input_bytes(self) -> int:
+        return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.mp_obs_ptr.nbytes +
+                   self.mp_obs_kf16.nbytes + self.okf_total.nbytes)
+
+
+def pack_view(v: WindowView) -> PackedView:
+    """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges."""
+    if v.M > (1 << 20) or v.K + v.H > 65535:
+        raise ValueError("window too large for the packed layout")
+    if v.M and int(v.mp_nobs.max()) > 65535:
+        raise ValueError("Observations() above 65535")
+    mp = v.feat_mp.astype(np.int64)
+    cell = np.where(v.feat_cell == CELL_NONE, SLOT_CELL_NONE, v.feat_cell).astype(np.int64)
+    slots = np.where(mp >= 0, (mp << 12) | cell, SLOT_EMPTY).astype(np.uint32)
+    return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
+                      mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), mp_obs_ptr=v.mp_obs_ptr,
+                      mp_obs_kf16=np.ascontiguousarray(v.mp_obs_kf.astype(np.uint16)), okf_total=v.okf_total,
+                      meta=dict(v.meta, packed=True))
 
 
 def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:

@@ -141,27 +141,65 @@ def test_compact_view_same_result(eng, name, seed):
     check_against_cpu(view, N, comp)
 
 
-def test_chunked_host_batch_equals_single_launch(build_native):
-    """Host views are copied and solved in chunks (copy of chunk c+1 overlaps the solve of chunk c): same results."""
+def test_overlapped_host_batch_equals_copy_first(build_native):
+    """Host views travel while the persistent kernel runs (per-window ready flags set by stream-ordered copies); the result
+    is the same as copying everything first, and it is still one launch."""
     import os
     from ms_slam_b200.engine import Engine
     views = [msgen.make_config("live", 20 + i)[0] for i in range(12)]
     N = 100
-    os.environ["MSS_CHUNK_WINDOWS"] = "3"
-    try:
-        e1 = Engine(N=N, lam=LAM, grid_lam=GLAM)
-    finally:
-        os.environ["MSS_CHUNK_WINDOWS"] = "0"
+    e1 = Engine(N=N, lam=LAM, grid_lam=GLAM)                 # default: overlapped
+    os.environ["MSS_OVERLAP_COPY"] = "0"
     try:
         e2 = Engine(N=N, lam=LAM, grid_lam=GLAM)
     finally:
-        del os.environ["MSS_CHUNK_WINDOWS"]
-    r1, r2 = e1.solve_batch(views), e2.solve_batch(views)
-    assert e1.stats()["kernel_launches"] == 4 and e2.stats()["kernel_launches"] == 1
+        del os.environ["MSS_OVERLAP_COPY"]
+    for _ in range(3):                                       # staging buffers are reused from call to call
+        r1, r2 = e1.solve_batch(views), e2.solve_batch(views)
+    assert e1.stats()["kernel_launches"] == 3 and e2.stats()["kernel_launches"] == 3
     for v, a, b in zip(views, r1, r2):
         assert np.array_equal(a.keep_bits, b.keep_bits) and a.objective == b.objective and a.rounds == b.rounds
         check_against_cpu(v, N, a)
     e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("name,seed", [("c1", 0), ("live", 3), ("c3", 1), ("c4", 1001)])
+def test_packed_layout_same_result(eng, name, seed):
+    """MSS_LAYOUT_PACKED (u32 slots, u16 tables) is the same window: bit-identical result, host and device resident."""
+    from ms_slam_b200.engine import DeviceView
+    from ms_slam_b200.window import pack_view
+    view, N = msgen.make_config(name, seed)
+    eng.set_params(N, LAM, GLAM)
+    soa = eng.solve(view)
+    for pv in (pack_view(view), pack_view(view.compact())):
+        pk = eng.solve(pv)
+        assert np.array_equal(soa.keep_bits, pk.keep_bits) and np.array_equal(soa.kf_cov, pk.kf_cov)
+        assert (soa.objective, soa.rounds, soa.n_vars, soa.n_cells, soa.nnz, soa.n_max) == \
+               (pk.objective, pk.rounds, pk.n_vars, pk.n_cells, pk.nnz, pk.n_max)
+        dv = DeviceView(eng, pv)
+        rd = eng.solve(dv)
+        assert np.array_equal(soa.keep_bits, rd.keep_bits) and soa.objective == rd.objective
+        dv.free()
+    check_against_cpu(view, N, pk)
+
+
+@pytest.mark.parametrize("name,seed", [("c1", 2), ("live", 5), ("c3", 0)])
+def test_discovery_order_view(eng, name, seed):
+    """FlattenWindow's numbering (map points in discovery order): parity with the emulation on the renumbered view, and the
+    selection mapped back to the original numbering has the same objective under the original model up to tie-breaks
+    (both within the 1 % bar of the same bound)."""
+    from ms_slam_b200.window import pack_view
+    view, N = msgen.make_config(name, seed)
+    eng.set_params(N, LAM, GLAM)
+    dview = view.compact().discovery_order()
+    res = eng.solve(pack_view(dview))
+    F = check_against_cpu(dview, N, res)
+    keep_old = np.ones(view.M, bool)
+    keep_old[dview.meta["mp_perm"]] = res.keep
+    model = om.build_model(view, N)
+    assert om.objective(model, om.keep_to_x(model, keep_old), N, LAM, GLAM) == F
+    base = eng.solve(view)
+    assert abs(F - base.objective) <= 0.002 * base.objective
 
 
 def test_edge_cases(eng):
