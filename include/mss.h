@@ -65,9 +65,11 @@ typedef struct mss_config {
     float   lambda;            /* Sparsification.Lambda      (mfLambda: cost of one missing point in a keyframe row) */
     float   grid_lambda;       /* Sparsification.GridLambda  (mfGridLambda: cost of one uncovered occupied cell) */
     int32_t max_rounds;        /* cap on propagation+greedy rounds per window (0 -> 256) */
-    int32_t all_rule_steps;    /* greedy steps that use the strict conflict-free rule before falling back (0 -> 64) */
+    int32_t all_rule_steps;    /* greedy steps that use the strict conflict-free rule before a deficient row may also nominate its
+                                  top-deficit candidates on its own (0 = none, the default: rows nominate from the first greedy step) */
     int32_t max_drop_rounds;   /* cap on reverse-delete rounds (0 -> 16) */
-    int32_t flags;             /* reserved, 0 */
+    int32_t stall_den;         /* a propagation round that decides fewer than 1/stall_den of the undecided points is followed by a
+                                  greedy step instead of another propagation round (0 -> 8, negative = never) */
 } mss_config;
 
 /* One window, flattened (SoA).  Snapshot of the pointer graph Sparsifying() walks:

@@ -424,6 +424,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     P.Ftot = (int)Ftot;
     P.N = h->cfg.min_points;
     P.max_rounds = h->cfg.max_rounds; P.all_rule_steps = h->cfg.all_rule_steps; P.max_drop_rounds = h->cfg.max_drop_rounds;
+    P.stall_den = h->cfg.stall_den;
     P.lam = (double)h->cfg.lambda; P.glam = (double)h->cfg.grid_lambda;
     P.watchdog_ns = h->watchdog_ns;
     P.tail_vars = std::min(h->tail_vars, mss::kTailVars); P.tail_ents = std::min(h->tail_ents, mss::kTailEnts);
@@ -569,7 +570,9 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if (!h) return MSS_E_NOMEM;
     h->cfg = *cfg;
     if (h->cfg.max_rounds <= 0) h->cfg.max_rounds = 256;
-    if (h->cfg.all_rule_steps <= 0) h->cfg.all_rule_steps = 64;
+    if (h->cfg.all_rule_steps < 0) h->cfg.all_rule_steps = 0;
+    if (h->cfg.stall_den == 0) h->cfg.stall_den = 8;
+    else if (h->cfg.stall_den < 0) h->cfg.stall_den = 0;
     if (h->cfg.max_drop_rounds < 0) h->cfg.max_drop_rounds = 0;
     else if (h->cfg.max_drop_rounds == 0) h->cfg.max_drop_rounds = 16;
     h->device = cfg->device;

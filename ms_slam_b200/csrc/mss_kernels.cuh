@@ -136,6 +136,7 @@ struct Params {
     int Ftot;                // outside-row segments start at ent + Ftot
     int N;
     int max_rounds, all_rule_steps, max_drop_rounds;
+    int stall_den;               // a PROP round that decides fewer than nfree / stall_den points is followed by GREEDY (0 = off)
     double lam, glam;
     unsigned long long watchdog_ns;
     int tail_vars, tail_ents;    // residual size handed to the shared-memory tail (<= kTailVars / kTailEnts; 0 = never)
@@ -1078,8 +1079,8 @@ __device__ __forceinline__ void warp_row_greedy(const Params& P, const WinDesc& 
 // of the IN points; both write the row's coverage / slack and the uncovered-cell count (the read-out uses the values of
 // the last sweep, which is the one that found nothing left to drop).
 template <int EPT>
-__device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, int n, const uint32_t* src, int need, int par,
-                                            bool accumulate, unsigned* tab, BlockScratch& S, int& cin, int& ccells) {
+__device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, int n, const uint32_t* src, uint32_t* dst, int need,
+                                            int par, bool accumulate, unsigned* tab, BlockScratch& S, int& cin, int& ccells) {
     const uint8_t* st_w = P.st + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1090,20 +1091,33 @@ __device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, i
     for (int b = 0; b < EPT; ++b)
         if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
     __syncthreads();
+    unsigned m[EPT];
 #pragma unroll
     for (int b = 0; b < EPT; ++b) {
-        if (X.e[b] == kEntInvalid || X.s[b] != ST_IN) continue;
-        ++cin;
+        const bool in = X.e[b] != kEntInvalid && X.s[b] == ST_IN;
+        m[b] = __ballot_sync(0xFFFFFFFFu, in);
+        if (!in) continue;
         const unsigned cell = X.e[b] & kCellCov;
         if (cell != kCellCov && atomicAdd(&tab[cell], 1u) == 0u) ++ccells;
     }
-    cin = __reduce_add_sync(0xFFFFFFFFu, cin);
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) cin += __popc(m[b]);          // warp count
     ccells = __reduce_add_sync(0xFFFFFFFFu, ccells);
     if (lane == 0) { S.pred[par][0][wid] = cin; S.pred[par][1][wid] = ccells; }
-    __syncthreads();
+    __syncthreads();                                    // every entry of src is in registers; counts and cell table published
+    int pos = 0;
     cin = 0; ccells = 0;
 #pragma unroll
-    for (int q = 0; q < kWarps; ++q) { cin += S.pred[par][0][q]; ccells += S.pred[par][1][q]; }
+    for (int q = 0; q < kWarps; ++q) { if (q < wid) pos += S.pred[par][0][q]; cin += S.pred[par][0][q]; ccells += S.pred[par][1][q]; }
+    {
+        // the row's IN list (the later sweeps of the reverse delete read it instead of the whole CSR segment)
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int b = 0; b < EPT; ++b) {
+            if ((m[b] >> lane) & 1u) dst[pos + __popc(m[b] & lt)] = X.e[b];
+            pos += __popc(m[b]);
+        }
+    }
     if (accumulate && cin > 0) {
         const bool critr = cin <= need;
 #pragma unroll
@@ -1119,17 +1133,18 @@ __device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, i
 }
 
 __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int R, int n, int off, int par, bool accumulate,
-                            unsigned* tab, BlockScratch& S) {
-    const uint32_t* src = P.ent + off;
+                            bool from_in, unsigned* tab, BlockScratch& S) {
+    const uint32_t* src = (from_in ? P.live : P.ent) + off;
+    uint32_t* dst = P.live + off;
     const uint8_t* st_w = P.st + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int cin = 0, ccells = 0, z = 0;
-    if (n > 0 && n <= kThreads) row_d1_regs<1>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
-    else if (n > 0 && n <= 2 * kThreads) row_d1_regs<2>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
-    else if (n > 0 && n <= 4 * kThreads) row_d1_regs<4>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
-    else if (n > 0 && n <= kRegRow) row_d1_regs<8>(P, D, n, src, need, par, accumulate, tab, S, cin, ccells);
+    if (n > 0 && n <= kThreads) row_d1_regs<1>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 2 * kThreads) row_d1_regs<2>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 4 * kThreads) row_d1_regs<4>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= kRegRow) row_d1_regs<8>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0) {
         zero_tab(tab);
         __syncthreads();
@@ -1153,6 +1168,18 @@ __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int
                 if (add) atomicAdd(&acc_w[e >> kCellBits], add);
             }
         }
+        // IN list of a long row (chunk by chunk; the barriers of the scan order the reads of a chunk before its writes)
+        int out_base = 0;
+        for (int base = 0; base < n; base += kThreads) {
+            const int i = base + (int)threadIdx.x;
+            uint32_t e = kEntInvalid;
+            bool in = false;
+            if (i < n) { e = src[i]; in = st_w[e >> kCellBits] == ST_IN; }
+            int total;
+            const int p = block_excl_scan(S, in ? 1 : 0, total);
+            if (in) dst[out_base + p] = e;
+            out_base += total;
+        }
     }
     if (threadIdx.x == 0) {
         const int slack = max(0, need - cin);
@@ -1161,23 +1188,27 @@ __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int
         uint32_t* slot = P.out + D.out_off + kHdrWords + words;
         slot[local] = (uint32_t)cin;
         slot[D.K + D.H + local] = (uint32_t)slack;
+        P.live_n[R] = cin;
         const int unc = P.row_ncell[R] - ccells;
         if (unc) atomicAdd(&rc.uncovered, (unsigned)unc);
         if (slack) atomicAdd(&rc.slack, (unsigned)slack);
     }
 }
 
-// D2: budgets of the reverse delete (per cell: keep at least one IN point; per row: at most cov - need removals)
+// D2: budgets of the reverse delete (per cell: keep at least one IN point; per row: at most cov - need removals).
+// Reads the row's IN list written by the D1 sweep just before (every entry is IN or CAND now).
 __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
-    const int n = P.ent_n[R];
+    const int n = P.live_n[R];
     if (n == 0) return;
-    const uint32_t* src = P.ent + P.row_off[R];
+    const uint32_t* src = P.live + P.row_off[R];
     const uint8_t* st_w = P.st + D.var_base;
     const float* gain_w = P.gain + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
-    zero_tab(tab);
-    for (int c = threadIdx.x; c < kCells; c += kThreads) keytab[c] = 0ull;
+    for (int i = threadIdx.x; i < n; i += kThreads) {           // lazy zeroing: only the cells this list touches
+        const unsigned cell = src[i] & kCellCov;
+        if (cell != kCellCov) { tab[cell] = 0u; keytab[cell] = 0ull; }
+    }
     __syncthreads();
     int cov = 0, ncand = 0, z = 0;
     for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -1600,7 +1631,8 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
             ++rounds;
             const unsigned changed = (unsigned)S.tcnt[0], nfree = (unsigned)S.tcnt[1];
             __syncthreads();                         // everyone has read the counters before they are zeroed again
-            if (changed > 0 && rounds < P.max_rounds) mode = MODE_PROP;
+            if (changed > 0 && rounds < P.max_rounds)
+                mode = (P.stall_den > 0 && rounds >= 2 && (unsigned long long)changed * (unsigned)P.stall_den < nfree) ? MODE_GREEDY : MODE_PROP;
             else if (nfree == 0) mode = drop_mode;
             else if (rounds >= P.max_rounds) { status = -5; mode = MODE_FORCE; }
             else mode = MODE_GREEDY;
@@ -1638,11 +1670,11 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
 // 256; long lists are processed by the whole CTA one after the other (the next row's entries are prefetched into L1 while
 // the current one is processed), short PROP / GREEDY lists by one warp each.
 __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc, const GroupCtx& G, int mode, bool from_csr,
-                                unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
+                                bool from_in, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
     const int rows = D.K + D.H;
     const int mine = (rows - G.cta + G.ncta - 1) / G.ncta;          // rows G.cta, G.cta + ncta, ...
-    const bool sweep = mode == MODE_D1 || mode == MODE_EVAL;        // whole CSR rows, every row (also empty ones) reports
-    const bool csr = from_csr || sweep;
+    const bool sweep = mode == MODE_D1 || mode == MODE_EVAL;        // every row (also empty ones) reports; the first sweep reads
+    const bool csr = from_csr || (sweep && !from_in);               // the CSR and leaves IN lists, later sweeps read those
     const int* listn = csr ? P.ent_n : P.live_n;
     const uint32_t* lists = csr ? P.ent : P.live;
     const int wid = threadIdx.x >> 5;
@@ -1676,7 +1708,7 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
                 if ((int)threadIdx.x * 32 < S.rown[ns]) prefetch_l1(lists + S.rowoff[ns] + threadIdx.x * 32);
             }
             if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], S.rowoff[slot], q & 1, from_csr, tab, S);
-            else if (sweep) { row_d1_eval(P, D, rc, R, S.rown[slot], S.rowoff[slot], q & 1, mode == MODE_D1, tab, S); __syncthreads(); }
+            else if (sweep) { row_d1_eval(P, D, rc, R, S.rown[slot], S.rowoff[slot], q & 1, mode == MODE_D1, from_in, tab, S); __syncthreads(); }
             else { row_greedy(P, D, R, S.rown[slot], keytab, S); __syncthreads(); }
         }
         for (int q = wid; q < nshort; q += kWarps) {
@@ -1765,11 +1797,19 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     int rounds = 1, greedy_steps = 0, drop_rounds = 0, status = 0;
     int seq = 0, mode;
     bool from_csr = true;
+    bool in_lists = false;          // the rows' IN lists exist (written by the first sweep of the reverse delete / read-out)
     int vbuf = 0, vcnt = (int)ws.rc[0].nfree;           // FREE list written by the last PROP phase
     unsigned prev_sumdeg = ws.rc[0].sumdeg;             // its total number of row entries
     unsigned unc_final = 0, slack_final = 0;
     auto after_prop = [&](unsigned changed, unsigned nfree) {
-        if (changed > 0 && rounds < P.max_rounds) return (int)MODE_PROP;
+        if (changed > 0 && rounds < P.max_rounds) {
+            // stall: propagation still moves, but slowly (deficient rows with many candidates creep through the window
+            // keyframe by keyframe) -> greedy step now.  Its row phase reads the live lists of the PROP row phase just done:
+            // cell flags and row coverage are one variable phase behind, state and gain are current (oracle/emulate.py
+            // restates exactly that); any selection is feasible, DROP removes what turns out redundant.
+            if (P.stall_den > 0 && rounds >= 2 && (unsigned long long)changed * (unsigned)P.stall_den < nfree) return (int)MODE_GREEDY;
+            return (int)MODE_PROP;
+        }
         if (nfree == 0) return drop_mode;
         if (rounds >= P.max_rounds) { status = -5; return (int)MODE_FORCE; }
         return (int)MODE_GREEDY;
@@ -1783,13 +1823,14 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
             reinterpret_cast<uint32_t*>(&ws.rc[(seq + 1) % 3])[threadIdx.x] = 0u;     // used by phase seq + 1
         // row phase
         if (mode == MODE_PROP || mode == MODE_GREEDY || mode == MODE_D1 || mode == MODE_EVAL) {
-            row_phase_lists(P, D, rc, G, mode, from_csr, tab, keytab, S);
+            row_phase_lists(P, D, rc, G, mode, from_csr, in_lists, tab, keytab, S);
             if (!group_sync(P, G)) return false;
+            if (mode == MODE_D1 || mode == MODE_EVAL) in_lists = true;
         } else if (mode == MODE_D2) {
             unsigned long long wsum = 0;
             for (int r = G.cta; r < rows; r += G.ncta) {
                 const int R = D.row_base + r;
-                wsum += (unsigned long long)P.ent_n[R];
+                wsum += (unsigned long long)P.live_n[R];
                 row_d2(P, D, R, tab, keytab, S);
                 __syncthreads();
             }

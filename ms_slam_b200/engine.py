@@ -30,7 +30,7 @@ class MssError(RuntimeError):
 class mss_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("min_points", C.c_int32), ("lambda_", C.c_float), ("grid_lambda", C.c_float),
                 ("max_rounds", C.c_int32), ("all_rule_steps", C.c_int32), ("max_drop_rounds", C.c_int32),
-                ("flags", C.c_int32)]
+                ("stall_den", C.c_int32)]
 
 
 class mss_window_view(C.Structure):
@@ -217,10 +217,10 @@ class Engine:
     """One engine handle = one CUDA device + stream (the reference's GRBEnv, MapSparsification.h:59)."""
 
     def __init__(self, N=100, lam=500.0, grid_lam=10.0, device=0, max_rounds=0, all_rule_steps=0,
-                 max_drop_rounds=0):
+                 max_drop_rounds=0, stall_den=0):
         self.lib = load_library()
         self.handle = C.c_void_p()
-        cfg = mss_config(device, N, lam, grid_lam, max_rounds, all_rule_steps, max_drop_rounds, 0)
+        cfg = mss_config(device, N, lam, grid_lam, max_rounds, all_rule_steps, max_drop_rounds, stall_den)
         rc = self.lib.mss_create(C.byref(cfg), C.byref(self.handle))
         if rc != MSS_OK:
             self.handle = None

@@ -72,9 +72,10 @@ def _admit_topk(rows, keys, k_row):
 
 
 class Emulator:
-    def __init__(self, view, N, lam, grid_lam, max_rounds=256, all_rule_steps=64, max_drop_rounds=16):
+    def __init__(self, view, N, lam, grid_lam, max_rounds=256, all_rule_steps=0, max_drop_rounds=16, stall_den=8):
         self.N, self.lam, self.glam = int(N), float(lam), float(grid_lam)
         self.max_rounds, self.all_rule_steps, self.max_drop_rounds = max_rounds, all_rule_steps, max_drop_rounds
+        self.stall_den = stall_den
         K, H, M = view.K, view.H, view.M
         self.K, self.H, self.M = K, H, M
         feat_kf = np.repeat(np.arange(K, dtype=np.int64), np.diff(view.feat_ptr))
@@ -115,6 +116,7 @@ class Emulator:
     def _prop_round(self):
         st, M = self.st, self.M
         nin_c, nfree_c, cov, free_r = self._stats()
+        self.row_view = (nin_c, cov)          # what the row phase of this round saw (the device's cell flags / row_cov)
         d = np.maximum(0, self.need - cov)
         fe = st[self.e_var] == FREE
         unc = fe & (nin_c[self.e_cell] == 0)
@@ -143,7 +145,10 @@ class Emulator:
     def _greedy_round(self):
         st, M = self.st, self.M
         any_rule = self.greedy_steps >= self.all_rule_steps
-        nin_c, nfree_c, cov, free_r = self._stats()
+        # GREEDY reads the live lists of the last PROP row phase: cell-covered flags and row coverage are the ones that phase
+        # saw (exact when that round changed nothing; one variable phase behind when GREEDY was triggered by a stall),
+        # state and gain are current
+        nin_c, cov = self.row_view
         d = np.maximum(0, self.need - cov)
         key = make_key(self.gain, np.arange(M))
         flags = np.zeros(M, np.int8)
@@ -202,6 +207,11 @@ class Emulator:
         while True:
             changed, nfree = self._prop_round()
             if changed > 0 and self.rounds < self.max_rounds:
+                # stall: propagation still moves, but slowly (deficient rows with many candidates creep through the window
+                # keyframe by keyframe) -> take a greedy step now instead of waiting for the fixed point
+                if not (self.stall_den > 0 and self.rounds >= 2 and changed * self.stall_den < nfree):
+                    continue
+                self._greedy_round()
                 continue
             if nfree == 0:
                 break

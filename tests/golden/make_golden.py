@@ -77,7 +77,8 @@ def main():
     bounds = json.load(open(bounds_path)) if os.path.exists(bounds_path) else {}
     jobs = [("c1", s, {}, True) for s in range(5)] + [("live", s, {}, True) for s in range(2)] + \
            [("c4", 0, dict(M=3000), True), ("live", 0, dict(M=1500, H=20), True)]
-    jobs += [("c3", 0, {}, False), ("c4", 1000, {}, False), ("c4", 1001, {}, False), ("c2", 0, {}, False)]
+    jobs += [("c3", 0, {}, False), ("c4", 1000, {}, False), ("c4", 1001, {}, False), ("c2", 0, {}, False),
+             ("c2", 7, {}, False), ("c2", 14, {}, False), ("c2", 176, {}, False)]
     if slow:
         jobs += [("c3", 0, {}, True), ("c5", 0, {}, False)]
     for name, seed, over, do_ilp in jobs:
@@ -100,8 +101,14 @@ def main():
 
     # ---- emulation checksums ------------------------------------------------------------------------------------------
     emu = {}
-    for name, seed, over in [("c1", 0, {}), ("c1", 1, {}), ("live", 0, {}), ("c3", 0, {}), ("c4", 1000, {}),
-                             ("c4", 0, dict(M=3000)), ("c2", 0, {})]:
+    emu_jobs = [("c1", 0, {}), ("c1", 1, {}), ("live", 0, {}), ("c3", 0, {}), ("c4", 1000, {}), ("c4", 0, dict(M=3000)),
+                ("c2", 0, {}), ("c2", 7, {}), ("c2", 14, {}), ("c2", 176, {})]      # c2:176 = nMax outlier, stall-triggered greedy
+    if slow:
+        emu_jobs += [("c5", 0, {})]
+    else:
+        old = json.load(open(os.path.join(HERE, "emulation.json"))) if os.path.exists(os.path.join(HERE, "emulation.json")) else {}
+        emu = {k: v for k, v in old.items() if k.startswith("c5:")}            # kept from the last --slow run
+    for name, seed, over in emu_jobs:
         view, N = msgen.make_config(name, seed, **over)
         r = em.solve(view, N, LAM, GLAM)
         bits = em.pack_bits(r["keep"])
