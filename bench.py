@@ -116,8 +116,9 @@ def kernel_alg_bytes(views, results, row_entries, var_visits):
        not counted: 64-bit reductions of the PROP / GREEDY / D1 row phases, live-list and FREE-list writes."""
     total = 0
     for v, r in zip(views, results):
-        obs_elt = 2 if hasattr(v, "mp_obs_kf16") else 4
-        total += view_floor_bytes(v) + obs_elt * v.O + 4 * (v.M + 1) + 39 * v.M + 12 * int(r.nnz)
+        # observations are streamed a second time by the fill pass (SoA: their pointers too)
+        again = 4 * v.O if hasattr(v, "obs_pairs") else 4 * v.O + 4 * (v.M + 1)
+        total += view_floor_bytes(v) + again + 39 * v.M + 12 * int(r.nnz)
     return total + 5 * int(row_entries) + 17 * int(var_visits)
 
 
@@ -315,7 +316,7 @@ def main():
             v = views[w]
             if args.layout == "packed":
                 hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
-                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.mp_obs_ptr, v.mp_obs_kf16, v.okf_total]))
+                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]))
             else:
                 hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
                                           *pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr, v.mp_obs_kf, v.okf_total]))

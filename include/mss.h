@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MSS_VERSION 110            /* 0.1.1: packed transport layout */
+#define MSS_VERSION 120            /* 0.1.2: packed transport layout (slots + pair list) */
 
 #define MSS_GRID_COLS 64           /* FRAME_GRID_COLS, /root/reference/include/Frame.h:45 */
 #define MSS_GRID_ROWS 48           /* FRAME_GRID_ROWS, /root/reference/include/Frame.h:44 */
@@ -51,7 +51,7 @@ typedef enum mss_memory {
  * PCIe every call (about 0.6x the bytes): FlattenWindow can emit either at the same host cost. */
 typedef enum mss_layout {
     MSS_LAYOUT_SOA = 0,      /* feat_mp i32 + feat_cell u16, mp_nobs i32, mp_obs_kf i32 */
-    MSS_LAYOUT_PACKED = 1    /* slots u32 = (map point << 12) | cell, mp_nobs16 u16, mp_obs_kf16 u16 */
+    MSS_LAYOUT_PACKED = 1    /* slots u32 = (map point << 12) | cell, mp_nobs16 u16, obs_pairs u32 = (map point << 12) | outside kf */
 } mss_layout;
 #define MSS_SLOT_CELL_NONE 0xFFFu      /* packed slot: keypoint outside the grid (MSS_CELL_NONE of the SOA form) */
 #define MSS_SLOT_EMPTY 0xFFFFFFFFu     /* packed slot: empty slot / bad map point (feat_mp == -1 of the SOA form) */
@@ -93,15 +93,15 @@ typedef struct mss_window_view {
                                         (window keyframes) are ignored and may be left out, as may the lists of map points
                                         that are not variables */
     const int32_t*  okf_total; /* [H]   GetNumberMPs() of each outside keyframe */
-    /* ---- MSS_LAYOUT_PACKED replaces feat_mp / feat_cell / mp_nobs / mp_obs_kf (those four may then be NULL); feat_ptr,
-     *      mp_obs_ptr and okf_total are used as above.  Requires M <= 2^20, Observations() <= 65535, K + H <= 65535
-     *      (the engine's own per-window limits). ---- */
+    /* ---- MSS_LAYOUT_PACKED replaces feat_mp / feat_cell / mp_nobs / mp_obs_ptr / mp_obs_kf (those five may then be NULL);
+     *      feat_ptr and okf_total are used as above.  Requires M <= 2^20, Observations() <= 65535, H <= 4095. ---- */
     int32_t layout;            /* mss_layout; 0 (SOA) for zero-initialised views */
     int32_t reserved;          /* 0 */
     const uint32_t* slots;     /* [F]   (map-point table index << 12) | (col*48+row), low 12 bits MSS_SLOT_CELL_NONE = not in mGrid;
                                         MSS_SLOT_EMPTY = empty slot */
     const uint16_t* mp_nobs16; /* [M]   MapPoint::Observations() */
-    const uint16_t* mp_obs_kf16; /* [O] KF-table index of each observation (as mp_obs_kf) */
+    const uint32_t* obs_pairs; /* [O]   observations of the window's map points by OUTSIDE keyframes only, in any order:
+                                        (map-point table index << 12) | j, j = 0..H-1 the outside keyframe (KF-table index K + j) */
 } mss_window_view;
 
 /* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view) or NULL. */

@@ -183,14 +183,16 @@ int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
     if (v.F < 0 || v.O < 0) { h->err = "view: negative F/O"; return MSS_E_BADARG; }
     if (v.memory != MSS_MEM_HOST && v.memory != MSS_MEM_DEVICE) { h->err = "view: bad memory kind"; return MSS_E_BADARG; }
     if (v.layout != MSS_LAYOUT_SOA && v.layout != MSS_LAYOUT_PACKED) { h->err = "view: bad layout"; return MSS_E_BADARG; }
-    if (!v.feat_ptr || !v.mp_obs_ptr) { h->err = "view: feat_ptr / mp_obs_ptr is NULL"; return MSS_E_BADARG; }
-    const bool null_arr = v.layout == MSS_LAYOUT_PACKED
-        ? ((v.F > 0 && !v.slots) || (v.M > 0 && !v.mp_nobs16) || (v.O > 0 && !v.mp_obs_kf16))
+    const bool pkv = v.layout == MSS_LAYOUT_PACKED;
+    if (!v.feat_ptr || (!pkv && !v.mp_obs_ptr)) { h->err = "view: feat_ptr / mp_obs_ptr is NULL"; return MSS_E_BADARG; }
+    if (pkv && v.H > 4095) { h->err = "view: more than 4095 outside keyframes in the packed layout (use MSS_LAYOUT_SOA)"; return MSS_E_BADARG; }
+    const bool null_arr = pkv
+        ? ((v.F > 0 && !v.slots) || (v.M > 0 && !v.mp_nobs16) || (v.O > 0 && !v.obs_pairs))
         : ((v.F > 0 && (!v.feat_mp || !v.feat_cell)) || (v.M > 0 && !v.mp_nobs) || (v.O > 0 && !v.mp_obs_kf));
     if (null_arr || (v.H > 0 && !v.okf_total)) { h->err = "view: NULL array with non-zero size"; return MSS_E_BADARG; }
     if (v.memory == MSS_MEM_HOST) {
         if (v.feat_ptr[0] != 0 || v.feat_ptr[v.K] != v.F) { h->err = "view: feat_ptr must start at 0 and end at F"; return MSS_E_BADARG; }
-        if (v.mp_obs_ptr[0] != 0 || v.mp_obs_ptr[v.M] != v.O) { h->err = "view: mp_obs_ptr must start at 0 and end at O"; return MSS_E_BADARG; }
+        if (!pkv && (v.mp_obs_ptr[0] != 0 || v.mp_obs_ptr[v.M] != v.O)) { h->err = "view: mp_obs_ptr must start at 0 and end at O"; return MSS_E_BADARG; }
     }
     return MSS_OK;
 }
@@ -234,8 +236,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         if (v.memory == MSS_MEM_HOST) {
             const bool pk = v.layout == MSS_LAYOUT_PACKED;
             stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
-                           align_up((size_t)v.M * (pk ? 2 : 4), 16) + align_up((size_t)(v.M + 1) * 4, 16) +
-                           align_up((size_t)v.O * (pk ? 2 : 4), 16) + align_up((size_t)v.H * 4, 16);
+                           align_up((size_t)v.M * (pk ? 2 : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
+                           align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16);
         }
     }
     if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
@@ -332,12 +334,12 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
             d.feat_mp = (const int*)stage(pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
             d.feat_cell = pk ? nullptr : (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
             d.mp_nobs = (const int*)stage(pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
-            d.mp_obs_ptr = (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
-            d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, (size_t)v.O * (pk ? 2 : 4));
+            d.mp_obs_ptr = pk ? nullptr : (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
+            d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
             d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
         } else if (pk) {
             d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)v.slots; d.feat_cell = nullptr; d.mp_nobs = (const int*)v.mp_nobs16;
-            d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = (const int*)v.mp_obs_kf16; d.okf_total = v.okf_total;
+            d.mp_obs_ptr = nullptr; d.mp_obs_kf = (const int*)v.obs_pairs; d.okf_total = v.okf_total;
         } else {
             d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
             d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
@@ -379,15 +381,15 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         // pinned blob per window, as FlattenWindow lays them out), travels with ONE copy
         {
             const void* src[7] = {v.feat_ptr, pk ? (const void*)v.slots : (const void*)v.feat_mp, pk ? nullptr : (const void*)v.feat_cell,
-                                  pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, v.mp_obs_ptr,
-                                  pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, v.okf_total};
+                                  pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
+                                  pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
             const size_t len[7] = {(size_t)(v.K + 1) * 4, (size_t)v.F * 4, pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
-                                   (size_t)(v.M + 1) * 4, (size_t)v.O * (pk ? 2 : 4), (size_t)v.H * 4};
+                                   pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
             const uint8_t* base = static_cast<const uint8_t*>(src[0]);
             size_t off = 0, end = 0;
             bool blob = (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
             for (int a = 0; a < 7 && blob; ++a) {
-                if (pk && a == 2) continue;
+                if (pk && (a == 2 || a == 4)) continue;
                 if (len[a]) { if (static_cast<const uint8_t*>(src[a]) != base + off) blob = false; end = off + len[a]; }
                 off += align_up(len[a], 16);
             }
@@ -397,8 +399,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         put(d.feat_mp, pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
         if (!pk) put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
         put(d.mp_nobs, pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
-        put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
-        put(d.mp_obs_kf, pk ? (const void*)v.mp_obs_kf16 : (const void*)v.mp_obs_kf, (size_t)v.O * (pk ? 2 : 4));
+        if (!pk) put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
+        put(d.mp_obs_kf, pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
         put(d.okf_total, v.okf_total, (size_t)v.H * 4);
     };
     const Chunk& ch0 = chunks[0];

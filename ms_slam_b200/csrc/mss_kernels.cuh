@@ -74,7 +74,8 @@ struct WinDesc {
     int obs_base;    // first entry of this window's outside rows in ent[] / live[] (after all keyframe segments)
     int var_base;    // global variable index of map point 0 (multiple of kVarTile)
     int out_off;     // u32 word offset of this window's result slot
-    int packed;      // MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs / mp_obs_kf are u16 arrays
+    int packed;      // MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs is a u16 array, mp_obs_kf holds
+                     // the outside observations as u32 pairs (map point << 12 | outside keyframe), mp_obs_ptr is unused
     int pad_[2];
 };
 
@@ -349,9 +350,7 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
 __device__ __forceinline__ int ld_nobs(const WinDesc& D, int mp) {
     return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : __ldg(D.mp_nobs + mp);
 }
-__device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) {
-    return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_obs_kf) + o) : __ldg(D.mp_obs_kf + o);
-}
+__device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) { return __ldg(D.mp_obs_kf + o); }      // SoA layout only
 // slot i of the view -> (map point or -1, cell or kCellNone)
 __device__ __forceinline__ void ld_slot(const WinDesc& D, int i, int& mp, unsigned& c) {
     if (D.packed) {
@@ -593,7 +592,7 @@ __device__ void w2_vars_and_outside_counts(const Params& P, const WinDesc& D, Wi
         if (nmax > 0) atomicMax(&ws.n_max, nmax);
         if (nv) atomicAdd(&ws.n_vars, nv);
     }
-    if (D.H == 0 || nv == 0) return;
+    if (D.H == 0 || nv == 0 || D.packed) return;           // packed layout: the pair list is walked by w2_pairs
 #pragma unroll
     for (int j = 0; j < kVpt; ++j) O.isvar[j * kVarTile + threadIdx.x] = isvar[j] ? 1 : 0;
     if (!obs_tile_load(D, ws, base, O)) return;
@@ -616,6 +615,39 @@ __device__ void w2_vars_and_outside_counts(const Params& P, const WinDesc& D, Wi
     }
     if (err) atomicOr(&ws.error, err);
     __syncthreads();
+}
+
+// Packed layout: the outside observations come as one flat list of (map point, outside keyframe) pairs, so no owner
+// search is needed.  W2 part: how many variables every outside keyframe observes (MapSparsification.cc:127-142).  A map
+// point is a variable exactly when its W1 counters are non-zero.
+__device__ void w2_pairs(const Params& P, const WinDesc& D, WinState& ws, int gt, int gsz) {
+    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
+    unsigned err = 0;
+    for (int o = gt; o < D.O; o += gsz) {
+        const uint32_t pr = __ldg(pairs + o);
+        const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
+        if (mp >= D.M || j >= D.H) { err |= ERR_INDEX; continue; }
+        if (P.acc[D.var_base + mp] != 0ull) atomicAdd(&P.ent_n[D.row_base + D.K + j], 1);
+    }
+    if (err) atomicOr(&ws.error, err);
+}
+
+// W4 part: fill the outside rows and add their round-1 contributions straight to the map points' counters; deg[] (zeroed
+// in W0) collects the number of outside rows of every variable
+__device__ void w4_pairs(const Params& P, const WinDesc& D, int gt, int gsz) {
+    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
+    for (int o = gt; o < D.O; o += gsz) {
+        const uint32_t pr = __ldg(pairs + o);
+        const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
+        const int g = D.var_base + mp;
+        if (P.st[g] != ST_FREE) continue;                   // (indices were validated by w2_pairs)
+        const int R = D.row_base + D.K + j;
+        const int pos = atomicAdd(&P.ocursor[R], 1);
+        P.ent[pos] = ((uint32_t)mp << kCellBits) | kCellCov;
+        const int need = P.row_need[R];
+        if (need > 0) atomicAdd(&P.acc[g], (1ull << 32) | (need >= P.ent_n[R] ? (1ull << 48) : 0ull));
+        atomicAdd(&P.deg[g], 1u);
+    }
 }
 
 // W3 (one CTA per window): exclusive scan of the outside-row counts -> segments, rhs of the outside rows
@@ -691,7 +723,13 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
         if (isvar[j]) { a[j] = P.acc[D.var_base + mp]; nobs[j] = ld_nobs(D, mp); any = true; }
     }
     unsigned nout[kVpt] = {0u, 0u, 0u, 0u};
-    if (D.H > 0 && __syncthreads_or(any)) {
+    if (D.packed) {
+        if (D.H > 0) {
+#pragma unroll
+            for (int j = 0; j < kVpt; ++j)
+                if (isvar[j]) nout[j] = P.deg[D.var_base + base + j * kVarTile + (int)threadIdx.x];     // written by w4_pairs
+        }
+    } else if (D.H > 0 && __syncthreads_or(any)) {
 #pragma unroll
         for (int j = 0; j < kVpt; ++j) {
             O.isvar[j * kVarTile + threadIdx.x] = isvar[j] ? 1 : 0;
@@ -1756,6 +1794,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         uint32_t* seen32 = reinterpret_cast<uint32_t*>(P.seen + D.var_base);
         for (int i = gt; i < mpad / 4; i += gsz) seen32[i] = 0u;
         for (int i = gt; i < mpad; i += gsz) P.acc[D.var_base + i] = 0ull;
+        if (D.packed && D.H > 0) for (int i = gt; i < mpad; i += gsz) P.deg[D.var_base + i] = 0u;
         for (int j = gt; j < D.H; j += gsz) P.ent_n[D.row_base + D.K + j] = 0;
         if (G.cta == 0) {
             uint32_t* z = reinterpret_cast<uint32_t*>(&ws);
@@ -1783,11 +1822,16 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     ObsTile& OT = *reinterpret_cast<ObsTile*>(keytab);             // shared scratch of the variable passes
     const int stiles = (D.M + kSuper - 1) / kSuper;
     for (int t = G.cta; t < stiles; t += G.ncta) w2_vars_and_outside_counts(P, D, ws, t, OT, S);
+    if (D.packed && D.H > 0) w2_pairs(P, D, ws, gt, gsz);
     if (!group_sync(P, G)) return false;
     if (G.cta == 0) w3_scan_outside(P, D, S);
     if (!group_sync(P, G)) return false;
     trace_mark(P, G, w, tn, 13, 0, t_win);
     if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
+    if (D.packed && D.H > 0) {
+        w4_pairs(P, D, gt, gsz);
+        if (!group_sync(P, G)) return false;
+    }
     for (int t = G.cta; t < stiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, OT);
     if (!group_sync(P, G)) return false;
     if (w == P.gwin[0] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();

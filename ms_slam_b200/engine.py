@@ -39,13 +39,13 @@ class mss_window_view(C.Structure):
                 ("feat_ptr", C.c_void_p), ("feat_mp", C.c_void_p), ("feat_cell", C.c_void_p), ("mp_nobs", C.c_void_p),
                 ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
                 ("layout", C.c_int32), ("reserved", C.c_int32),
-                ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("mp_obs_kf16", C.c_void_p)]
+                ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("obs_pairs", C.c_void_p)]
 
 
-def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, mp_obs_ptr, mp_obs_kf16, okf_total) -> "mss_window_view":
+def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total) -> "mss_window_view":
     """MSS_LAYOUT_PACKED view from raw addresses"""
-    return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, mp_obs_ptr, None, okf_total,
-                           LAYOUT_PACKED, 0, slots, mp_nobs16, mp_obs_kf16)
+    return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, None, None, okf_total,
+                           LAYOUT_PACKED, 0, slots, mp_nobs16, obs_pairs)
 
 
 class mss_result(C.Structure):
@@ -164,7 +164,7 @@ class DeviceView:
     """A window view resident in device memory (inputs already in HBM: bench `value`, MSS_MEM_DEVICE)."""
 
     _ARR = ("feat_ptr", "feat_mp", "feat_cell", "mp_nobs", "mp_obs_ptr", "mp_obs_kf", "okf_total")
-    _ARR_PACKED = ("feat_ptr", "slots", "mp_nobs16", "mp_obs_ptr", "mp_obs_kf16", "okf_total")
+    _ARR_PACKED = ("feat_ptr", "slots", "mp_nobs16", "obs_pairs", "okf_total")
 
     def __init__(self, engine: "Engine", view):
         self.engine = engine
@@ -285,8 +285,7 @@ class Engine:
     def _host_view(v) -> mss_window_view:
         if isinstance(v, PackedView):
             return packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
-                                 v.mp_nobs16.ctypes.data, v.mp_obs_ptr.ctypes.data, v.mp_obs_kf16.ctypes.data,
-                                 v.okf_total.ctypes.data)
+                                 v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data)
         return mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
                                v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
                                v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data)

@@ -80,14 +80,15 @@ void WindowSnapshot::Blob::Reserve(size_t bytes) {
 void WindowSnapshot::Pack() {
     packed = false;
     const size_t M = mp_nobs.size(), F = feat_mp.size(), O = mp_obs_kf.size();
-    if (M > (1u << 20) || K + H > 65535) return;
+    if (M > (1u << 20) || H > 4095) return;
     for (int32_t n : mp_nobs) if (n < 0 || n > 65535) return;
     auto up = [](size_t x) { return (x + 15) / 16 * 16; };
     off_slots = up((size_t)(K + 1) * 4);
     off_nobs = off_slots + up(F * 4);
-    off_obs_ptr = off_nobs + up(M * 2);
-    off_obs_kf = off_obs_ptr + up((M + 1) * 4);
-    off_okf = off_obs_kf + up(O * 2);
+    n_pairs = 0;
+    for (size_t o = 0; o < O; ++o) n_pairs += mp_obs_kf[o] >= K ? 1 : 0;       // FlattenWindow emits outside observations only
+    off_pairs = off_nobs + up(M * 2);
+    off_okf = off_pairs + up(n_pairs * 4);
     const size_t total = off_okf + up((size_t)H * 4);
     if (!blob) blob = std::make_shared<Blob>();
     blob->Reserve(total);
@@ -100,9 +101,11 @@ void WindowSnapshot::Pack() {
     }
     uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
     for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
-    memcpy(blob->p + off_obs_ptr, mp_obs_ptr.data(), (M + 1) * 4);
-    uint16_t* okf = reinterpret_cast<uint16_t*>(blob->p + off_obs_kf);
-    for (size_t o = 0; o < O; ++o) okf[o] = (uint16_t)mp_obs_kf[o];
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(blob->p + off_pairs);
+    size_t np = 0;
+    for (size_t p = 0; p < M; ++p)
+        for (int32_t o = mp_obs_ptr[p]; o < mp_obs_ptr[p + 1]; ++o)
+            if (mp_obs_kf[o] >= K) pairs[np++] = ((uint32_t)p << 12) | (uint32_t)(mp_obs_kf[o] - K);
     if (H) memcpy(blob->p + off_okf, okf_total.data(), (size_t)H * 4);
     packed = true;
 }
@@ -110,14 +113,13 @@ void WindowSnapshot::Pack() {
 mss_window_view WindowSnapshot::View() const {
     mss_window_view v{};
     if (packed && blob && blob->p) {
-        v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)mp_obs_kf.size();
+        v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)n_pairs;
         v.memory = MSS_MEM_HOST;
         v.layout = MSS_LAYOUT_PACKED;
         v.feat_ptr = reinterpret_cast<const int32_t*>(blob->p);
         v.slots = reinterpret_cast<const uint32_t*>(blob->p + off_slots);
         v.mp_nobs16 = reinterpret_cast<const uint16_t*>(blob->p + off_nobs);
-        v.mp_obs_ptr = reinterpret_cast<const int32_t*>(blob->p + off_obs_ptr);
-        v.mp_obs_kf16 = reinterpret_cast<const uint16_t*>(blob->p + off_obs_kf);
+        v.obs_pairs = reinterpret_cast<const uint32_t*>(blob->p + off_pairs);
         v.okf_total = reinterpret_cast<const int32_t*>(blob->p + off_okf);
         return v;
     }

@@ -35,7 +35,7 @@ struct WindowSnapshot {
     double flatten_ms = 0.0;
     // MSS_LAYOUT_PACKED transport form of the same arrays in ONE host blob (pinned when a CUDA device is present), laid
     // out back to back at 16-byte boundaries so the engine moves the window with a single copy.  Built by FlattenWindow
-    // whenever the window fits the packed ranges (M <= 2^20, nObs <= 65535, K + H <= 65535); View() then returns it.
+    // whenever the window fits the packed ranges (M <= 2^20, nObs <= 65535, H <= 4095); View() then returns it.
     struct Blob {
         uint8_t* p = nullptr;
         size_t cap = 0;
@@ -44,7 +44,7 @@ struct WindowSnapshot {
         void Reserve(size_t bytes);
     };
     std::shared_ptr<Blob> blob;
-    size_t off_slots = 0, off_nobs = 0, off_obs_ptr = 0, off_obs_kf = 0, off_okf = 0;
+    size_t off_slots = 0, off_nobs = 0, off_pairs = 0, off_okf = 0, n_pairs = 0;
     bool packed = false;
     void Pack();
     mss_window_view View() const;

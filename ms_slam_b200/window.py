@@ -169,8 +169,7 @@ class PackedView:
     feat_ptr: np.ndarray      # int32 [K+1]
     slots: np.ndarray         # uint32 [F]
     mp_nobs16: np.ndarray     # uint16 [M]
-    mp_obs_ptr: np.ndarray    # int32 [M+1]
-    mp_obs_kf16: np.ndarray   # uint16 [O]
+    obs_pairs: np.ndarray     # uint32 [O] (map point << 12) | outside keyframe j (KF-table index K + j)
     okf_total: np.ndarray     # int32 [H]
     meta: dict = field(default_factory=dict)
 
@@ -180,26 +179,27 @@ class PackedView:
 
     @property
     def O(self) -> int:
-        return int(self.mp_obs_kf16.shape[0])
+        return int(self.obs_pairs.shape[0])
 
     def input_bytes(self) -> int:
-        return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.mp_obs_ptr.nbytes +
-                   self.mp_obs_kf16.nbytes + self.okf_total.nbytes)
+        return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.obs_pairs.nbytes + self.okf_total.nbytes)
 
 
 def pack_view(v: WindowView) -> PackedView:
     """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges."""
-    if v.M > (1 << 20) or v.K + v.H > 65535:
+    if v.M > (1 << 20) or v.H > 4095:
         raise ValueError("window too large for the packed layout")
     if v.M and int(v.mp_nobs.max()) > 65535:
         raise ValueError("Observations() above 65535")
     mp = v.feat_mp.astype(np.int64)
     cell = np.where(v.feat_cell == CELL_NONE, SLOT_CELL_NONE, v.feat_cell).astype(np.int64)
     slots = np.where(mp >= 0, (mp << 12) | cell, SLOT_EMPTY).astype(np.uint32)
+    owner = np.repeat(np.arange(v.M, dtype=np.int64), np.diff(v.mp_obs_ptr))
+    outside = v.mp_obs_kf >= v.K                     # observations by window keyframes are not part of the pair list
+    pairs = ((owner[outside] << 12) | (v.mp_obs_kf[outside].astype(np.int64) - v.K)).astype(np.uint32)
     return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
-                      mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), mp_obs_ptr=v.mp_obs_ptr,
-                      mp_obs_kf16=np.ascontiguousarray(v.mp_obs_kf.astype(np.uint16)), okf_total=v.okf_total,
-                      meta=dict(v.meta, packed=True))
+                      mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
+                      okf_total=v.okf_total, meta=dict(v.meta, packed=True))
 
 
 def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:
