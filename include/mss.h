@@ -96,7 +96,9 @@ typedef struct mss_window_view {
     /* ---- MSS_LAYOUT_PACKED replaces feat_mp / feat_cell / mp_nobs / mp_obs_ptr / mp_obs_kf (those five may then be NULL);
      *      feat_ptr and okf_total are used as above.  Requires M <= 2^20, Observations() <= 65535, H <= 4095. ---- */
     int32_t layout;            /* mss_layout; 0 (SOA) for zero-initialised views */
-    int32_t reserved;          /* 0 */
+    int32_t n_max_floor;       /* nMaxObservation (MapSparsification.cc:66-76) is at least this; 0 for a whole window.  A component
+                                  of a larger window (mss_components) carries the window-wide nMax here, so that its costs are
+                                  the ones the whole-window model would use */
     const uint32_t* slots;     /* [F]   (map-point table index << 12) | (col*48+row), low 12 bits MSS_SLOT_CELL_NONE = not in mGrid;
                                         MSS_SLOT_EMPTY = empty slot */
     const uint16_t* mp_nobs16; /* [M]   MapPoint::Observations() */
@@ -153,6 +155,14 @@ int mss_solve(mss_handle* h, const mss_window_view* view, mss_result* result);
  * rank w % nranks and the results of all windows are all-gathered (keep bits + per-row coverage only), so every rank
  * returns all nwin results; views of windows owned by other ranks need only K, H, M filled in. */
 int mss_solve_batch(mss_handle* h, int32_t nwin, const mss_window_view* views, mss_result* results);
+
+/* Connected components of one window (any layout / memory kind).  The reference's final flush puts every unsparsified
+ * keyframe into ONE model (MapSparsification.cc:38-47); that model decomposes exactly along the components of the graph
+ * {keyframe rows, window + outside} x {variables}, so each component is an independent window (give it the window-wide
+ * nMax through n_max_floor) and a flush can be solved as a batch / sharded over GPUs.  row_label[K+H] and mp_label[M]
+ * (same memory kind as the view) receive dense component ids, numbered in order of the first keyframe row of each
+ * component; mp_label is -1 for map points that are not variables.  n_max receives the window-wide nMaxObservation. */
+int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_label, int32_t* mp_label, int32_t* ncomp, int32_t* n_max);
 
 /* Multi-GPU: one process per GPU.  Rank 0 calls mss_comm_unique_id, ships the 128 bytes to the other ranks by any
  * means (torch.distributed broadcast, MPI, a file), then every rank calls mss_comm_init. */

@@ -51,8 +51,9 @@ __global__ void cc_init_kernel(int* parent, uint8_t* isvar, int R, int M) {
 }
 
 // one CTA per keyframe row (grid-stride): union (k, p) for every valid grid-listed slot; marks the variables
-__global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, unsigned* err) {
+__global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, unsigned* err, int* n_max) {
     const int R = D.K + D.H;
+    int nmax = 0;
     for (int k = blockIdx.x; k < D.K; k += gridDim.x) {
         const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
         if (beg < 0 || end < beg || end > D.F) { if (threadIdx.x == 0) atomicOr(err, ERR_PTR); continue; }
@@ -62,11 +63,26 @@ __global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, un
             ld_slot(D, i, mp, c);
             if (mp < 0) { if (mp < -1) atomicOr(err, ERR_INDEX); continue; }
             if (mp >= D.M) { atomicOr(err, ERR_INDEX); continue; }
+            nmax = max(nmax, ld_nobs(D, mp));                   // every valid slot counts for nMax (:66-76)
             if (c == kCellNone) continue;                       // not in mGrid: no variable through this slot (:84-107)
             if (c >= (unsigned)kCells) { atomicOr(err, ERR_INDEX); continue; }
             isvar[mp] = 1;
             cc_union(parent, k, R + mp);
         }
+    }
+    nmax = __reduce_max_sync(0xFFFFFFFFu, nmax);
+    if ((threadIdx.x & 31) == 0 && nmax > 0) atomicMax(n_max, nmax);
+}
+
+// packed layout: the outside observations are a flat pair list
+__global__ void cc_pairs_kernel(const WinDesc D, int* parent, const uint8_t* isvar, unsigned* err) {
+    const int R = D.K + D.H;
+    const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < D.O; o += gridDim.x * blockDim.x) {
+        const uint32_t pr = __ldg(pairs + o);
+        const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
+        if (mp >= D.M || j >= D.H) { atomicOr(err, ERR_INDEX); continue; }
+        if (isvar[mp]) cc_union(parent, D.K + j, R + mp);
     }
 }
 

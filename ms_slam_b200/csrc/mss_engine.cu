@@ -5,6 +5,7 @@
 // /root/reference/include/MapSparsification.h:59, /root/reference/src/MapSparsification.cc:6,20,61,153-157).
 #include "../../include/mss.h"
 #include "mss_kernels.cuh"
+#include "mss_components.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -96,6 +97,7 @@ struct mss_handle {
     DevBuf<uint8_t> stage;           // host views staged here
     DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart | ready flags
     unsigned* h_one = nullptr;       // pinned constant 1: source of the ready-flag copies
+    DevBuf<int> cc;                  // mss_components: parent[R + M] | row_label[R] | mp_label[M] | ncomp, n_max, err
     Ctrl* ctrl = nullptr;            // = sync.p
     // pinned host mirrors
     uint8_t* h_meta = nullptr; size_t h_meta_cap = 0;
@@ -329,6 +331,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         memset(&d, 0, sizeof(d));
         const bool pk = v.layout == MSS_LAYOUT_PACKED;
         d.packed = pk ? 1 : 0;
+        d.n_max_floor = v.n_max_floor;
         if (v.memory == MSS_MEM_HOST) {
             d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
             d.feat_mp = (const int*)stage(pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
@@ -619,7 +622,7 @@ void mss_destroy(mss_handle* h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->deg);
-    release(h->seen); release(h->vlist); release(h->trace); release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync);
+    release(h->seen); release(h->vlist); release(h->trace); release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync); release(h->cc);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -645,6 +648,77 @@ int mss_solve(mss_handle* h, const mss_window_view* view, mss_result* result) {
     if (!h) return MSS_E_BADARG;
     if (h->nranks > 1) { h->err = "mss_solve on a handle with a communicator: use mss_solve_batch"; return MSS_E_BADARG; }
     return solve_batch_impl(h, 1, view, result);
+}
+
+int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_label, int32_t* mp_label, int32_t* ncomp, int32_t* n_max) {
+    if (!h) return MSS_E_BADARG;
+    h->err.clear();
+    if (!view || !ncomp) { h->err = "NULL view / ncomp"; return MSS_E_BADARG; }
+    const mss_window_view& v = *view;
+    int rc = validate_view(h, v, true);
+    if (rc != MSS_OK) return rc;
+    if (v.M > mss::kMaxWindowMps || v.K + v.H > mss::kMaxWindowRows) { h->err = "view: window too large"; return MSS_E_BADARG; }
+    MSS_CUDA(h, cudaSetDevice(h->device));
+    const bool pk = v.layout == MSS_LAYOUT_PACKED, host = v.memory == MSS_MEM_HOST;
+    const int R = v.K + v.H, M = v.M;
+    if ((rc = ensure(h, h->cc, (size_t)2 * (R + M) + 16))) return rc;
+    if ((rc = ensure(h, h->seen, (size_t)M + 16))) return rc;
+    WinDesc d;
+    memset(&d, 0, sizeof(d));
+    d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O; d.packed = pk ? 1 : 0;
+    if (host) {
+        const void* src[7] = {v.feat_ptr, pk ? (const void*)v.slots : (const void*)v.feat_mp, pk ? nullptr : (const void*)v.feat_cell,
+                              pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
+                              pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
+        const size_t len[7] = {(size_t)(v.K + 1) * 4, (size_t)v.F * 4, pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+                               pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
+        size_t total = 0;
+        for (int a = 0; a < 7; ++a) total += align_up(len[a], 16);
+        if ((rc = ensure(h, h->stage, total + 16))) return rc;
+        const void* dst[7];
+        size_t off = 0;
+        for (int a = 0; a < 7; ++a) {
+            dst[a] = h->stage.p + off;
+            if (len[a]) MSS_CUDA(h, cudaMemcpyAsync(h->stage.p + off, src[a], len[a], cudaMemcpyHostToDevice, h->stream));
+            off += align_up(len[a], 16);
+        }
+        d.feat_ptr = (const int*)dst[0]; d.feat_mp = (const int*)dst[1]; d.feat_cell = pk ? nullptr : (const uint16_t*)dst[2];
+        d.mp_nobs = (const int*)dst[3]; d.mp_obs_ptr = pk ? nullptr : (const int*)dst[4]; d.mp_obs_kf = (const int*)dst[5];
+        d.okf_total = (const int*)dst[6];
+    } else if (pk) {
+        d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)v.slots; d.mp_nobs = (const int*)v.mp_nobs16; d.mp_obs_kf = (const int*)v.obs_pairs;
+        d.okf_total = v.okf_total;
+    } else {
+        d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
+        d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
+    }
+    int* parent = h->cc.p;
+    int* d_row = h->cc.p + (R + M);
+    int* d_mp = d_row + R;
+    int* d_misc = d_mp + M;            // ncomp, n_max, err
+    uint8_t* isvar = h->seen.p;
+    MSS_CUDA(h, cudaMemsetAsync(d_misc, 0, 3 * sizeof(int), h->stream));
+    const int T = 256;
+    if (R + M > 0) mss::cc_init_kernel<<<(R + M + T - 1) / T, T, 0, h->stream>>>(parent, isvar, R, M);
+    if (v.K > 0) mss::cc_slots_kernel<<<std::min(v.K, 4 * h->sm_count), T, 0, h->stream>>>(d, parent, isvar, (unsigned*)(d_misc + 2), d_misc + 1);
+    if (v.O > 0) {
+        if (pk) mss::cc_pairs_kernel<<<std::min((v.O + T - 1) / T, 4 * h->sm_count), T, 0, h->stream>>>(d, parent, isvar, (unsigned*)(d_misc + 2));
+        else mss::cc_outside_kernel<<<(M + T - 1) / T, T, 0, h->stream>>>(d, parent, isvar, (unsigned*)(d_misc + 2));
+    }
+    mss::cc_rows_kernel<<<1, 1024, 0, h->stream>>>(parent, d_row, d_misc, R);
+    if (M > 0) mss::cc_vars_kernel<<<(M + T - 1) / T, T, 0, h->stream>>>(parent, d_row, isvar, d_mp, R, M);
+    MSS_CUDA(h, cudaGetLastError());
+    h->stats.kernel_launches += 3 + (v.K > 0) + (v.O > 0);
+    int misc[3] = {0, 0, 0};
+    MSS_CUDA(h, cudaMemcpyAsync(misc, d_misc, sizeof(misc), cudaMemcpyDeviceToHost, h->stream));
+    const cudaMemcpyKind back = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (row_label && R) MSS_CUDA(h, cudaMemcpyAsync(row_label, d_row, (size_t)R * 4, back, h->stream));
+    if (mp_label && M) MSS_CUDA(h, cudaMemcpyAsync(mp_label, d_mp, (size_t)M * 4, back, h->stream));
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (misc[2]) { h->err = "view failed device-side validation (index out of range or bad pointer table)"; return MSS_E_BADARG; }
+    *ncomp = misc[0];
+    if (n_max) *n_max = misc[1];
+    return MSS_OK;
 }
 
 int mss_solve_batch(mss_handle* h, int32_t nwin, const mss_window_view* views, mss_result* results) {

@@ -76,7 +76,8 @@ struct WinDesc {
     int out_off;     // u32 word offset of this window's result slot
     int packed;      // MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs is a u16 array, mp_obs_kf holds
                      // the outside observations as u32 pairs (map point << 12 | outside keyframe), mp_obs_ptr is unused
-    int pad_[2];
+    int n_max_floor; // nMax is at least this (a component of a larger window keeps the window-wide nMax)
+    int pad_[1];
 };
 
 // per-phase counters; three copies rotate so that a copy is zeroed two phases before it is used again
@@ -1799,6 +1800,8 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         if (G.cta == 0) {
             uint32_t* z = reinterpret_cast<uint32_t*>(&ws);
             for (int i = threadIdx.x; i < (int)(sizeof(WinState) / 4); i += kThreads) z[i] = 0u;
+            __syncthreads();
+            if (threadIdx.x == 0) ws.n_max = max(D.n_max_floor, 0);
             if (threadIdx.x == 0) P.out[D.out_off + 14] = 0u;                          // "slot not written"
         }
     }

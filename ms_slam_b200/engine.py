@@ -38,14 +38,14 @@ class mss_window_view(C.Structure):
                 ("memory", C.c_int32),
                 ("feat_ptr", C.c_void_p), ("feat_mp", C.c_void_p), ("feat_cell", C.c_void_p), ("mp_nobs", C.c_void_p),
                 ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
-                ("layout", C.c_int32), ("reserved", C.c_int32),
+                ("layout", C.c_int32), ("n_max_floor", C.c_int32),
                 ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("obs_pairs", C.c_void_p)]
 
 
-def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total) -> "mss_window_view":
+def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total, n_max_floor=0) -> "mss_window_view":
     """MSS_LAYOUT_PACKED view from raw addresses"""
     return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, None, None, okf_total,
-                           LAYOUT_PACKED, 0, slots, mp_nobs16, obs_pairs)
+                           LAYOUT_PACKED, n_max_floor, slots, mp_nobs16, obs_pairs)
 
 
 class mss_result(C.Structure):
@@ -68,7 +68,7 @@ class mss_stats(C.Structure):
 SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_set_params", "mss_solve",
            "mss_solve_batch", "mss_comm_unique_id", "mss_comm_init", "mss_comm_destroy", "mss_host_alloc",
            "mss_host_free", "mss_device_alloc", "mss_device_free", "mss_memcpy_h2d", "mss_memcpy_d2h",
-           "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace"]
+           "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace", "mss_components"]
 
 _lib = None
 
@@ -92,6 +92,8 @@ def load_library(path: str = LIB_PATH):
     lib.mss_set_params.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float]
     lib.mss_solve.argtypes = [C.c_void_p, C.POINTER(mss_window_view), C.POINTER(mss_result)]
     lib.mss_solve_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(mss_window_view), C.POINTER(mss_result)]
+    lib.mss_components.argtypes = [C.c_void_p, C.POINTER(mss_window_view), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32)]
     lib.mss_comm_unique_id.argtypes = [C.c_void_p]
     lib.mss_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.mss_comm_destroy.argtypes = [C.c_void_p]
@@ -172,6 +174,7 @@ class DeviceView:
         if self.packed:
             self._ARR = self._ARR_PACKED
         self.K, self.H, self.M, self.F, self.O = view.K, view.H, view.M, view.F, view.O
+        self.n_max_floor = int(getattr(view, "n_max_floor", 0))
         self.ptrs = {}
         lib, h = engine.lib, engine.handle
         for name in self._ARR:
@@ -189,8 +192,10 @@ class DeviceView:
 
     def c_view(self) -> mss_window_view:
         if self.packed:
-            return packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR])
-        return mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR])
+            return packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
+                                 n_max_floor=self.n_max_floor)
+        return mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
+                               LAYOUT_SOA, self.n_max_floor)
 
     def fetch(self):
         """copy the device-resident result arrays back to numpy (not part of any timed region)"""
@@ -285,10 +290,20 @@ class Engine:
     def _host_view(v) -> mss_window_view:
         if isinstance(v, PackedView):
             return packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
-                                 v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data)
+                                 v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data,
+                                 n_max_floor=v.n_max_floor)
         return mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
                                v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
-                               v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data)
+                               v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data, LAYOUT_SOA, v.n_max_floor)
+
+    def components(self, view):
+        """Connected components of a host window view (WindowView or PackedView): (row_label[K+H], mp_label[M], ncomp, n_max)"""
+        cv = self._host_view(view)
+        rows = np.zeros(view.K + view.H, np.int32)
+        mps = np.zeros(view.M, np.int32)
+        nc, nm = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.mss_components(self.handle, C.byref(cv), rows.ctypes.data, mps.ctypes.data, C.byref(nc), C.byref(nm)))
+        return rows, mps, int(nc.value), int(nm.value)
 
     def solve_batch(self, views, raise_on_status=True):
         """views: list of WindowView (host) or DeviceView. Returns list of Result (all windows, on every rank)."""

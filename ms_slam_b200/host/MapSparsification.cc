@@ -110,8 +110,64 @@ void WindowSnapshot::Pack() {
     packed = true;
 }
 
+void SplitSnapshot(const WindowSnapshot& in, const vector<int32_t>& row_label, const vector<int32_t>& mp_label, int n_max,
+                   vector<WindowSnapshot>& parts) {
+    parts.clear();
+    const int K = in.K, H = in.H;
+    const size_t M = in.mp_nobs.size();
+    // components in order of their first window keyframe (labels are dense in that order already)
+    vector<int32_t> comp_of;                     // label -> part index or -1
+    for (int k = 0; k < K; ++k) {
+        const int32_t c = row_label[k];
+        if ((size_t)c >= comp_of.size()) comp_of.resize(c + 1, -1);
+        if (comp_of[c] < 0) { comp_of[c] = (int32_t)parts.size(); parts.emplace_back(); }
+    }
+    vector<int32_t> mp_new(M, -1), okf_new(H, -1);
+    for (size_t p = 0; p < M; ++p) {
+        const int32_t c = mp_label[p];
+        if (c < 0 || (size_t)c >= comp_of.size() || comp_of[c] < 0) continue;
+        WindowSnapshot& q = parts[comp_of[c]];
+        mp_new[p] = (int32_t)q.mp_nobs.size();
+        q.mp_nobs.push_back(in.mp_nobs[p]);
+        q.is_var.push_back(1);
+        q.vpMapPoints.push_back(in.vpMapPoints[p]);
+        q.part_mp.push_back((int32_t)p);
+    }
+    for (int j = 0; j < H; ++j) {
+        const int32_t c = row_label[K + j];
+        if ((size_t)c >= comp_of.size() || comp_of[c] < 0) continue;      // sees no variable of any window keyframe
+        WindowSnapshot& q = parts[comp_of[c]];
+        okf_new[j] = q.H++;
+        q.okf_total.push_back(in.okf_total[j]);
+        q.vpOutsideKFs.push_back(in.vpOutsideKFs[j]);
+    }
+    for (WindowSnapshot& q : parts) { q.feat_ptr.assign(1, 0); q.mp_obs_ptr.assign(1, 0); q.n_max_floor = n_max; }
+    for (int k = 0; k < K; ++k) {
+        WindowSnapshot& q = parts[comp_of[row_label[k]]];
+        for (int32_t s = in.feat_ptr[k]; s < in.feat_ptr[k + 1]; ++s) {
+            const int32_t p = in.feat_mp[s];
+            if (p < 0 || mp_new[p] < 0) continue;                        // not a variable: counts for nMax only (carried)
+            q.feat_mp.push_back(mp_new[p]);
+            q.feat_cell.push_back(in.feat_cell[s]);
+        }
+        q.feat_ptr.push_back((int32_t)q.feat_mp.size());
+        q.K++;
+    }
+    for (size_t p = 0; p < M; ++p) {
+        if (mp_new[p] < 0) continue;
+        WindowSnapshot& q = parts[comp_of[mp_label[p]]];
+        for (int32_t o = in.mp_obs_ptr[p]; o < in.mp_obs_ptr[p + 1]; ++o) {
+            const int32_t kf = in.mp_obs_kf[o];
+            if (kf >= K && okf_new[kf - K] >= 0) q.mp_obs_kf.push_back(q.K + okf_new[kf - K]);
+        }
+        q.mp_obs_ptr.push_back((int32_t)q.mp_obs_kf.size());
+    }
+    for (WindowSnapshot& q : parts) q.Pack();
+}
+
 mss_window_view WindowSnapshot::View() const {
     mss_window_view v{};
+    v.n_max_floor = n_max_floor;
     if (packed && blob && blob->p) {
         v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)n_pairs;
         v.memory = MSS_MEM_HOST;
@@ -273,7 +329,9 @@ void MapSparsification::Run() {
             vector<shared_ptr<KeyFrame>> vRemain;
             for (const shared_ptr<KeyFrame>& pKF : mpAtlas->GetAllKeyFrames())
                 if (!pKF->mbSparsified) vRemain.push_back(pKF);
+            mbFlushing = true;          // the flush window is split into its independent components (one batch launch)
             Sparsifying(vRemain);
+            mbFlushing = false;
             for (const shared_ptr<KeyFrame>& pKF : vRemain) pKF->EraseBadDescriptor();
             break;
         }
@@ -293,7 +351,48 @@ void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
     Clock::time_point t0 = Clock::now();
     int rc = MSS_E_CUDA;
     mss_result res{};
-    if (mpEngine) {
+    bool solved = false;
+    if (mpEngine && mbFlushing && mLast.K > 1) {
+        // final flush (MapSparsification.cc:38-47): the model is block diagonal along the connected components of the
+        // keyframe x variable graph -> solve the components as one batch of independent windows (same objective)
+        mss_set_params(mpEngine, mnMinNum, mfLambda, mfGridLambda);
+        const mss_window_view whole = mLast.View();
+        vector<int32_t> rowLabel(mLast.K + mLast.H), mpLabel(M);
+        int32_t ncomp = 0, nmax = 0;
+        if (mss_components(mpEngine, &whole, rowLabel.data(), mpLabel.data(), &ncomp, &nmax) == MSS_OK) {
+            vector<WindowSnapshot> parts;
+            SplitSnapshot(mLast, rowLabel, mpLabel, nmax, parts);
+            if (parts.size() > 1) {
+                const size_t n = parts.size();
+                vector<mss_window_view> views(n);
+                vector<mss_result> results(n);
+                vector<vector<uint32_t>> bits(n);
+                for (size_t i = 0; i < n; ++i) {
+                    views[i] = parts[i].View();
+                    bits[i].assign((parts[i].mp_nobs.size() + 31) / 32, 0xFFFFFFFFu);
+                    results[i] = mss_result{};
+                    results[i].keep_bits = bits[i].data();
+                }
+                rc = mss_solve_batch(mpEngine, (int32_t)n, views.data(), results.data());
+                if (rc == MSS_OK || rc == MSS_E_NOCONVERGE) {
+                    for (size_t i = 0; i < n; ++i) {
+                        for (size_t q = 0; q < parts[i].part_mp.size(); ++q)
+                            if (!((bits[i][q >> 5] >> (q & 31)) & 1u)) {
+                                const size_t p = (size_t)parts[i].part_mp[q];
+                                mKeepBits[p >> 5] &= ~(1u << (p & 31));
+                            }
+                        res.n_vars += results[i].n_vars; res.n_kept += results[i].n_kept; res.objective += results[i].objective;
+                        res.rounds = std::max(res.rounds, results[i].rounds);
+                    }
+                    rep.components = (int)n;
+                } else {
+                    std::cerr << "MapSparsification: window " << mnId << " not sparsified: " << mss_last_error(mpEngine) << std::endl;
+                }
+                solved = true;
+            }
+        }
+    }
+    if (mpEngine && !solved) {
         // the yaml values can be changed through the public member between windows, like upstream
         mss_set_params(mpEngine, mnMinNum, mfLambda, mfGridLambda);
         const mss_window_view view = mLast.View();

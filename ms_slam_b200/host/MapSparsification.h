@@ -46,6 +46,8 @@ struct WindowSnapshot {
     std::shared_ptr<Blob> blob;
     size_t off_slots = 0, off_nobs = 0, off_pairs = 0, off_okf = 0, n_pairs = 0;
     bool packed = false;
+    int n_max_floor = 0;       // window-wide nMax carried by a component of a larger window (mss.h)
+    std::vector<int32_t> part_mp;   // component only: index of each of its map points in the parent snapshot
     void Pack();
     mss_window_view View() const;
 };
@@ -53,6 +55,13 @@ struct WindowSnapshot {
 // Passes 1-3 of the reference (MapSparsification.cc:66-151) as ONE walk over the pointer graph that only records what it
 // sees; stamps mnMapSaprsificationId / mnMapSparsificationId / mnIndexForSparsification like the reference (:81,93,98).
 void FlattenWindow(const std::vector<std::shared_ptr<KeyFrame>>& vpKFs, long unsigned int nId, WindowSnapshot& out);
+
+// Independent sub-windows of a snapshot from the labels of mss_components: one per component that contains a window
+// keyframe, each carrying the window-wide nMax.  The reference solves the final flush as ONE model
+// (MapSparsification.cc:38-47); the model is block diagonal along these components, so solving them as a batch gives the
+// same objective and lets a flush shard over GPUs.
+void SplitSnapshot(const WindowSnapshot& in, const std::vector<int32_t>& row_label, const std::vector<int32_t>& mp_label,
+                   int n_max, std::vector<WindowSnapshot>& parts);
 
 struct SparsificationSettings {
     int N = 0, WindowLength = 0, NonLocalKF = 0;
@@ -88,6 +97,7 @@ public:
     struct WindowReport {
         int status = 0;                 // mss_status of the solve (0 ok); on error every map point was kept
         int K = 0, H = 0, M = 0, n_vars = 0, n_kept = 0, n_deleted = 0, rounds = 0;
+        int components = 1;             // independent sub-windows the window was solved as (one batch launch)
         double objective = 0.0, flatten_ms = 0.0, solve_ms = 0.0, apply_ms = 0.0;
     };
     std::vector<WindowReport> GetReports();
@@ -106,6 +116,7 @@ private:
     long unsigned int mnId;
     bool mbStopRequested;
     bool mbStopped;
+    bool mbFlushing = false;            // Sparsifying() is running the final flush
 
     mss_handle* mpEngine;               // replaces GRBEnv mGRBEnv (include/MapSparsification.h:59)
     float mfLambda;

@@ -223,16 +223,16 @@ int msh_map_counts(void* h, int64_t* out3) {
     return 0;
 }
 
-// reports of the windows processed so far: 12 doubles each
+// reports of the windows processed so far: 13 doubles each
 int msh_reports(void* h, double* out, int cap_windows) {
     World* w = static_cast<World*>(h);
     const auto reps = w->ms->GetReports();
     const int n = std::min(cap_windows, (int)reps.size());
     for (int i = 0; i < n; ++i) {
         const auto& r = reps[i];
-        double* o = out + 12 * i;
+        double* o = out + 13 * i;
         o[0] = r.status; o[1] = r.K; o[2] = r.H; o[3] = r.M; o[4] = r.n_vars; o[5] = r.n_kept; o[6] = r.n_deleted; o[7] = r.rounds;
-        o[8] = r.objective; o[9] = r.flatten_ms; o[10] = r.solve_ms; o[11] = r.apply_ms;
+        o[8] = r.objective; o[9] = r.flatten_ms; o[10] = r.solve_ms; o[11] = r.apply_ms; o[12] = r.components;
     }
     return (int)reps.size();
 }

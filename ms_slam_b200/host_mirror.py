@@ -122,7 +122,8 @@ class World:
         return dict(map_points=int(out[0]), sparsified_map_points=int(out[1]), sparsified_keyframes=int(out[2]))
 
     def reports(self):
-        out = np.zeros(12 * 64, np.float64)
+        out = np.zeros(13 * 64, np.float64)
         n = min(self.lib.msh_reports(self.h, _p(out), 64), 64)
-        keys = ["status", "K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "objective", "flatten_ms", "solve_ms", "apply_ms"]
-        return [dict(zip(keys, out[12 * i:12 * i + 12].tolist())) for i in range(n)]
+        keys = ["status", "K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "objective", "flatten_ms", "solve_ms", "apply_ms",
+                "components"]
+        return [dict(zip(keys, out[13 * i:13 * i + 13].tolist())) for i in range(n)]

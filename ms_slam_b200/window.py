@@ -41,6 +41,7 @@ class WindowView:
     kf_gid: np.ndarray = None  # uint64 [K+H]
     mp_gid: np.ndarray = None  # uint64 [M]
     meta: dict = field(default_factory=dict)
+    n_max_floor: int = 0       # nMax is at least this (component of a larger window, include/mss.h)
 
     def __post_init__(self):
         c = np.ascontiguousarray
@@ -90,7 +91,7 @@ class WindowView:
         obs_ptr[1:] = np.cumsum(np.bincount(mp[out], minlength=self.M))
         v = WindowView(K=self.K, H=self.H, feat_ptr=feat_ptr, feat_mp=self.feat_mp[keep], feat_cell=self.feat_cell[keep],
                        mp_nobs=self.mp_nobs, mp_obs_ptr=obs_ptr, mp_obs_kf=self.mp_obs_kf[out], okf_total=self.okf_total,
-                       kf_gid=self.kf_gid, mp_gid=self.mp_gid)
+                       kf_gid=self.kf_gid, mp_gid=self.mp_gid, n_max_floor=self.n_max_floor)
         v.meta = dict(self.meta, compact=True)
         return v
 
@@ -114,7 +115,8 @@ class WindowView:
         src = np.repeat(self.mp_obs_ptr[:-1][perm] - obs_ptr[:-1], cnt) + np.arange(int(obs_ptr[-1]))
         v = WindowView(K=self.K, H=self.H, feat_ptr=self.feat_ptr, feat_mp=feat_mp, feat_cell=self.feat_cell,
                        mp_nobs=self.mp_nobs[perm], mp_obs_ptr=obs_ptr, mp_obs_kf=self.mp_obs_kf[src], okf_total=self.okf_total,
-                       kf_gid=self.kf_gid, mp_gid=self.mp_gid[perm] if self.mp_gid is not None and len(self.mp_gid) == self.M else self.mp_gid)
+                       kf_gid=self.kf_gid, mp_gid=self.mp_gid[perm] if self.mp_gid is not None and len(self.mp_gid) == self.M else self.mp_gid,
+                       n_max_floor=self.n_max_floor)
         v.meta = dict(self.meta, discovery_order=True, mp_perm=perm)
         return v
 
@@ -155,6 +157,84 @@ class WindowView:
         return cls(K=int(z["K"]), H=int(z["H"]), **{n: z[n] for n in cls._ARRAYS})
 
 
+def split_components(view: WindowView, row_label, mp_label, n_max: int):
+    """Independent sub-windows of a window, from the labels mss_components returns (include/mss.h).  Only components that
+    contain a window keyframe become windows (an outside keyframe that sees no variable constrains nothing).  Every part
+    carries the window-wide nMax as n_max_floor.  Returns [(part, kf_idx, mp_idx)]: part.K keyframes = view keyframes kf_idx
+    (in order), part map points = view map points mp_idx (in order; non-variables that only count for nMax are dropped,
+    nMax being carried explicitly)."""
+    row_label = np.asarray(row_label)
+    mp_label = np.asarray(mp_label)
+    K, H = view.K, view.H
+    feat_kf = np.repeat(np.arange(K, dtype=np.int64), np.diff(view.feat_ptr))
+    obs_mp = np.repeat(np.arange(view.M, dtype=np.int64), np.diff(view.mp_obs_ptr))
+    parts = []
+    for c in np.unique(row_label[:K]):
+        kf_idx = np.nonzero(row_label[:K] == c)[0]
+        okf_idx = np.nonzero(row_label[K:] == c)[0]
+        mp_idx = np.nonzero(mp_label == c)[0]
+        mp_new = np.full(view.M, -1, np.int64)
+        mp_new[mp_idx] = np.arange(mp_idx.size)
+        kf_new = np.full(K + H, -1, np.int64)
+        kf_new[kf_idx] = np.arange(kf_idx.size)
+        kf_new[K + okf_idx] = kf_idx.size + np.arange(okf_idx.size)
+        sl = np.isin(feat_kf, kf_idx)
+        f_mp = view.feat_mp[sl].astype(np.int64)
+        f_mp = np.where(f_mp >= 0, mp_new[np.maximum(f_mp, 0)], -1)      # slots of non-variables become empty
+        feat_ptr = np.zeros(kf_idx.size + 1, np.int64)
+        feat_ptr[1:] = np.cumsum(np.diff(view.feat_ptr)[kf_idx])
+        ob = (mp_new[obs_mp] >= 0) & (kf_new[view.mp_obs_kf] >= 0)
+        cnt = np.bincount(mp_new[obs_mp[ob]], minlength=mp_idx.size)
+        obs_ptr = np.zeros(mp_idx.size + 1, np.int64)
+        obs_ptr[1:] = np.cumsum(cnt)
+        part = WindowView(K=int(kf_idx.size), H=int(okf_idx.size), feat_ptr=feat_ptr, feat_mp=f_mp, feat_cell=view.feat_cell[sl],
+                          mp_nobs=view.mp_nobs[mp_idx], mp_obs_ptr=obs_ptr, mp_obs_kf=kf_new[view.mp_obs_kf[ob]],
+                          okf_total=view.okf_total[okf_idx], kf_gid=np.concatenate([view.kf_gid[kf_idx], view.kf_gid[K + okf_idx]]),
+                          mp_gid=view.mp_gid[mp_idx], n_max_floor=int(n_max))
+        parts.append((part, kf_idx, mp_idx))
+    return parts
+
+
+def merge_views(views, interleave: bool = True) -> WindowView:
+    """One window made of several independent ones (disjoint map points and keyframes): what a final flush over an atlas
+    with several covisibility components looks like.  With interleave the window keyframes of the inputs alternate, so
+    components are not contiguous keyframe ranges.  Map points are concatenated in input order."""
+    Ks = [v.K for v in views]
+    order = []                                            # (view, local kf) in merged window order
+    if interleave:
+        for i in range(max(Ks) if Ks else 0):
+            order += [(a, i) for a, v in enumerate(views) if i < v.K]
+    else:
+        for a, v in enumerate(views):
+            order += [(a, i) for i in range(v.K)]
+    K = len(order)
+    mp_base = np.concatenate([[0], np.cumsum([v.M for v in views])]).astype(np.int64)
+    okf_base = K + np.concatenate([[0], np.cumsum([v.H for v in views])]).astype(np.int64)
+    kf_pos = [np.full(v.K, -1, np.int64) for v in views]
+    for pos, (a, i) in enumerate(order):
+        kf_pos[a][i] = pos
+    feat_ptr, feat_mp, feat_cell = [0], [], []
+    for a, i in order:
+        v = views[a]
+        s, e = int(v.feat_ptr[i]), int(v.feat_ptr[i + 1])
+        m = v.feat_mp[s:e].astype(np.int64)
+        feat_mp.append(np.where(m >= 0, m + mp_base[a], -1))
+        feat_cell.append(v.feat_cell[s:e])
+        feat_ptr.append(feat_ptr[-1] + (e - s))
+    obs_ptr, obs_kf = [np.zeros(1, np.int64)], []
+    off = 0
+    for a, v in enumerate(views):
+        kf = v.mp_obs_kf.astype(np.int64)
+        obs_kf.append(np.where(kf < v.K, kf_pos[a][np.minimum(kf, max(v.K - 1, 0))] if v.K else kf, kf - v.K + okf_base[a]))
+        obs_ptr.append(v.mp_obs_ptr[1:].astype(np.int64) + off)
+        off += v.O
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return WindowView(K=K, H=int(sum(v.H for v in views)), feat_ptr=np.asarray(feat_ptr), feat_mp=cat(feat_mp, np.int32),
+                      feat_cell=cat(feat_cell, np.uint16), mp_nobs=cat([v.mp_nobs for v in views], np.int32),
+                      mp_obs_ptr=np.concatenate(obs_ptr), mp_obs_kf=cat(obs_kf, np.int32),
+                      okf_total=cat([v.okf_total for v in views], np.int32))
+
+
 SLOT_CELL_NONE = 0xFFF        # include/mss.h MSS_SLOT_CELL_NONE
 SLOT_EMPTY = 0xFFFFFFFF       # include/mss.h MSS_SLOT_EMPTY
 
@@ -172,6 +252,7 @@ class PackedView:
     obs_pairs: np.ndarray     # uint32 [O] (map point << 12) | outside keyframe j (KF-table index K + j)
     okf_total: np.ndarray     # int32 [H]
     meta: dict = field(default_factory=dict)
+    n_max_floor: int = 0
 
     @property
     def F(self) -> int:
@@ -199,7 +280,7 @@ def pack_view(v: WindowView) -> PackedView:
     pairs = ((owner[outside] << 12) | (v.mp_obs_kf[outside].astype(np.int64) - v.K)).astype(np.uint32)
     return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
                       mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
-                      okf_total=v.okf_total, meta=dict(v.meta, packed=True))
+                      okf_total=v.okf_total, meta=dict(v.meta, packed=True), n_max_floor=v.n_max_floor)
 
 
 def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:

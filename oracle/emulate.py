@@ -80,7 +80,7 @@ class Emulator:
         self.K, self.H, self.M = K, H, M
         feat_kf = np.repeat(np.arange(K, dtype=np.int64), np.diff(view.feat_ptr))
         valid = view.feat_mp >= 0
-        self.n_max = int(view.mp_nobs[view.feat_mp[valid]].max()) if valid.any() else 0
+        self.n_max = max(int(view.mp_nobs[view.feat_mp[valid]].max()) if valid.any() else 0, int(getattr(view, "n_max_floor", 0)))
         grid = valid & (view.feat_cell != CELL_NONE)
         self.e_row = feat_kf[grid]
         self.e_var = view.feat_mp[grid].astype(np.int64)

@@ -73,6 +73,7 @@ def build_model(view, N) -> Model:
     feat_kf = np.repeat(np.arange(K, dtype=np.int64), np.diff(view.feat_ptr))
     valid = view.feat_mp >= 0
     n_max = int(view.mp_nobs[view.feat_mp[valid]].max()) if valid.any() else 0
+    n_max = max(n_max, int(getattr(view, "n_max_floor", 0)))      # component of a larger window: window-wide nMax (mss.h)
     grid = valid & (view.feat_cell != CELL_NONE)
     idx = np.nonzero(grid)[0]
     e_kf = feat_kf[idx]

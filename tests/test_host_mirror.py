@@ -198,3 +198,43 @@ def test_final_flush_takes_all_unsparsified_keyframes(hm):
     finally:
         eng.close()
         w.close()
+
+
+@pytest.mark.gpu
+def test_final_flush_splits_into_components(hm):
+    """A flush over an atlas with three disjoint covisibility components: the C++ class finds the components on the device
+    (mss_components), solves them as ONE batch of independent windows carrying the window-wide nMax, and deletes exactly
+    what the engine selects for each component; the union satisfies every row of the undivided model and its objective is
+    the sum of the parts (the flush model of MapSparsification.cc:38-47 is block diagonal)."""
+    from ms_slam_b200 import merge_views, split_components, pack_view
+    from ms_slam_b200.engine import Engine
+    from oracle import ilp_model as om, components as oc
+    N = 100
+    parts = [msgen.make_config("live", 41)[0], msgen.make_config("c1", 6)[0], msgen.make_config("live", 42, M=1500, H=20)[0]]
+    whole = merge_views(parts, interleave=True)
+    w = hm.World(whole, N=N, window_length=8)
+    eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    try:
+        w.start()
+        w.feed(0, 5)
+        assert w.finish() == 0
+        reps = w.reports()
+        assert len(reps) == 1 and reps[0]["K"] == whole.K and reps[0]["status"] == 0
+        flat, mp_ids, okf_ids, is_var = w.snapshot(1)
+        rows, mps, nc, nmax = oc.components(flat)
+        split = split_components(flat, rows, mps, nmax)
+        assert reps[0]["components"] == len(split) >= 3
+        res = eng.solve_batch([pack_view(p.compact()) for p, _, _ in split])
+        exp_bad = np.zeros(whole.M, bool)
+        for (p, _, mp_idx), r in zip(split, res):
+            exp_bad[mp_ids[mp_idx[~r.keep]]] = True
+        assert np.array_equal(w.bad_flags(), exp_bad)
+        assert reps[0]["objective"] == sum(r.objective for r in res)
+        model = om.build_model(whole, N)
+        x = om.keep_to_x(model, ~exp_bad)
+        assert om.rows_satisfied(model, x, N)[0]
+        assert om.objective(model, x, N, LAM, GLAM) == reps[0]["objective"]
+        assert w.forwarded_ids() == list(range(whole.K))
+    finally:
+        eng.close()
+        w.close()
