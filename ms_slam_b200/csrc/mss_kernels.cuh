@@ -651,6 +651,82 @@ __device__ void w4_pairs(const Params& P, const WinDesc& D, int gt, int gsz) {
     }
 }
 
+__device__ __forceinline__ void prop_decide(const Params& P, unsigned long long a, int cost_i, uint8_t* st, float* gain, unsigned deg,
+                                            int& changed, int& nfree, int& sumdeg);
+__device__ __forceinline__ void prop_commit(RoundCnt& rc, int* vdst, int mp, int changed, int nfree, int sumdeg);
+__device__ __forceinline__ void prop_commit4(RoundCnt& rc, int* vdst, const int* mp, const int* nfree);
+__device__ __forceinline__ void prop_flush(RoundCnt& rc, int changed, int sumdeg);
+
+// Packed layout: W2 and the round-1 decision of W4 as flat passes over the map points (no owner search, hence no shared
+// staging and no per-tile barriers; four independent map points in flight per thread, consecutive threads on consecutive
+// map points).  Same arithmetic as the tile versions.
+__device__ void w2_flat(const Params& P, const WinDesc& D, WinState& ws, int gt, int gsz, BlockScratch& S) {
+    const int mpad = ((max(D.M, 1) + kVarTile - 1) / kVarTile) * kVarTile;
+    int nmax = 0, nv = 0;
+    for (int base = gt; base < mpad; base += gsz * kVpt) {
+        unsigned long long a[kVpt];
+        uint8_t sn[kVpt];
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int mp = base + j * gsz;
+            a[j] = mp < D.M ? P.acc[D.var_base + mp] : 0ull;
+            sn[j] = mp < D.M ? P.seen[D.var_base + mp] : (uint8_t)0;
+        }
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int mp = base + j * gsz;
+            if (mp < mpad) P.st[D.var_base + mp] = a[j] != 0ull ? (uint8_t)ST_FREE : (uint8_t)ST_NOTVAR;
+            if (a[j] != 0ull || sn[j]) nmax = max(nmax, ld_nobs(D, mp));
+            nv += a[j] != 0ull ? 1 : 0;
+        }
+    }
+    nmax = block_max(S, nmax);
+    int z0 = 0, z1 = 0;
+    block_sum3(S, nv, z0, z1);
+    if (threadIdx.x == 0) {
+        if (nmax > 0) atomicMax(&ws.n_max, nmax);
+        if (nv) atomicAdd(&ws.n_vars, nv);
+    }
+}
+
+__device__ void w4_flat(const Params& P, const WinDesc& D, WinState& ws, int gt, int gsz) {
+    const int lim = (D.M + 31) & ~31;                       // warp-uniform bound: the commit uses full-warp ballots
+    int changed = 0, sumdeg = 0;
+    for (int base = gt; base < lim; base += gsz * kVpt) {
+        bool isvar[kVpt];
+        unsigned long long a[kVpt];
+        int nobs[kVpt];
+        unsigned nout[kVpt];
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int mp = base + j * gsz;
+            isvar[j] = mp < D.M && P.st[D.var_base + mp] == ST_FREE;
+        }
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int g = D.var_base + base + j * gsz;
+            a[j] = 0ull; nobs[j] = 0; nout[j] = 0u;
+            if (isvar[j]) { a[j] = P.acc[g]; nobs[j] = ld_nobs(D, base + j * gsz); if (D.H > 0) nout[j] = P.deg[g]; }
+        }
+        int mps[kVpt], nfr[kVpt];
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int mp = base + j * gsz;
+            const int g = D.var_base + mp;
+            mps[j] = mp;
+            nfr[j] = 0;
+            if (isvar[j]) {
+                const unsigned deg = (unsigned)(a[j] & 0xFFFFu) + nout[j];
+                P.deg[g] = deg;
+                P.acc[g] = 0ull;
+                prop_decide(P, a[j], ws.n_max - nobs[j], &P.st[g], &P.gain[g], deg, changed, nfr[j], sumdeg);
+            }
+        }
+        prop_commit4(ws.rc[0], P.vlist + D.var_base, mps, nfr);
+    }
+    prop_flush(ws.rc[0], changed, sumdeg);
+}
+
 // W3 (one CTA per window): exclusive scan of the outside-row counts -> segments, rhs of the outside rows
 __device__ void w3_scan_outside(const Params& P, const WinDesc& D, BlockScratch& S) {
     int carry = 0;
@@ -702,6 +778,35 @@ __device__ __forceinline__ void prop_commit(RoundCnt& rc, int* vdst, int mp, int
     }
     pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
     if (nfree) vdst[pos + __popc(mk & ((1u << lane) - 1u))] = mp;
+}
+
+// The same for kVpt decisions per thread at once: ONE reservation per warp for all of them (the counters of a window live
+// in one cache line, so per-decision atomics from every warp of the group serialise in L2); changed / sumdeg are left to
+// the caller, which adds them up over its whole loop and flushes them once (prop_flush).
+__device__ __forceinline__ void prop_commit4(RoundCnt& rc, int* vdst, const int* mp, const int* nfree) {
+    const int lane = threadIdx.x & 31;
+    unsigned mk[4];
+    int tot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mk[j] = __ballot_sync(0xFFFFFFFFu, nfree[j] != 0); tot += __popc(mk[j]); }
+    if (tot == 0) return;
+    int pos = 0;
+    if (lane == 0) pos = (int)atomicAdd(&rc.nfree, (unsigned)tot);
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (nfree[j]) vdst[pos + __popc(mk[j] & lt)] = mp[j];
+        pos += __popc(mk[j]);
+    }
+}
+__device__ __forceinline__ void prop_flush(RoundCnt& rc, int changed, int sumdeg) {
+    changed = __reduce_add_sync(0xFFFFFFFFu, changed);
+    sumdeg = __reduce_add_sync(0xFFFFFFFFu, sumdeg);
+    if ((threadIdx.x & 31) == 0) {
+        if (changed) atomicAdd(&rc.changed, (unsigned)changed);
+        if (sumdeg) atomicAdd(&rc.sumdeg, (unsigned)sumdeg);
+    }
 }
 
 // W4: per super-tile of map points: fill the outside rows, add their round-1 contributions, take the round-1 decision
@@ -1297,6 +1402,45 @@ __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, 
 __device__ void var_list_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int greedy_steps,
                                const int* vsrc, int nsrc, int* vdst, const GroupCtx& G) {
     const bool any_rule = greedy_steps >= P.all_rule_steps;
+    if (mode == MODE_PROP) {
+        // four list positions per thread and iteration: independent loads in flight, one list reservation per warp
+        const int gsz = G.ncta * kThreads;
+        int changed = 0, sumdeg = 0;
+        for (int base = G.cta * kThreads + (int)threadIdx.x; base - (int)(threadIdx.x & 31) < nsrc; base += gsz * 4) {
+            int mps[4], nfr[4];
+            uint8_t s4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * gsz;
+                mps[j] = i < nsrc ? vsrc[i] : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = mps[j] >= 0 ? P.st[D.var_base + mps[j]] : (uint8_t)ST_NOTVAR;
+            unsigned long long a4[4];
+            int nobs4[4];
+            unsigned deg4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a4[j] = 0ull; nobs4[j] = 0; deg4[j] = 0u;
+                if (s4[j] == ST_FREE) {
+                    const int g = D.var_base + mps[j];
+                    a4[j] = P.acc[g]; nobs4[j] = ld_nobs(D, mps[j]); deg4[j] = P.deg[g];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                nfr[j] = 0;
+                if (s4[j] == ST_FREE) {
+                    const int g = D.var_base + mps[j];
+                    if (a4[j]) P.acc[g] = 0ull;
+                    prop_decide(P, a4[j], ws.n_max - nobs4[j], &P.st[g], &P.gain[g], deg4[j], changed, nfr[j], sumdeg);
+                }
+            }
+            prop_commit4(rc, vdst, mps, nfr);
+        }
+        prop_flush(rc, changed, sumdeg);
+        return;
+    }
     for (int base = G.cta * kThreads; base < nsrc; base += G.ncta * kThreads) {
         const int i = base + (int)threadIdx.x;
         int mp = -1, g = 0;
@@ -1824,18 +1968,30 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     // ---- W2..W4: outside rows + round 1 ----------------------------------------------------------------------------
     ObsTile& OT = *reinterpret_cast<ObsTile*>(keytab);             // shared scratch of the variable passes
     const int stiles = (D.M + kSuper - 1) / kSuper;
-    for (int t = G.cta; t < stiles; t += G.ncta) w2_vars_and_outside_counts(P, D, ws, t, OT, S);
-    if (D.packed && D.H > 0) w2_pairs(P, D, ws, gt, gsz);
+    if (D.packed) {
+        w2_flat(P, D, ws, gt, gsz, S);
+        if (D.H > 0) w2_pairs(P, D, ws, gt, gsz);
+    } else {
+        for (int t = G.cta; t < stiles; t += G.ncta) w2_vars_and_outside_counts(P, D, ws, t, OT, S);
+    }
     if (!group_sync(P, G)) return false;
-    if (G.cta == 0) w3_scan_outside(P, D, S);
-    if (!group_sync(P, G)) return false;
-    trace_mark(P, G, w, tn, 13, 0, t_win);
-    if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
-    if (D.packed && D.H > 0) {
-        w4_pairs(P, D, gt, gsz);
+    trace_mark(P, G, w, tn, 12, 0, t_win);
+    if (D.H > 0) {                            // (no outside rows: nothing to scan, one barrier less)
+        if (G.cta == 0) w3_scan_outside(P, D, S);
         if (!group_sync(P, G)) return false;
     }
-    for (int t = G.cta; t < stiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, OT);
+    trace_mark(P, G, w, tn, 13, 0, t_win);
+    if (ws.error) return true;                // view failed validation: the slot stays unwritten (host keeps every point)
+    if (D.packed) {
+        if (D.H > 0) {
+            w4_pairs(P, D, gt, gsz);
+            if (!group_sync(P, G)) return false;
+            trace_mark(P, G, w, tn, 15, 0, t_win);
+        }
+        w4_flat(P, D, ws, gt, gsz);
+    } else {
+        for (int t = G.cta; t < stiles; t += G.ncta) w4_fill_and_round1(P, D, ws, t, OT);
+    }
     if (!group_sync(P, G)) return false;
     if (w == P.gwin[0] && G.cta == 0 && threadIdx.x == 0) P.ctrl->t_build = globaltimer_ns();
 
