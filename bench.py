@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--order", default="discovery", choices=["generated", "discovery"],
                     help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
                          "(mnIndexForSparsification, MapSparsification.cc:91-99) or as msgen draws them (random)")
+    ap.add_argument("--unsorted-slots", action="store_true", help="packed layout: keep the slots of a keyframe in slot order")
     ap.add_argument("--layout", default="packed", choices=["packed", "soa"], help="transport layout of the views (include/mss.h mss_layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -267,7 +268,7 @@ def main():
         def make(w):
             v = msgen.make_config(args.workload, seed=w)[0].compact()
             v = v.discovery_order() if args.order == "discovery" else v
-            return pack_view(v) if args.layout == "packed" else v
+            return pack_view(v, sort_slots=not args.unsorted_slots) if args.layout == "packed" else v
         views = dict(zip(mine, pool.map(make, mine)))
     K, H, M = cfg["K"], cfg["H"], cfg["M"]
     words, rows = (M + 31) // 32, K + H

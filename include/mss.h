@@ -100,7 +100,8 @@ typedef struct mss_window_view {
                                   of a larger window (mss_components) carries the window-wide nMax here, so that its costs are
                                   the ones the whole-window model would use */
     const uint32_t* slots;     /* [F]   (map-point table index << 12) | (col*48+row), low 12 bits MSS_SLOT_CELL_NONE = not in mGrid;
-                                        MSS_SLOT_EMPTY = empty slot */
+                                        MSS_SLOT_EMPTY = empty slot.  The order of the slots inside a keyframe is free (the
+                                        result does not depend on it); sorted by value is the fastest */
     const uint16_t* mp_nobs16; /* [M]   MapPoint::Observations() */
     const uint32_t* obs_pairs; /* [O]   observations of the window's map points by OUTSIDE keyframes only, in any order:
                                         (map-point table index << 12) | j, j = 0..H-1 the outside keyframe (KF-table index K + j) */

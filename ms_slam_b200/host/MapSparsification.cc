@@ -99,6 +99,9 @@ void WindowSnapshot::Pack() {
         const uint32_t cell = feat_cell[i] == (uint16_t)MSS_CELL_NONE ? MSS_SLOT_CELL_NONE : (uint32_t)feat_cell[i];
         slots[i] = feat_mp[i] < 0 ? MSS_SLOT_EMPTY : (((uint32_t)feat_mp[i] << 12) | cell);
     }
+    // the order of the slots inside a keyframe carries no meaning for the model; sorted by map-point index the 32 entries
+    // a warp handles touch neighbouring map points (nearly coalesced state gathers in the row phases)
+    for (int k = 0; k < K; ++k) std::sort(slots + feat_ptr[k], slots + feat_ptr[k + 1]);
     uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
     for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
     uint32_t* pairs = reinterpret_cast<uint32_t*>(blob->p + off_pairs);

@@ -266,8 +266,11 @@ class PackedView:
         return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.obs_pairs.nbytes + self.okf_total.nbytes)
 
 
-def pack_view(v: WindowView) -> PackedView:
-    """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges."""
+def pack_view(v: WindowView, sort_slots: bool = False) -> PackedView:
+    """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges.
+    sort_slots: order the slots of every keyframe by map-point index (the order of the slots inside a keyframe carries no
+    meaning for the model; sorted, the 32 entries a warp handles touch neighbouring map points, which turns the state
+    gathers of the row phases into nearly coalesced accesses).  FlattenWindow emits this order."""
     if v.M > (1 << 20) or v.H > 4095:
         raise ValueError("window too large for the packed layout")
     if v.M and int(v.mp_nobs.max()) > 65535:
@@ -275,6 +278,9 @@ def pack_view(v: WindowView) -> PackedView:
     mp = v.feat_mp.astype(np.int64)
     cell = np.where(v.feat_cell == CELL_NONE, SLOT_CELL_NONE, v.feat_cell).astype(np.int64)
     slots = np.where(mp >= 0, (mp << 12) | cell, SLOT_EMPTY).astype(np.uint32)
+    if sort_slots and slots.size:
+        kf = np.repeat(np.arange(v.K, dtype=np.int64), np.diff(v.feat_ptr))
+        slots = slots[np.lexsort((slots, kf))]
     owner = np.repeat(np.arange(v.M, dtype=np.int64), np.diff(v.mp_obs_ptr))
     outside = v.mp_obs_kf >= v.K                     # observations by window keyframes are not part of the pair list
     pairs = ((owner[outside] << 12) | (v.mp_obs_kf[outside].astype(np.int64) - v.K)).astype(np.uint32)
