@@ -1467,52 +1467,70 @@ __device__ void var_list_phase(const Params& P, const WinDesc& D, WinState& ws, 
     }
 }
 
-// D1 / D2 / EVAL look at every map point of a 256-wide tile (one thread per map point)
-__device__ void var_tile_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int tile, BlockScratch& S) {
-    const int mp = tile * kVarTile + (int)threadIdx.x;
-    const int g = D.var_base + mp;
-    const bool inb = mp < D.M;
-    const uint8_t s = inb ? P.st[g] : (uint8_t)ST_NOTVAR;
-    int c0 = 0, c1 = 0, c2 = 0;
-    switch (mode) {
-    case MODE_D1: {
-        if (s == ST_IN) {
-            const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0ull;
-            const double critc = (double)(a & 0xFFFFu), critr = (double)((a >> 32) & 0xFFFFu);
-            const double cost = (double)(ws.n_max - ld_nobs(D, mp));
-            const double dF = __dadd_rn(__dadd_rn(-cost, __dmul_rn(P.glam, critc)), __dmul_rn(P.lam, critr));
-            if (dF < 0.0) { P.st[g] = ST_CAND; P.gain[g] = (float)(-dF); c0 = 1; }
+// D1 / D2 / EVAL look at every map point: one flat pass, four map points in flight per thread (a warp always holds 32
+// consecutive map points, which is what the ballot-packed keep words need), counters flushed once per warp
+__device__ void var_flat_phase(const Params& P, const WinDesc& D, WinState& ws, RoundCnt& rc, int mode, int gt, int gsz) {
+    const int lim = (D.M + 31) & ~31;
+    const int words = (D.M + 31) >> 5;
+    int ncand = 0, kept = 0;
+    long long cost = 0;
+    for (int base = gt; base < lim; base += gsz * kVpt) {
+        uint8_t s4[kVpt];
+#pragma unroll
+        for (int j = 0; j < kVpt; ++j) {
+            const int mp = base + j * gsz;
+            s4[j] = mp < D.M ? P.st[D.var_base + mp] : (uint8_t)ST_NOTVAR;
         }
-        if (__syncthreads_or(c0)) {
-            block_sum3(S, c0, c1, c2);
-            if (threadIdx.x == 0 && c0) atomicAdd(&rc.ncand, (unsigned)c0);
+        if (mode == MODE_D1) {
+            unsigned long long a4[kVpt];
+            int nobs4[kVpt];
+#pragma unroll
+            for (int j = 0; j < kVpt; ++j) {
+                a4[j] = 0ull; nobs4[j] = 0;
+                if (s4[j] == ST_IN) { a4[j] = P.acc[D.var_base + base + j * gsz]; nobs4[j] = ld_nobs(D, base + j * gsz); }
+            }
+#pragma unroll
+            for (int j = 0; j < kVpt; ++j) {
+                if (s4[j] != ST_IN) continue;
+                const int g = D.var_base + base + j * gsz;
+                if (a4[j]) P.acc[g] = 0ull;
+                const double critc = (double)(a4[j] & 0xFFFFu), critr = (double)((a4[j] >> 32) & 0xFFFFu);
+                const double c = (double)(ws.n_max - nobs4[j]);
+                const double dF = __dadd_rn(__dadd_rn(-c, __dmul_rn(P.glam, critc)), __dmul_rn(P.lam, critr));
+                if (dF < 0.0) { P.st[g] = ST_CAND; P.gain[g] = (float)(-dF); ++ncand; }
+            }
+        } else if (mode == MODE_D2) {
+#pragma unroll
+            for (int j = 0; j < kVpt; ++j) {
+                if (s4[j] != ST_CAND) continue;
+                const int g = D.var_base + base + j * gsz;
+                const unsigned long long a = P.acc[g];
+                if (a) P.acc[g] = 0ull;
+                P.st[g] = (a & FLAG_BLOCKED) ? ST_IN : ST_OUT;
+            }
+        } else {    // MODE_EVAL / MODE_EVALV: read-out (MapSparsification.cc:159-166): bit = 0 only for variables the solve rejected
+#pragma unroll
+            for (int j = 0; j < kVpt; ++j) {
+                const int mp = base + j * gsz;
+                if (mp >= lim) break;                                   // (warp-uniform)
+                const bool keep = mp < D.M && s4[j] != ST_OUT;
+                const unsigned word = __ballot_sync(0xFFFFFFFFu, keep);
+                if ((threadIdx.x & 31) == 0 && (mp >> 5) < words) P.out[D.out_off + kHdrWords + (mp >> 5)] = word;
+                if (s4[j] == ST_IN) { ++kept; cost += (long long)(ws.n_max - ld_nobs(D, mp)); }
+            }
         }
-    } break;
-    case MODE_D2: {
-        if (s == ST_CAND) {
-            const unsigned long long a = P.acc[g];
-            if (a) P.acc[g] = 0ull;
-            P.st[g] = (a & FLAG_BLOCKED) ? ST_IN : ST_OUT;
-        }
-    } break;
-    case MODE_EVAL:
-    case MODE_EVALV: {
-        // read-out (MapSparsification.cc:159-166): bit = 0 only for variables the solve rejected
-        const bool keep = inb && (s != ST_OUT);
-        const unsigned word = __ballot_sync(0xFFFFFFFFu, keep);
-        const int words = (D.M + 31) >> 5;
-        const int widx = mp >> 5;
-        if ((threadIdx.x & 31) == 0 && widx < words) P.out[D.out_off + kHdrWords + widx] = word;
-        int kept = (s == ST_IN) ? 1 : 0;
-        int cost = kept ? (ws.n_max - ld_nobs(D, mp)) : 0;    // < 2^31 per block: 256 * nMax
-        block_sum3(S, kept, cost, c2);
-        if (threadIdx.x == 0 && kept) {
+    }
+    if (mode == MODE_D1) {
+        ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
+        if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(&rc.ncand, (unsigned)ncand);
+    } else if (mode == MODE_EVAL || mode == MODE_EVALV) {
+        kept = __reduce_add_sync(0xFFFFFFFFu, kept);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+        if ((threadIdx.x & 31) == 0 && kept) {
             atomicAdd(&rc.nkept, (unsigned)kept);
             atomicAdd(&rc.sumcost, (unsigned long long)cost);
         }
-    } break;
-    default: break;
     }
 }
 
@@ -1928,7 +1946,6 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     const WinDesc D = P.win[w];
     WinState& ws = P.ws[w];
     const int rows = D.K + D.H;
-    const int tiles = (D.M + kVarTile - 1) / kVarTile;
     const int gt = G.cta * kThreads + (int)threadIdx.x, gsz = G.ncta * kThreads;
     const unsigned long long t_win = globaltimer_ns();
     int tn = 0;
@@ -2048,7 +2065,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
             var_list_phase(P, D, ws, rc, mode, greedy_steps, P.vlist + (size_t)vbuf * P.Mpad + D.var_base, vcnt,
                            P.vlist + (size_t)(vbuf ^ 1) * P.Mpad + D.var_base, G);
         } else {
-            for (int t = G.cta; t < tiles; t += G.ncta) var_tile_phase(P, D, ws, rc, mode, t, S);
+            var_flat_phase(P, D, ws, rc, mode, gt, gsz);
         }
         if (!group_sync(P, G)) return false;
         trace_mark(P, G, w, tn, mode, rc.nfree, t_win);
