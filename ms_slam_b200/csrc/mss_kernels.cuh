@@ -1339,6 +1339,61 @@ __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int
     }
 }
 
+// D2 on an IN list held in registers (one load of the entries, one gather of the states)
+template <int EPT>
+__device__ __forceinline__ void row_d2_regs(const Params& P, const WinDesc& D, int n, const uint32_t* src, int need, unsigned* tab,
+                                            unsigned long long* keytab, BlockScratch& S) {
+    const float* gain_w = P.gain + D.var_base;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    RowRegs<EPT> X;
+    load_row(X, src, n, P.st + D.var_base);
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        const unsigned cell = X.e[b] & kCellCov;
+        if (X.e[b] != kEntInvalid && cell != kCellCov) { tab[cell] = 0u; keytab[cell] = 0ull; }
+    }
+    __syncthreads();
+    int cov = 0, ncand = 0, z = 0;
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if (X.e[b] == kEntInvalid || (X.s[b] != ST_IN && X.s[b] != ST_CAND)) continue;
+        ++cov;
+        if (X.s[b] == ST_CAND) ++ncand;
+        if ((X.e[b] & kCellCov) != kCellCov) atomicAdd(&tab[X.e[b] & kCellCov], 1u);
+    }
+    block_sum3(S, cov, ncand, z);
+    if (ncand == 0) return;
+    unsigned long long key[EPT];
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        key[b] = 0ull;
+        if (X.e[b] != kEntInvalid && X.s[b] == ST_CAND) {
+            const unsigned v = X.e[b] >> kCellBits, cell = X.e[b] & kCellCov;
+            key[b] = make_key(gain_w[v], v);
+            if (cell != kCellCov && tab[cell] >= 2u) atomicMax(&keytab[cell], key[b]);
+        }
+    }
+    __syncthreads();
+    unsigned blocked = 0u;
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if (!key[b]) continue;
+        const unsigned cell = X.e[b] & kCellCov;
+        if (cell != kCellCov && tab[cell] >= 2u && keytab[cell] != key[b]) blocked |= 1u << b;
+    }
+    const int u = cov - need;
+    if (u > 0 && ncand > u) {
+        const unsigned long long thr = block_kth_largest(S, u, [&](auto sink) {
+#pragma unroll
+            for (int b = 0; b < EPT; ++b) if (key[b]) sink(key[b]);
+        });
+#pragma unroll
+        for (int b = 0; b < EPT; ++b) if (key[b] && !(key[b] > thr)) blocked |= 1u << b;
+    }
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) if ((blocked >> b) & 1u) atomicOr(&acc_w[X.e[b] >> kCellBits], FLAG_BLOCKED);
+}
+
 // D2: budgets of the reverse delete (per cell: keep at least one IN point; per row: at most cov - need removals).
 // Reads the row's IN list written by the D1 sweep just before (every entry is IN or CAND now).
 __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, unsigned long long* keytab, BlockScratch& S) {
@@ -1349,6 +1404,9 @@ __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, 
     const float* gain_w = P.gain + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
+    if (n <= kThreads) { row_d2_regs<1>(P, D, n, src, need, tab, keytab, S); return; }
+    if (n <= 2 * kThreads) { row_d2_regs<2>(P, D, n, src, need, tab, keytab, S); return; }
+    if (n <= 4 * kThreads) { row_d2_regs<4>(P, D, n, src, need, tab, keytab, S); return; }
     for (int i = threadIdx.x; i < n; i += kThreads) {           // lazy zeroing: only the cells this list touches
         const unsigned cell = src[i] & kCellCov;
         if (cell != kCellCov) { tab[cell] = 0u; keytab[cell] = 0ull; }
