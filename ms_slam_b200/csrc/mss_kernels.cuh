@@ -396,7 +396,7 @@ __device__ __forceinline__ void load_row(RowRegs<EPT>& X, const uint32_t* __rest
 // coalesced or shared memory.  A map point becomes a variable exactly when its counters are non-zero after W1, so W2 can
 // derive the state array with coalesced stores; valid slots outside the grid only leave a "seen" mark for nMax.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, unsigned* tab, BlockScratch& S) {
+__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, int par, unsigned* tab, BlockScratch& S) {
     const int R = D.row_base + k;
     const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
     if (beg < 0 || end < beg || end > D.F) {
@@ -436,20 +436,26 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
 #pragma unroll
         for (int b = 0; b < kEpt; ++b) if (e[b] != kEntInvalid) tab[e[b] & kCellCov] = 0u;
         __syncthreads();
-        int nz = 0, ncell = 0, z = 0;
+        int nz = 0, ncell = 0;
         unsigned m[kEpt];
 #pragma unroll
         for (int b = 0; b < kEpt; ++b) {
             const bool v = e[b] != kEntInvalid;
-            if (v) { ++nz; if (atomicAdd(&tab[e[b] & kCellCov], 1u) == 0u) ++ncell; }
+            if (v && atomicAdd(&tab[e[b] & kCellCov], 1u) == 0u) ++ncell;
             m[b] = __ballot_sync(0xFFFFFFFFu, v);
         }
-        block_sum3(S, nz, ncell, z);                                    // barriers publish tab
         int wcnt = 0;
 #pragma unroll
         for (int b = 0; b < kEpt; ++b) wcnt += __popc(m[b]);
-        int total;
-        int pos = warp_excl_scan(S, wcnt, total);
+        ncell = __reduce_add_sync(0xFFFFFFFFu, ncell);
+        // one exchange for the row totals and the warps' write offsets; the scratch is double-buffered by row parity, so
+        // the only other barriers of a row are the one after the lazy zeroing and the caller's
+        if (lane == 0) { S.pred[par][0][wid] = wcnt; S.pred[par][1][wid] = ncell; }
+        __syncthreads();                                                // publishes the cell table and the partial sums
+        int pos = 0;
+        ncell = 0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) { if (q < wid) pos += S.pred[par][0][q]; nz += S.pred[par][0][q]; ncell += S.pred[par][1][q]; }
         const bool critr = defi && P.N >= nz;
         const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -2035,7 +2041,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
                 if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
             }
         }
-        w1_build_row(P, D, ws, k, tab, S);
+        w1_build_row(P, D, ws, k, (k / G.ncta) & 1, tab, S);
         __syncthreads();
     }
     if (!group_sync(P, G)) return false;
