@@ -285,9 +285,9 @@ def main():
             cv[w] = d.c_view()
             cr[w].keep_bits, cr[w].kf_cov, cr[w].kf_slack = d.d_keep, d.d_cov, d.d_slack
         else:
+            # a window of another rank: its bitmask arrives in the all-gathered device buffer; no host array is asked for
+            # in this arm (results stay in HBM like the inputs), only the header (status, counters) comes back
             cv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
-            host_keep[w] = np.zeros(words, np.uint32)
-            cr[w].keep_bits = host_keep[w].ctypes.data
     # ---- host arm (e2e): pinned views + pinned results --------------------------------------------------------------------
     pins = []
     hv = (E.mss_window_view * nwin)()

@@ -68,6 +68,22 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
 
+// device-resident result arrays are filled by one small kernel (one CTA per window) instead of three copies per window
+struct ResCopy {
+    const uint32_t* slot;
+    uint32_t* keep;
+    int32_t* cov;
+    int32_t* slack;
+    int words_keep, rows;
+};
+__global__ void scatter_results_kernel(const ResCopy* rc) {
+    const ResCopy r = rc[blockIdx.x];
+    const uint32_t* src = r.slot + mss::kHdrWords;
+    if (r.keep) for (int i = threadIdx.x; i < r.words_keep; i += blockDim.x) r.keep[i] = src[i];
+    if (r.cov) for (int i = threadIdx.x; i < r.rows; i += blockDim.x) r.cov[i] = (int32_t)src[r.words_keep + i];
+    if (r.slack) for (int i = threadIdx.x; i < r.rows; i += blockDim.x) r.slack[i] = (int32_t)src[r.words_keep + r.rows + i];
+}
+
 struct mss_handle {
     mss_config cfg{};
     int device = 0;
@@ -291,6 +307,12 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     sync_words += align_up((size_t)std::max(nl, 1), 32);
     int grid = chunks[0].grid;
 
+    // result scatter table (device-resident result arrays), appended to the descriptor blob
+    int n_dev_res = 0;
+    for (int w = 0; w < nwin; ++w)
+        if (views[w].memory == MSS_MEM_DEVICE && (results[w].keep_bits || results[w].kf_cov || results[w].kf_slack)) ++n_dev_res;
+    const size_t off_res = meta_bytes;
+    meta_bytes += align_up((size_t)std::max(n_dev_res, 1) * sizeof(ResCopy), 16);
     int rc;
     if ((rc = ensure(h, h->meta, meta_bytes))) return rc;
     if ((rc = ensure(h, h->ws, (size_t)std::max(nl, 1)))) return rc;
@@ -366,6 +388,16 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         for (int i = 0; i < ch.count; ++i) h_gwin[i] = ch.order[i];
     }
     // descriptors first, on the compute stream (the kernel needs them at once)
+    {
+        ResCopy* hr = reinterpret_cast<ResCopy*>(h->h_meta + off_res);
+        int q = 0;
+        for (int w = 0; w < nwin; ++w) {
+            const mss_result& r = results[w];
+            if (views[w].memory != MSS_MEM_DEVICE || !(r.keep_bits || r.kf_cov || r.kf_slack)) continue;
+            const SlotLayout sl = slot_of(views[w]);
+            hr[q++] = ResCopy{h->out.p + out_off[w], r.keep_bits, r.kf_cov, r.kf_slack, sl.words_keep, sl.rows};
+        }
+    }
     MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
     h2d += (int64_t)meta_bytes;
     MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
@@ -468,20 +500,51 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         if (nrc != 0) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(nrc); return MSS_E_NCCL; }
     }
     // ---- hand-back ------------------------------------------------------------------------------------------------------
-    MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
+    // Only what the caller asked for crosses PCIe: the whole slot of a window whose result arrays are host buffers, the
+    // 64-byte header (status + counters) of every other window (device-resident results, or windows of other ranks the
+    // caller did not ask arrays for -- their bitmasks stay in the all-gathered device buffer).
+    int64_t d2h = 0;
+    {
+        int n_full = 0;
+        bool uniform = true;
+        for (int w = 0; w < nwin; ++w) {
+            const mss_result& r = results[w];
+            if (views[w].memory != MSS_MEM_DEVICE && (r.keep_bits || r.kf_cov || r.kf_slack)) ++n_full;
+            if (w > 0 && out_off[w] - out_off[w - 1] != out_off[1] - out_off[0]) uniform = false;
+        }
+        if (nranks > 1) uniform = true;                        // rank-major slots with one stride
+        const size_t stride = nranks > 1 ? (size_t)slot_stride : (nwin > 1 ? (size_t)(out_off[1] - out_off[0]) : (size_t)slot_of(views[0]).total);
+        const size_t nslots = nranks > 1 ? (size_t)nranks * spr : (size_t)nwin;
+        auto wants_full = [&](int w) {
+            const mss_result& r = results[w];
+            return views[w].memory != MSS_MEM_DEVICE && (r.keep_bits || r.kf_cov || r.kf_slack);
+        };
+        if (n_full == nwin) {
+            MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
+            d2h += (int64_t)(out_words * 4);
+        } else {
+            if (uniform) {      // headers of all slots in one strided copy
+                MSS_CUDA(h, cudaMemcpy2DAsync(h->h_out, stride * 4, h->out.p, stride * 4, (size_t)mss::kHdrWords * 4, nslots,
+                                              cudaMemcpyDeviceToHost, h->stream));
+                d2h += (int64_t)(nslots * mss::kHdrWords * 4);
+            }
+            for (int w = 0; w < nwin; ++w) {
+                const bool full = wants_full(w);
+                if (!full && uniform) continue;
+                const size_t words = full ? (size_t)slot_of(views[w]).total : (size_t)mss::kHdrWords;
+                MSS_CUDA(h, cudaMemcpyAsync(h->h_out + out_off[w], h->out.p + out_off[w], words * 4, cudaMemcpyDeviceToHost, h->stream));
+                d2h += (int64_t)(words * 4);
+            }
+        }
+    }
     for (int c = 0; c < nchunks; ++c)
         MSS_CUDA(h, cudaMemcpyAsync(&h->h_ctrl[c], h->sync.p + chunks[c].sync_off, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
-    int64_t d2h = (int64_t)(out_words * 4 + (size_t)nchunks * sizeof(Ctrl));
+    d2h += (int64_t)((size_t)nchunks * sizeof(Ctrl));
     bool aborted = false;
-    for (int w = 0; w < nwin; ++w) {       // device-resident result buffers are filled device-to-device
-        const mss_window_view& v = views[w];
-        mss_result& r = results[w];
-        if (v.memory != MSS_MEM_DEVICE) continue;
-        const SlotLayout s = slot_of(v);
-        const uint32_t* slot = h->out.p + out_off[w];
-        if (r.keep_bits && s.words_keep) MSS_CUDA(h, cudaMemcpyAsync(r.keep_bits, slot + mss::kHdrWords, (size_t)s.words_keep * 4, cudaMemcpyDeviceToDevice, h->stream));
-        if (r.kf_cov && s.rows) MSS_CUDA(h, cudaMemcpyAsync(r.kf_cov, slot + mss::kHdrWords + s.words_keep, (size_t)s.rows * 4, cudaMemcpyDeviceToDevice, h->stream));
-        if (r.kf_slack && s.rows) MSS_CUDA(h, cudaMemcpyAsync(r.kf_slack, slot + mss::kHdrWords + s.words_keep + s.rows, (size_t)s.rows * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if (n_dev_res > 0) {                   // device-resident result buffers are filled device-to-device, all windows in one launch
+        scatter_results_kernel<<<n_dev_res, 256, 0, h->stream>>>(reinterpret_cast<const ResCopy*>(h->meta.p + off_res));
+        MSS_CUDA(h, cudaGetLastError());
+        h->stats.kernel_launches += 1;
     }
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (gated) MSS_CUDA(h, cudaStreamSynchronize(h->copy_stream));     // (only an aborted launch can finish before its copies)
