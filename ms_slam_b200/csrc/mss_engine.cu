@@ -1,5 +1,6 @@
-// mss_engine.cu -- host side of libmss.so: device arena, batch layout, cooperative launch, result hand-back, NCCL
-// all-gather of the result slots, and the extern "C" entry points declared in include/mss.h.
+// mss_engine.cu -- host side of libmss.so: device arena, batch layout, ONE cooperative launch per call (host views are
+// copied on a second stream while it runs, per-window ready flags), result hand-back (only what was asked for crosses
+// PCIe), NCCL all-gather of the result slots, connected components, and the extern "C" entry points of include/mss.h.
 //
 // Replaces the GUROBI environment/model objects of the reference (GRBEnv mGRBEnv, GRBModel model:
 // /root/reference/include/MapSparsification.h:59, /root/reference/src/MapSparsification.cc:6,20,61,153-157).

@@ -15,15 +15,22 @@
 //
 // Selection algorithm, per variable state FREE / IN / OUT (oracle/emulate.py restates it on the CPU, bit for bit):
 //   PROP   exact dominance to a fixed point: ub_p <= 0 -> OUT, lb_p >= 0 -> IN
-//   GREEDY conflict-free step: a FREE point is taken iff it is the best candidate of every uncovered cell it lies in
-//          and within the top-deficit candidates of every deficient row it lies in
+//   GREEDY when PROP stops, or stalls (a round decides fewer than 1/stall_den of the undecided points): a FREE point is
+//          taken iff it has positive gain and is the best candidate of every uncovered cell it lies in and within the
+//          top-deficit candidates of every deficient row it lies in, or a deficient row nominates it
 //   DROP   budgeted reverse delete; per-cell / per-row budgets make the summed deltas exact
 // Every decision is made from integer counters (integer atomics) and keys with a unique tie-break, so the result does not
 // depend on scheduling, on the group partition or on the order of entries inside a list.
 //
 // Work per round is proportional to the UNDECIDED part of the window: round 1 is fused into the build (W1/W4), round 2
 // streams the CSR once, and from then on every row keeps a compacted "live list" of its FREE entries (cell field
-// rewritten to kCellCov once the cell is covered) plus a running row coverage, so later rounds touch only those.
+// rewritten to kCellCov once the cell is covered) plus a running row coverage, so later rounds touch only those.  The
+// reverse delete sweeps the CSR once, leaves each row's IN list in the (then dead) live-list segment and reads only
+// those afterwards.
+//
+// Views come in two layouts (include/mss.h mss_layout): SoA arrays, or the packed transport form (u32 slots, u16 nObs,
+// outside observations as a flat pair list) for which W2 / W4 are flat passes without shared staging.  Host views may
+// still be in flight when the kernel starts: a group waits for the ready flag of the window it draws (Params::ready).
 #pragma once
 
 #include <cuda_runtime.h>

@@ -64,3 +64,83 @@ def test_save_load_roundtrip(tmp_path):
     for name in WindowView._ARRAYS:
         assert np.array_equal(getattr(v, name), getattr(w, name))
     assert w.input_bytes() == v.input_bytes()
+
+
+# ---- transport forms (what FlattenWindow emits / bench.py ships) -------------------------------------------------------
+def _unpack(pv):
+    """PackedView -> (kf, mp, cell) triples of the valid slots and (mp, outside kf) pairs"""
+    kf = np.repeat(np.arange(pv.K), np.diff(pv.feat_ptr))
+    ok = pv.slots != 0xFFFFFFFF
+    cell = (pv.slots & 0xFFF).astype(np.int64)
+    cell = np.where(cell == 0xFFF, CELL_NONE, cell)
+    return (kf[ok], (pv.slots >> 12).astype(np.int64)[ok], cell[ok]), ((pv.obs_pairs >> 12).astype(np.int64), (pv.obs_pairs & 0xFFF).astype(np.int64))
+
+
+@pytest.mark.parametrize("name,seed", [("c1", 0), ("live", 1), ("c3", 0)])
+def test_packed_view_carries_the_same_window(name, seed):
+    from ms_slam_b200 import pack_view
+    v, _ = msgen.make_config(name, seed)
+    valid = v.feat_mp >= 0
+    kf = np.repeat(np.arange(v.K), np.diff(v.feat_ptr))
+    want = sorted(zip(kf[valid].tolist(), v.feat_mp[valid].tolist(), v.feat_cell[valid].tolist()))
+    owner = np.repeat(np.arange(v.M), np.diff(v.mp_obs_ptr))
+    out = v.mp_obs_kf >= v.K
+    want_pairs = sorted(zip(owner[out].tolist(), (v.mp_obs_kf[out] - v.K).tolist()))
+    for pv in (pack_view(v), pack_view(v.compact()), pack_view(v.compact(), sort_slots=True)):
+        (k, m, c), (pm, pj) = _unpack(pv)
+        assert sorted(zip(k.tolist(), m.tolist(), c.tolist())) == want
+        assert sorted(zip(pm.tolist(), pj.tolist())) == want_pairs
+        assert np.array_equal(pv.mp_nobs16, v.mp_nobs) and np.array_equal(pv.okf_total, v.okf_total)
+    srt = pack_view(v.compact(), sort_slots=True)
+    for k in range(srt.K):                                   # sorted inside every keyframe, keyframe boundaries untouched
+        seg = srt.slots[srt.feat_ptr[k]:srt.feat_ptr[k + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) >= 0)
+    assert pack_view(v.compact()).input_bytes() < 0.62 * v.compact().input_bytes()
+
+
+def test_packed_view_range_checks():
+    from ms_slam_b200 import pack_view
+    v = make_view(1, [[(0, 0)]], [70000])
+    with pytest.raises(ValueError):
+        pack_view(v)
+
+
+@pytest.mark.parametrize("name,seed", [("c1", 1), ("live", 2)])
+def test_discovery_order_is_a_renumbering(name, seed):
+    v, _ = msgen.make_config(name, seed)
+    d = v.compact().discovery_order()
+    d.validate()
+    perm = d.meta["mp_perm"]
+    assert np.array_equal(np.sort(perm), np.arange(v.M))
+    assert np.array_equal(d.mp_nobs, v.mp_nobs[perm])
+    # first appearances (keyframes in window order, slots in slot order) are 0, 1, 2, ...
+    seen = d.feat_mp[d.feat_mp >= 0]
+    _, first = np.unique(seen, return_index=True)
+    assert np.all(np.diff(first) > 0)
+    # same incidences after mapping back
+    kf = np.repeat(np.arange(d.K), np.diff(d.feat_ptr))
+    a = sorted(zip(kf.tolist(), perm[d.feat_mp].tolist(), d.feat_cell.tolist()))
+    c = v.compact()
+    kfc = np.repeat(np.arange(c.K), np.diff(c.feat_ptr))
+    assert a == sorted(zip(kfc.tolist(), c.feat_mp.tolist(), c.feat_cell.tolist()))
+
+
+def test_merge_views_is_block_diagonal():
+    from ms_slam_b200 import merge_views
+    parts = [msgen.make_config("c1", 7)[0], msgen.make_config("live", 9, M=1500, H=20)[0]]
+    for inter in (True, False):
+        w = merge_views(parts, interleave=inter)
+        w.validate()
+        assert (w.K, w.H, w.M, w.F, w.O) == tuple(sum(getattr(p, a) for p in parts) for a in ("K", "H", "M", "F", "O"))
+        # no slot of a keyframe of part 0 holds a map point of part 1 and vice versa
+        kf = np.repeat(np.arange(w.K), np.diff(w.feat_ptr))
+        ok = w.feat_mp >= 0
+        part_of_mp = (w.feat_mp[ok] >= parts[0].M).astype(int)
+        nslots = np.diff(w.feat_ptr)
+        # a keyframe belongs to the part whose slot count it has at its position in the interleaving / concatenation
+        kf_part = np.zeros(w.K, int)
+        for k in range(w.K):
+            seg = w.feat_mp[w.feat_ptr[k]:w.feat_ptr[k + 1]]
+            seg = seg[seg >= 0]
+            kf_part[k] = int(seg[0] >= parts[0].M) if seg.size else 0
+        assert np.array_equal(part_of_mp, kf_part[kf[ok]])
