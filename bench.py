@@ -228,7 +228,8 @@ def main():
                     help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
                          "(mnIndexForSparsification, MapSparsification.cc:91-99) or as msgen draws them (random)")
     ap.add_argument("--unsorted-slots", action="store_true", help="packed layout: keep the slots of a keyframe in slot order")
-    ap.add_argument("--layout", default="packed", choices=["packed", "soa"], help="transport layout of the views (include/mss.h mss_layout)")
+    ap.add_argument("--layout", default="packed16", choices=["packed16", "packed", "soa"],
+                    help="transport layout of the views (include/mss.h mss_layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -268,6 +269,8 @@ def main():
         def make(w):
             v = msgen.make_config(args.workload, seed=w)[0].compact()
             v = v.discovery_order() if args.order == "discovery" else v
+            if args.layout == "packed16":
+                return pack_view(v, tokens16=True)
             return pack_view(v, sort_slots=not args.unsorted_slots) if args.layout == "packed" else v
         views = dict(zip(mine, pool.map(make, mine)))
     K, H, M = cfg["K"], cfg["H"], cfg["M"]
@@ -315,9 +318,10 @@ def main():
     for w in range(nwin):
         if w in views and not args.no_e2e:
             v = views[w]
-            if args.layout == "packed":
+            if args.layout in ("packed", "packed16"):
                 hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
-                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]))
+                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]),
+                                        tokens16=args.layout == "packed16")
             else:
                 hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
                                           *pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr, v.mp_obs_kf, v.okf_total]))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MSS_VERSION 120            /* 0.1.2: packed transport layout (slots + pair list) */
+#define MSS_VERSION 130            /* 0.1.3: packed transport layouts (u32 slots / u16 tokens + pair list), components */
 
 #define MSS_GRID_COLS 64           /* FRAME_GRID_COLS, /root/reference/include/Frame.h:45 */
 #define MSS_GRID_ROWS 48           /* FRAME_GRID_ROWS, /root/reference/include/Frame.h:44 */
@@ -51,7 +51,8 @@ typedef enum mss_memory {
  * PCIe every call (about 0.6x the bytes): FlattenWindow can emit either at the same host cost. */
 typedef enum mss_layout {
     MSS_LAYOUT_SOA = 0,      /* feat_mp i32 + feat_cell u16, mp_nobs i32, mp_obs_kf i32 */
-    MSS_LAYOUT_PACKED = 1    /* slots u32 = (map point << 12) | cell, mp_nobs16 u16, obs_pairs u32 = (map point << 12) | outside kf */
+    MSS_LAYOUT_PACKED = 1,   /* slots u32 = (map point << 12) | cell, mp_nobs16 u16, obs_pairs u32 = (map point << 12) | outside kf */
+    MSS_LAYOUT_PACKED16 = 2  /* as PACKED, but the slots of a keyframe are sorted by map-point index and delta-coded as u16 tokens */
 } mss_layout;
 #define MSS_SLOT_CELL_NONE 0xFFFu      /* packed slot: keypoint outside the grid (MSS_CELL_NONE of the SOA form) */
 #define MSS_SLOT_EMPTY 0xFFFFFFFFu     /* packed slot: empty slot / bad map point (feat_mp == -1 of the SOA form) */
@@ -103,6 +104,12 @@ typedef struct mss_window_view {
                                         MSS_SLOT_EMPTY = empty slot.  The order of the slots inside a keyframe is free (the
                                         result does not depend on it); sorted by value is the fastest */
     const uint16_t* mp_nobs16; /* [M]   MapPoint::Observations() */
+    /* ---- MSS_LAYOUT_PACKED16: slots16 replaces slots; F counts TOKENS and feat_ptr holds token ranges.  The slots of a
+     *      keyframe are sorted by map-point table index; a running index starts at 0 in every keyframe.  Token t:
+     *        (t >> 12) < 15 : a slot: index += t >> 12; cell = t & 0xFFF (MSS_SLOT_CELL_NONE = not in mGrid)
+     *        (t >> 12) == 15: no slot: index += 15 * ((t & 0xFFF) + 1)
+     *      (about 1.03 tokens per slot for windows numbered in discovery order: 2.06 bytes per slot instead of 4) ---- */
+    const uint16_t* slots16;   /* [F]   tokens */
     const uint32_t* obs_pairs; /* [O]   observations of the window's map points by OUTSIDE keyframes only, in any order:
                                         (map-point table index << 12) | j, j = 0..H-1 the outside keyframe (KF-table index K + j) */
 } mss_window_view;

@@ -57,6 +57,45 @@ __global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, un
     for (int k = blockIdx.x; k < D.K; k += gridDim.x) {
         const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
         if (beg < 0 || end < beg || end > D.F) { if (threadIdx.x == 0) atomicOr(err, ERR_PTR); continue; }
+        if (D.packed == 2) {
+            // 16-bit tokens: the map-point index is a running sum over the keyframe's tokens (block scan per chunk)
+            __shared__ int s_w[32];
+            __shared__ int s_carry;
+            const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp);
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry = 0;
+            __syncthreads();
+            for (int base = beg; base < end; base += blockDim.x) {
+                const int i = base + (int)threadIdx.x;
+                int adv = 0;
+                bool slot = false;
+                unsigned c = kCellNone;
+                if (i < end) adv = tok_decode(__ldg(tk + i), slot, c);
+                int x = adv;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += y;
+                }
+                if (lane == 31) s_w[wid] = x;
+                __syncthreads();
+                int woff = 0, tot = 0;
+                for (int q = 0; q < nw; ++q) { const int t = s_w[q]; if (q < wid) woff += t; tot += t; }
+                const int mp = s_carry + woff + x;
+                __syncthreads();
+                if (threadIdx.x == 0) s_carry += tot;
+                __syncthreads();
+                if (!slot) continue;
+                if (mp >= D.M) { atomicOr(err, ERR_INDEX); continue; }
+                nmax = max(nmax, ld_nobs(D, mp));
+                if (c == kCellNone) continue;
+                if (c >= (unsigned)kCells) { atomicOr(err, ERR_INDEX); continue; }
+                isvar[mp] = 1;
+                cc_union(parent, k, R + mp);
+            }
+            continue;
+        }
         for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) {
             int mp;
             unsigned c;

@@ -167,6 +167,12 @@ int ensure_pinned(mss_handle* h, void** p, size_t* cap, size_t bytes) {
 template <class T>
 void release(DevBuf<T>& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
+inline const void* slots_ptr(const mss_window_view& v) {
+    return v.layout == MSS_LAYOUT_PACKED16 ? (const void*)v.slots16 : v.layout == MSS_LAYOUT_PACKED ? (const void*)v.slots : (const void*)v.feat_mp;
+}
+inline size_t slots_bytes(const mss_window_view& v) { return (size_t)v.F * (v.layout == MSS_LAYOUT_PACKED16 ? 2 : 4); }
+inline int packed_code(const mss_window_view& v) { return v.layout == MSS_LAYOUT_PACKED16 ? 2 : v.layout == MSS_LAYOUT_PACKED ? 1 : 0; }
+
 struct SlotLayout { int words_keep, rows, total; };
 inline SlotLayout slot_of(const mss_window_view& v) {
     SlotLayout s;
@@ -201,12 +207,13 @@ int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
     if (!owned) return MSS_OK;
     if (v.F < 0 || v.O < 0) { h->err = "view: negative F/O"; return MSS_E_BADARG; }
     if (v.memory != MSS_MEM_HOST && v.memory != MSS_MEM_DEVICE) { h->err = "view: bad memory kind"; return MSS_E_BADARG; }
-    if (v.layout != MSS_LAYOUT_SOA && v.layout != MSS_LAYOUT_PACKED) { h->err = "view: bad layout"; return MSS_E_BADARG; }
-    const bool pkv = v.layout == MSS_LAYOUT_PACKED;
+    if (v.layout != MSS_LAYOUT_SOA && v.layout != MSS_LAYOUT_PACKED && v.layout != MSS_LAYOUT_PACKED16) { h->err = "view: bad layout"; return MSS_E_BADARG; }
+    const bool pkv = v.layout != MSS_LAYOUT_SOA;
+    const void* pk_slots = v.layout == MSS_LAYOUT_PACKED16 ? (const void*)v.slots16 : (const void*)v.slots;
     if (!v.feat_ptr || (!pkv && !v.mp_obs_ptr)) { h->err = "view: feat_ptr / mp_obs_ptr is NULL"; return MSS_E_BADARG; }
     if (pkv && v.H > 4095) { h->err = "view: more than 4095 outside keyframes in the packed layout (use MSS_LAYOUT_SOA)"; return MSS_E_BADARG; }
     const bool null_arr = pkv
-        ? ((v.F > 0 && !v.slots) || (v.M > 0 && !v.mp_nobs16) || (v.O > 0 && !v.obs_pairs))
+        ? ((v.F > 0 && !pk_slots) || (v.M > 0 && !v.mp_nobs16) || (v.O > 0 && !v.obs_pairs))
         : ((v.F > 0 && (!v.feat_mp || !v.feat_cell)) || (v.M > 0 && !v.mp_nobs) || (v.O > 0 && !v.mp_obs_kf));
     if (null_arr || (v.H > 0 && !v.okf_total)) { h->err = "view: NULL array with non-zero size"; return MSS_E_BADARG; }
     if (v.memory == MSS_MEM_HOST) {
@@ -253,8 +260,8 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         if (v.K + v.H > mss::kMaxWindowRows) { h->err = "view: more than 65535 keyframe rows in one window"; return MSS_E_BADARG; }
         Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ftot += v.F; Otot += v.O;
         if (v.memory == MSS_MEM_HOST) {
-            const bool pk = v.layout == MSS_LAYOUT_PACKED;
-            stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up((size_t)v.F * 4, 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
+            const bool pk = v.layout != MSS_LAYOUT_SOA;
+            stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up(slots_bytes(v), 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
                            align_up((size_t)v.M * (pk ? 2 : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
                            align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16);
         }
@@ -352,19 +359,19 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         const mss_window_view& v = views[local[i]];
         WinDesc d;
         memset(&d, 0, sizeof(d));
-        const bool pk = v.layout == MSS_LAYOUT_PACKED;
-        d.packed = pk ? 1 : 0;
+        const bool pk = v.layout != MSS_LAYOUT_SOA;
+        d.packed = packed_code(v);
         d.n_max_floor = v.n_max_floor;
         if (v.memory == MSS_MEM_HOST) {
             d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
-            d.feat_mp = (const int*)stage(pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
+            d.feat_mp = (const int*)stage(slots_ptr(v), slots_bytes(v));
             d.feat_cell = pk ? nullptr : (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
             d.mp_nobs = (const int*)stage(pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
             d.mp_obs_ptr = pk ? nullptr : (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
             d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
             d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
         } else if (pk) {
-            d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)v.slots; d.feat_cell = nullptr; d.mp_nobs = (const int*)v.mp_nobs16;
+            d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)slots_ptr(v); d.feat_cell = nullptr; d.mp_nobs = (const int*)v.mp_nobs16;
             d.mp_obs_ptr = nullptr; d.mp_obs_kf = (const int*)v.obs_pairs; d.okf_total = v.okf_total;
         } else {
             d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
@@ -411,15 +418,15 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         const mss_window_view& v = views[local[i]];
         if (v.memory != MSS_MEM_HOST) return;
         const WinDesc& d = hd[i];
-        const bool pk = v.layout == MSS_LAYOUT_PACKED;
+        const bool pk = v.layout != MSS_LAYOUT_SOA;
         auto put = [&](const void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream); };
         // a view whose arrays lie back to back on the host, in staging order and each at the next 16-byte boundary (one
         // pinned blob per window, as FlattenWindow lays them out), travels with ONE copy
         {
-            const void* src[7] = {v.feat_ptr, pk ? (const void*)v.slots : (const void*)v.feat_mp, pk ? nullptr : (const void*)v.feat_cell,
+            const void* src[7] = {v.feat_ptr, slots_ptr(v), pk ? nullptr : (const void*)v.feat_cell,
                                   pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
                                   pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
-            const size_t len[7] = {(size_t)(v.K + 1) * 4, (size_t)v.F * 4, pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+            const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
                                    pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
             const uint8_t* base = static_cast<const uint8_t*>(src[0]);
             size_t off = 0, end = 0;
@@ -432,7 +439,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
             if (blob) { put(d.feat_ptr, base, end); return; }
         }
         put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
-        put(d.feat_mp, pk ? (const void*)v.slots : (const void*)v.feat_mp, (size_t)v.F * 4);
+        put(d.feat_mp, slots_ptr(v), slots_bytes(v));
         if (!pk) put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
         put(d.mp_nobs, pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
         if (!pk) put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
@@ -723,18 +730,18 @@ int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_labe
     if (rc != MSS_OK) return rc;
     if (v.M > mss::kMaxWindowMps || v.K + v.H > mss::kMaxWindowRows) { h->err = "view: window too large"; return MSS_E_BADARG; }
     MSS_CUDA(h, cudaSetDevice(h->device));
-    const bool pk = v.layout == MSS_LAYOUT_PACKED, host = v.memory == MSS_MEM_HOST;
+    const bool pk = v.layout != MSS_LAYOUT_SOA, host = v.memory == MSS_MEM_HOST;
     const int R = v.K + v.H, M = v.M;
     if ((rc = ensure(h, h->cc, (size_t)2 * (R + M) + 16))) return rc;
     if ((rc = ensure(h, h->seen, (size_t)M + 16))) return rc;
     WinDesc d;
     memset(&d, 0, sizeof(d));
-    d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O; d.packed = pk ? 1 : 0;
+    d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O; d.packed = packed_code(v);
     if (host) {
-        const void* src[7] = {v.feat_ptr, pk ? (const void*)v.slots : (const void*)v.feat_mp, pk ? nullptr : (const void*)v.feat_cell,
+        const void* src[7] = {v.feat_ptr, slots_ptr(v), pk ? nullptr : (const void*)v.feat_cell,
                               pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
                               pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
-        const size_t len[7] = {(size_t)(v.K + 1) * 4, (size_t)v.F * 4, pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+        const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
                                pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
         size_t total = 0;
         for (int a = 0; a < 7; ++a) total += align_up(len[a], 16);
@@ -750,7 +757,7 @@ int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_labe
         d.mp_nobs = (const int*)dst[3]; d.mp_obs_ptr = pk ? nullptr : (const int*)dst[4]; d.mp_obs_kf = (const int*)dst[5];
         d.okf_total = (const int*)dst[6];
     } else if (pk) {
-        d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)v.slots; d.mp_nobs = (const int*)v.mp_nobs16; d.mp_obs_kf = (const int*)v.obs_pairs;
+        d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)slots_ptr(v); d.mp_nobs = (const int*)v.mp_nobs16; d.mp_obs_kf = (const int*)v.obs_pairs;
         d.okf_total = v.okf_total;
     } else {
         d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;

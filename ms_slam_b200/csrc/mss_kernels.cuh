@@ -81,8 +81,9 @@ struct WinDesc {
     int obs_base;    // first entry of this window's outside rows in ent[] / live[] (after all keyframe segments)
     int var_base;    // global variable index of map point 0 (multiple of kVarTile)
     int out_off;     // u32 word offset of this window's result slot
-    int packed;      // MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs is a u16 array, mp_obs_kf holds
+    int packed;      // 1 = MSS_LAYOUT_PACKED: feat_mp holds u32 (map point << 12 | cell) slots, mp_nobs is a u16 array, mp_obs_kf holds
                      // the outside observations as u32 pairs (map point << 12 | outside keyframe), mp_obs_ptr is unused
+                     // 2 = MSS_LAYOUT_PACKED16: as 1, but feat_mp holds u16 tokens (delta of the map-point index << 12 | cell)
     int n_max_floor; // nMax is at least this (a component of a larger window keeps the window-wide nMax)
     int pad_[1];
 };
@@ -195,7 +196,7 @@ struct BlockScratch {
     unsigned short rowq[kThreads];
     int rown[kThreads];
     int rowoff[kThreads];
-    int pred[2][2][kWarps];  // parity-buffered partial sums / warp counts of the row phases (saves the protective barriers)
+    int pred[2][3][kWarps];  // parity-buffered partial sums / warp counts of the row phases (saves the protective barriers)
     int pscan[2][kWarps];
     int qn[2];
     unsigned rows_live, maxlive;
@@ -359,7 +360,18 @@ __device__ __forceinline__ int ld_nobs(const WinDesc& D, int mp) {
     return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : __ldg(D.mp_nobs + mp);
 }
 __device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) { return __ldg(D.mp_obs_kf + o); }      // SoA layout only
-// slot i of the view -> (map point or -1, cell or kCellNone)
+// MSS_LAYOUT_PACKED16: the slots of a keyframe, sorted by map-point index, as 16-bit tokens.  d = t >> 12, low = t & 0xFFF:
+//   d < 15  a slot: map point = previous map point + d (0 at the start of the keyframe), cell = low (0xFFF = not in mGrid)
+//   d == 15 no slot: the running map-point index advances by 15 * (low + 1)
+// tok_decode returns the advance of the running index; slot / cell describe the token
+__device__ __forceinline__ int tok_decode(unsigned t, bool& slot, unsigned& cell) {
+    const unsigned d = t >> 12, low = t & 0xFFFu;
+    slot = d < 15u;
+    cell = low == 0xFFFu ? kCellNone : low;
+    return slot ? (int)d : 15 * (int)(low + 1u);
+}
+
+// slot i of the view -> (map point or -1, cell or kCellNone)  [SoA and MSS_LAYOUT_PACKED; tokens are decoded by their readers]
 __device__ __forceinline__ void ld_slot(const WinDesc& D, int i, int& mp, unsigned& c) {
     if (D.packed) {
         const uint32_t s = __ldg(reinterpret_cast<const uint32_t*>(D.feat_mp) + i);
@@ -420,24 +432,57 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
     uint8_t* seen_w = P.seen + D.var_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool defi = P.N > 0;
+    const bool tok = D.packed == 2;
     unsigned err = 0;
     if (nslots <= kRegRow) {
         // slots in registers: warp w owns a contiguous chunk, lane-strided (coalesced loads, list order = slot order)
         const int per = (((nslots + kWarps - 1) / kWarps) + 31) & ~31;
         const int nb = per >> 5;
         uint32_t e[kEpt];
+        int pre[kEpt];                  // tokens: inclusive prefix of the index advances inside this warp's chunk
+        unsigned offgrid = 0u;          // tokens: bit b = my token of chunk b is a valid slot outside the grid
+        int chunk_total = 0;
+        if (tok) {
+            const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp) + beg;
+            int run = 0;
 #pragma unroll
-        for (int b = 0; b < kEpt; ++b) {
-            const int idx = wid * per + b * 32 + lane;
-            int mp = -1;
-            unsigned c = kCellNone;
-            if (b < nb && idx < nslots) ld_slot(D, beg + idx, mp, c);
-            e[b] = kEntInvalid;
-            if (mp < -1 || mp >= D.M) err |= ERR_INDEX;
-            else if (mp >= 0) {
-                if (c == kCellNone) seen_w[mp] = 1;                             // valid slot, not in mGrid (MapSparsification.cc:69-75)
-                else if (c >= (unsigned)kCells) err |= ERR_INDEX;
-                else e[b] = ((uint32_t)mp << kCellBits) | c;
+            for (int b = 0; b < kEpt; ++b) {
+                const int idx = wid * per + b * 32 + lane;
+                int adv = 0;
+                bool slot = false;
+                unsigned c = kCellNone;
+                if (b < nb && idx < nslots) adv = tok_decode(__ldg(tk + idx), slot, c);
+                int x = adv;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += y;
+                }
+                pre[b] = run + x;
+                run += __shfl_sync(0xFFFFFFFFu, x, 31);
+                e[b] = kEntInvalid;                                             // provisionally: the cell alone (the map point
+                if (slot) {                                                     // index needs the other warps' totals)
+                    if (c == kCellNone) offgrid |= 1u << b;
+                    else if (c >= (unsigned)kCells) err |= ERR_INDEX;
+                    else e[b] = c;
+                }
+            }
+            chunk_total = run;
+        } else {
+#pragma unroll
+            for (int b = 0; b < kEpt; ++b) {
+                const int idx = wid * per + b * 32 + lane;
+                int mp = -1;
+                unsigned c = kCellNone;
+                if (b < nb && idx < nslots) ld_slot(D, beg + idx, mp, c);
+                e[b] = kEntInvalid;
+                pre[b] = 0;
+                if (mp < -1 || mp >= D.M) err |= ERR_INDEX;
+                else if (mp >= 0) {
+                    if (c == kCellNone) seen_w[mp] = 1;                         // valid slot, not in mGrid (MapSparsification.cc:69-75)
+                    else if (c >= (unsigned)kCells) err |= ERR_INDEX;
+                    else e[b] = ((uint32_t)mp << kCellBits) | c;
+                }
             }
         }
 #pragma unroll
@@ -457,12 +502,27 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
         ncell = __reduce_add_sync(0xFFFFFFFFu, ncell);
         // one exchange for the row totals and the warps' write offsets; the scratch is double-buffered by row parity, so
         // the only other barriers of a row are the one after the lazy zeroing and the caller's
-        if (lane == 0) { S.pred[par][0][wid] = wcnt; S.pred[par][1][wid] = ncell; }
+        if (lane == 0) { S.pred[par][0][wid] = wcnt; S.pred[par][1][wid] = ncell; S.pred[par][2][wid] = chunk_total; }
         __syncthreads();                                                // publishes the cell table and the partial sums
-        int pos = 0;
+        int pos = 0, mp_base = 0;
         ncell = 0;
 #pragma unroll
-        for (int q = 0; q < kWarps; ++q) { if (q < wid) pos += S.pred[par][0][q]; nz += S.pred[par][0][q]; ncell += S.pred[par][1][q]; }
+        for (int q = 0; q < kWarps; ++q) {
+            if (q < wid) { pos += S.pred[par][0][q]; mp_base += S.pred[par][2][q]; }
+            nz += S.pred[par][0][q]; ncell += S.pred[par][1][q];
+        }
+        if (tok) {                                                      // the map-point indices are known now
+#pragma unroll
+            for (int b = 0; b < kEpt; ++b) {
+                const unsigned mp = (unsigned)(mp_base + pre[b]);
+                if (e[b] != kEntInvalid) {
+                    if (mp >= (unsigned)D.M) err |= ERR_INDEX;          // (the window is rejected; index 0 keeps W1 in bounds)
+                    e[b] = ((mp < (unsigned)D.M ? mp : 0u) << kCellBits) | e[b];
+                } else if ((offgrid >> b) & 1u) {
+                    if (mp < (unsigned)D.M) seen_w[mp] = 1; else err |= ERR_INDEX;
+                }
+            }
+        }
         const bool critr = defi && P.N >= nz;
         const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -490,24 +550,44 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
         zero_tab(tab);
         __syncthreads();
         int nz = 0, ncell = 0, z = 0;
+        const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp) + beg;
         for (int i = threadIdx.x; i < nslots; i += kThreads) {
-            int mp;
+            int mp = 0;
             unsigned c;
-            ld_slot(D, beg + i, mp, c);
-            if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
-            if (mp >= D.M) { err |= ERR_INDEX; continue; }
-            if (c == kCellNone) { seen_w[mp] = 1; continue; }
+            if (tok) {                                                  // pass 1 needs the cells only
+                bool slot;
+                tok_decode(__ldg(tk + i), slot, c);
+                if (!slot || c == kCellNone) continue;
+            } else {
+                ld_slot(D, beg + i, mp, c);
+                if (mp < 0) { if (mp < -1) err |= ERR_INDEX; continue; }
+                if (mp >= D.M) { err |= ERR_INDEX; continue; }
+                if (c == kCellNone) { seen_w[mp] = 1; continue; }
+            }
             if (c >= (unsigned)kCells) { err |= ERR_INDEX; continue; }
             ++nz;
             if (atomicAdd(&tab[c], 1u) == 0u) ++ncell;
         }
         block_sum3(S, nz, ncell, z);
         const bool critr = defi && P.N >= nz;
-        int out_base = 0;
+        int out_base = 0, mp_carry = 0;
         for (int base = 0; base < nslots; base += kThreads) {
             const int i = base + (int)threadIdx.x;
             uint32_t e = kEntInvalid;
-            if (i < nslots) {
+            if (tok) {
+                int adv = 0;
+                bool slot = false;
+                unsigned c = kCellNone;
+                if (i < nslots) adv = tok_decode(__ldg(tk + i), slot, c);
+                int tot;
+                const int mp = mp_carry + block_excl_scan(S, adv, tot) + adv;       // running map-point index, token order
+                mp_carry += tot;
+                if (slot) {
+                    if (mp >= D.M) err |= ERR_INDEX;
+                    else if (c == kCellNone) seen_w[mp] = 1;
+                    else if (c < (unsigned)kCells) e = ((uint32_t)mp << kCellBits) | c;
+                }
+            } else if (i < nslots) {
                 int mp;
                 unsigned c;
                 ld_slot(D, beg + i, mp, c);
@@ -2044,7 +2124,12 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         if (k + G.ncta < D.K) {                  // next row of this CTA: pull its slots towards L1 while this one is processed
             const int nb = __ldg(D.feat_ptr + k + G.ncta), ne = __ldg(D.feat_ptr + k + G.ncta + 1);
             if (nb >= 0 && ne <= D.F) {
-                for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
+                if (D.packed == 2) {
+                    const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp);
+                    for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(tk + i);
+                } else {
+                    for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
+                }
                 if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
             }
         }

@@ -78,13 +78,34 @@ void WindowSnapshot::Blob::Reserve(size_t bytes) {
 }
 
 void WindowSnapshot::Pack() {
+    // MSS_LAYOUT_PACKED16 (include/mss.h): valid slots only, sorted by map-point index inside every keyframe (the order of
+    // the slots inside a keyframe carries no meaning for the model; sorted, the entries a warp handles touch neighbouring
+    // map points) and delta-coded as 16-bit tokens; u16 nObs; the outside observations as one pair list.
     packed = false;
     const size_t M = mp_nobs.size(), F = feat_mp.size(), O = mp_obs_kf.size();
     if (M > (1u << 20) || H > 4095) return;
     for (int32_t n : mp_nobs) if (n < 0 || n > 65535) return;
     auto up = [](size_t x) { return (x + 15) / 16 * 16; };
+    std::vector<uint32_t> slots(F);
+    for (size_t i = 0; i < F; ++i) {
+        const uint32_t cell = feat_cell[i] == (uint16_t)MSS_CELL_NONE ? MSS_SLOT_CELL_NONE : (uint32_t)feat_cell[i];
+        slots[i] = feat_mp[i] < 0 ? MSS_SLOT_EMPTY : (((uint32_t)feat_mp[i] << 12) | cell);
+    }
+    std::vector<int32_t> tok_ptr(K + 1, 0);
+    for (int k = 0; k < K; ++k) {
+        std::sort(slots.begin() + feat_ptr[k], slots.begin() + feat_ptr[k + 1]);       // empty slots sort to the end
+        uint32_t prev = 0;
+        int32_t nt = 0;
+        for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
+            const uint32_t mp = slots[i] >> 12, units = (mp - prev) / 15u;
+            nt += 1 + (int32_t)((units + 4095u) / 4096u);
+            prev = mp;
+        }
+        tok_ptr[k + 1] = tok_ptr[k] + nt;
+    }
+    n_tokens = (size_t)tok_ptr[K];
     off_slots = up((size_t)(K + 1) * 4);
-    off_nobs = off_slots + up(F * 4);
+    off_nobs = off_slots + up(n_tokens * 2);
     n_pairs = 0;
     for (size_t o = 0; o < O; ++o) n_pairs += mp_obs_kf[o] >= K ? 1 : 0;       // FlattenWindow emits outside observations only
     off_pairs = off_nobs + up(M * 2);
@@ -93,15 +114,22 @@ void WindowSnapshot::Pack() {
     if (!blob) blob = std::make_shared<Blob>();
     blob->Reserve(total);
     if (!blob->p) return;
-    memcpy(blob->p, feat_ptr.data(), (size_t)(K + 1) * 4);
-    uint32_t* slots = reinterpret_cast<uint32_t*>(blob->p + off_slots);
-    for (size_t i = 0; i < F; ++i) {
-        const uint32_t cell = feat_cell[i] == (uint16_t)MSS_CELL_NONE ? MSS_SLOT_CELL_NONE : (uint32_t)feat_cell[i];
-        slots[i] = feat_mp[i] < 0 ? MSS_SLOT_EMPTY : (((uint32_t)feat_mp[i] << 12) | cell);
+    memcpy(blob->p, tok_ptr.data(), (size_t)(K + 1) * 4);
+    uint16_t* tok = reinterpret_cast<uint16_t*>(blob->p + off_slots);
+    size_t t = 0;
+    for (int k = 0; k < K; ++k) {
+        uint32_t prev = 0;
+        for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
+            const uint32_t mp = slots[i] >> 12, gap = mp - prev;
+            for (uint32_t units = gap / 15u; units > 0;) {                      // 15 * (low + 1) per escape token
+                const uint32_t u = std::min(units, 4096u);
+                tok[t++] = (uint16_t)((15u << 12) | (u - 1u));
+                units -= u;
+            }
+            tok[t++] = (uint16_t)(((gap % 15u) << 12) | (slots[i] & 0xFFFu));
+            prev = mp;
+        }
     }
-    // the order of the slots inside a keyframe carries no meaning for the model; sorted by map-point index the 32 entries
-    // a warp handles touch neighbouring map points (nearly coalesced state gathers in the row phases)
-    for (int k = 0; k < K; ++k) std::sort(slots + feat_ptr[k], slots + feat_ptr[k + 1]);
     uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
     for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
     uint32_t* pairs = reinterpret_cast<uint32_t*>(blob->p + off_pairs);
@@ -172,11 +200,11 @@ mss_window_view WindowSnapshot::View() const {
     mss_window_view v{};
     v.n_max_floor = n_max_floor;
     if (packed && blob && blob->p) {
-        v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)n_pairs;
+        v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)n_tokens; v.O = (int32_t)n_pairs;
         v.memory = MSS_MEM_HOST;
-        v.layout = MSS_LAYOUT_PACKED;
+        v.layout = MSS_LAYOUT_PACKED16;
         v.feat_ptr = reinterpret_cast<const int32_t*>(blob->p);
-        v.slots = reinterpret_cast<const uint32_t*>(blob->p + off_slots);
+        v.slots16 = reinterpret_cast<const uint16_t*>(blob->p + off_slots);
         v.mp_nobs16 = reinterpret_cast<const uint16_t*>(blob->p + off_nobs);
         v.obs_pairs = reinterpret_cast<const uint32_t*>(blob->p + off_pairs);
         v.okf_total = reinterpret_cast<const int32_t*>(blob->p + off_okf);

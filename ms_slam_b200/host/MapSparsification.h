@@ -33,7 +33,7 @@ struct WindowSnapshot {
     std::vector<std::shared_ptr<KeyFrame>> vpOutsideKFs;      // ordered by KeyFrame::mnId
     int K = 0, H = 0;
     double flatten_ms = 0.0;
-    // MSS_LAYOUT_PACKED transport form of the same arrays in ONE host blob (pinned when a CUDA device is present), laid
+    // MSS_LAYOUT_PACKED16 transport form of the same arrays in ONE host blob (pinned when a CUDA device is present), laid
     // out back to back at 16-byte boundaries so the engine moves the window with a single copy.  Built by FlattenWindow
     // whenever the window fits the packed ranges (M <= 2^20, nObs <= 65535, H <= 4095); View() then returns it.
     struct Blob {
@@ -44,7 +44,7 @@ struct WindowSnapshot {
         void Reserve(size_t bytes);
     };
     std::shared_ptr<Blob> blob;
-    size_t off_slots = 0, off_nobs = 0, off_pairs = 0, off_okf = 0, n_pairs = 0;
+    size_t off_slots = 0, off_nobs = 0, off_pairs = 0, off_okf = 0, n_pairs = 0, n_tokens = 0;
     bool packed = false;
     int n_max_floor = 0;       // window-wide nMax carried by a component of a larger window (mss.h)
     std::vector<int32_t> part_mp;   // component only: index of each of its map points in the parent snapshot

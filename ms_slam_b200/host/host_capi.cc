@@ -125,6 +125,24 @@ void msh_snapshot_copy(void* h, int which, int32_t* feat_ptr, int32_t* feat_mp, 
     for (size_t j = 0; j < s.vpOutsideKFs.size(); ++j) okf_ids[j] = (int64_t)s.vpOutsideKFs[j]->mnId;
 }
 
+// the packed transport blob of a snapshot (MSS_LAYOUT_PACKED16): sizes first (out4 = tokens, pairs, packed flag, blob bytes),
+// then the arrays; tok_ptr[K+1], tokens[n_tokens], nobs16[M], pairs[n_pairs]
+void msh_snapshot_packed_sizes(void* h, int which, int64_t* out4) {
+    const WindowSnapshot& s = snap(static_cast<World*>(h), which);
+    const mss_window_view v = s.View();
+    out4[0] = (int64_t)s.n_tokens; out4[1] = (int64_t)s.n_pairs; out4[2] = s.packed ? 1 : 0;
+    out4[3] = (v.layout == MSS_LAYOUT_PACKED16) ? (int64_t)(s.off_okf + (size_t)s.H * 4) : 0;
+}
+void msh_snapshot_packed_copy(void* h, int which, int32_t* tok_ptr, uint16_t* tokens, uint16_t* nobs16, uint32_t* pairs) {
+    const WindowSnapshot& s = snap(static_cast<World*>(h), which);
+    const mss_window_view v = s.View();
+    if (v.layout != MSS_LAYOUT_PACKED16) return;
+    memcpy(tok_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
+    memcpy(tokens, v.slots16, (size_t)v.F * 2);
+    memcpy(nobs16, v.mp_nobs16, (size_t)v.M * 2);
+    memcpy(pairs, v.obs_pairs, (size_t)v.O * 4);
+}
+
 // The calls System makes at start-up (src/System.cc:160): run the sparsifier on its own thread.
 int msh_start(void* h) {
     World* w = static_cast<World*>(h);

@@ -35,6 +35,8 @@ def load_library(path: str = LIB_PATH):
         lib.msh_snapshot_copy.restype = None
         lib.msh_bad_flags.restype = None
         lib.msh_keyframe_state.restype = None
+        lib.msh_snapshot_packed_sizes.restype = None
+        lib.msh_snapshot_packed_copy.restype = None
         _lib = lib
     return _lib
 
@@ -90,6 +92,21 @@ class World:
         self.lib.msh_snapshot_copy(self.h, which, _p(a["feat_ptr"]), _p(a["feat_mp"]), _p(a["feat_cell"]), _p(a["mp_nobs"]),
                                    _p(a["mp_obs_ptr"]), _p(a["mp_obs_kf"]), _p(a["okf_total"]), _p(mp_ids), _p(okf_ids), _p(is_var))
         return WindowView(K=K, H=H, **a), mp_ids, okf_ids, is_var.astype(bool)
+
+    def snapshot_packed(self, which=1):
+        """The packed transport blob FlattenWindow built for the last window: dict(tok_ptr, tokens, nobs16, pairs, blob_bytes)
+        or None when the window did not fit the packed ranges"""
+        sz = np.zeros(4, np.int64)
+        self.lib.msh_snapshot_packed_sizes(self.h, which, _p(sz))
+        if not sz[2]:
+            return None
+        s5 = np.zeros(5, np.int32)
+        self.lib.msh_snapshot_sizes(self.h, which, _p(s5))
+        K, M = int(s5[0]), int(s5[2])
+        out = dict(tok_ptr=np.zeros(K + 1, np.int32), tokens=np.zeros(int(sz[0]), np.uint16), nobs16=np.zeros(M, np.uint16),
+                   pairs=np.zeros(int(sz[1]), np.uint32), blob_bytes=int(sz[3]))
+        self.lib.msh_snapshot_packed_copy(self.h, which, _p(out["tok_ptr"]), _p(out["tokens"]), _p(out["nobs16"]), _p(out["pairs"]))
+        return out
 
     # the calls the rest of the SLAM system makes
     def start(self): return self.lib.msh_start(self.h)

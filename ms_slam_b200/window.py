@@ -247,7 +247,7 @@ class PackedView:
     H: int
     M: int
     feat_ptr: np.ndarray      # int32 [K+1]
-    slots: np.ndarray         # uint32 [F]
+    slots: np.ndarray         # uint32 [F] (MSS_LAYOUT_PACKED) or uint16 tokens [F] (MSS_LAYOUT_PACKED16, see pack_view)
     mp_nobs16: np.ndarray     # uint16 [M]
     obs_pairs: np.ndarray     # uint32 [O] (map point << 12) | outside keyframe j (KF-table index K + j)
     okf_total: np.ndarray     # int32 [H]
@@ -266,7 +266,33 @@ class PackedView:
         return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.obs_pairs.nbytes + self.okf_total.nbytes)
 
 
-def pack_view(v: WindowView, sort_slots: bool = False) -> PackedView:
+def _tokens16(slots_sorted, feat_ptr):
+    """u32 slots, sorted inside every keyframe -> (u16 tokens, token feat_ptr) of MSS_LAYOUT_PACKED16 (include/mss.h)"""
+    K = feat_ptr.size - 1
+    n = slots_sorted.size
+    kf = np.repeat(np.arange(K, dtype=np.int64), np.diff(feat_ptr))
+    mp = (slots_sorted >> 12).astype(np.int64)
+    cell = (slots_sorted & 0xFFF).astype(np.int64)
+    first = np.zeros(n, bool)
+    first[feat_ptr[:-1][np.diff(feat_ptr) > 0]] = True
+    prev = np.concatenate([[0], mp[:-1]])
+    gap = np.where(first, mp, mp - prev)                   # the running index starts at 0 in every keyframe
+    units = gap // 15                                      # advanced by escape tokens, 15 * (low + 1) each, low <= 4095
+    nesc = (units + 4095) // 4096
+    ntok = nesc + 1
+    start = np.concatenate([[0], np.cumsum(ntok)])
+    tok = np.zeros(int(start[-1]), np.uint16)
+    tok[start[1:] - 1] = (((gap % 15) << 12) | cell).astype(np.uint16)          # the slot token closes its group
+    for j in range(int(nesc.max()) if n else 0):           # j-th escape of the slots that need more than j
+        sel = nesc > j
+        u = np.minimum(units[sel] - 4096 * j, 4096)
+        tok[start[:-1][sel] + j] = ((15 << 12) | (u - 1)).astype(np.uint16)
+    tptr = np.zeros(K + 1, np.int64)
+    tptr[1:] = np.cumsum(np.bincount(kf, weights=ntok, minlength=K)).astype(np.int64)
+    return tok, tptr
+
+
+def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False) -> PackedView:
     """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges.
     sort_slots: order the slots of every keyframe by map-point index (the order of the slots inside a keyframe carries no
     meaning for the model; sorted, the 32 entries a warp handles touch neighbouring map points, which turns the state
@@ -278,12 +304,22 @@ def pack_view(v: WindowView, sort_slots: bool = False) -> PackedView:
     mp = v.feat_mp.astype(np.int64)
     cell = np.where(v.feat_cell == CELL_NONE, SLOT_CELL_NONE, v.feat_cell).astype(np.int64)
     slots = np.where(mp >= 0, (mp << 12) | cell, SLOT_EMPTY).astype(np.uint32)
-    if sort_slots and slots.size:
+    if (sort_slots or tokens16) and slots.size:
         kf = np.repeat(np.arange(v.K, dtype=np.int64), np.diff(v.feat_ptr))
         slots = slots[np.lexsort((slots, kf))]
     owner = np.repeat(np.arange(v.M, dtype=np.int64), np.diff(v.mp_obs_ptr))
     outside = v.mp_obs_kf >= v.K                     # observations by window keyframes are not part of the pair list
     pairs = ((owner[outside] << 12) | (v.mp_obs_kf[outside].astype(np.int64) - v.K)).astype(np.uint32)
+    if tokens16:
+        # MSS_LAYOUT_PACKED16: valid slots only, sorted by map point inside every keyframe, delta-coded as u16 tokens
+        kf = np.repeat(np.arange(v.K, dtype=np.int64), np.diff(v.feat_ptr))
+        ok = slots != SLOT_EMPTY
+        ptr = np.zeros(v.K + 1, np.int64)
+        ptr[1:] = np.cumsum(np.bincount(kf[ok], minlength=v.K))
+        tok, tptr = _tokens16(slots[ok], ptr)
+        return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=np.ascontiguousarray(tptr, dtype=np.int32), slots=np.ascontiguousarray(tok),
+                          mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
+                          okf_total=v.okf_total, meta=dict(v.meta, packed=True, tokens16=True), n_max_floor=v.n_max_floor)
     return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
                       mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
                       okf_total=v.okf_total, meta=dict(v.meta, packed=True), n_max_floor=v.n_max_floor)

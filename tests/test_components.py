@@ -65,7 +65,7 @@ def test_gpu_components_match_oracle(build_native):
              make_view(0, [], [5, 6])]
     for v in cases:
         ref = oc.components(v)
-        for view in (v, pack_view(v.compact())):
+        for view in (v, pack_view(v.compact()), pack_view(v, tokens16=True)):
             rows, mps, nc, nmax = eng.components(view)
             assert np.array_equal(rows, ref[0]) and np.array_equal(mps, ref[1]) and (nc, nmax) == (ref[2], ref[3])
     eng.close()

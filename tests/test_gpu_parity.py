@@ -172,7 +172,7 @@ def test_packed_layout_same_result(eng, name, seed):
     view, N = msgen.make_config(name, seed)
     eng.set_params(N, LAM, GLAM)
     soa = eng.solve(view)
-    for pv in (pack_view(view), pack_view(view.compact()), pack_view(view.compact(), sort_slots=True)):
+    for pv in (pack_view(view), pack_view(view.compact()), pack_view(view.compact(), sort_slots=True), pack_view(view, tokens16=True)):
         pk = eng.solve(pv)
         assert np.array_equal(soa.keep_bits, pk.keep_bits) and np.array_equal(soa.kf_cov, pk.kf_cov)
         assert (soa.objective, soa.rounds, soa.n_vars, soa.n_cells, soa.nnz, soa.n_max) == \

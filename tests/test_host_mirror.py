@@ -77,6 +77,56 @@ def test_flatten_roundtrip(hm, name, seed, over):
         w.close()
 
 
+def decode_tokens(tok_ptr, tokens):
+    """MSS_LAYOUT_PACKED16 tokens -> (kf, mp, cell) of every slot, the way the device decodes them (include/mss.h)"""
+    out = []
+    for k in range(tok_ptr.size - 1):
+        mp = 0
+        for t in tokens[tok_ptr[k]:tok_ptr[k + 1]].tolist():
+            d, low = t >> 12, t & 0xFFF
+            if d < 15:
+                mp += d
+                out.append((k, mp, 0xFFFF if low == 0xFFF else low))
+            else:
+                mp += 15 * (low + 1)
+    return out
+
+
+@pytest.mark.parametrize("name,seed,over", [("c1", 0, {}), ("live", 3, dict(M=1500, H=20)), ("c3", 0, {})])
+def test_flatten_packed_blob_matches_the_python_packer(hm, name, seed, over):
+    """The blob FlattenWindow ships (u16 tokens, u16 nObs, outside pair list) decodes to exactly the snapshot's slots, and is
+    token for token what ms_slam_b200.window.pack_view(tokens16=True) produces for the same snapshot."""
+    from ms_slam_b200 import pack_view
+    view, N = msgen.make_config(name, seed, **over)
+    w = hm.World(view, N=N)
+    try:
+        flat, mp_ids, okf_ids, is_var = w.flatten_only()
+        blob = w.snapshot_packed(0)
+        assert blob is not None
+        ref = pack_view(flat, tokens16=True)
+        assert np.array_equal(blob["tok_ptr"], ref.feat_ptr) and np.array_equal(blob["tokens"], ref.slots)
+        assert np.array_equal(blob["nobs16"], ref.mp_nobs16) and np.array_equal(np.sort(blob["pairs"]), np.sort(ref.obs_pairs))
+        kf = np.repeat(np.arange(flat.K), np.diff(flat.feat_ptr))
+        want = sorted(zip(kf.tolist(), flat.feat_mp.tolist(), flat.feat_cell.tolist()))
+        assert sorted(decode_tokens(blob["tok_ptr"], blob["tokens"])) == want
+        assert blob["blob_bytes"] < 0.40 * flat.input_bytes()
+    finally:
+        w.close()
+
+
+def test_token_coding_escapes():
+    """gaps of 15 and more use escape tokens (15 * (low + 1) each, several when the gap exceeds 61440)"""
+    from ms_slam_b200 import pack_view
+    M = 400000
+    slots = [[(0, 5), (14, 6), (15, 7), (29, None), (30, 9), (100000, 10), (399999, 11)], [(61439, 1), (61440, 2), (122881, 3)], []]
+    v = make_view(3, slots, [5] * M)
+    pv = pack_view(v, tokens16=True)
+    got = decode_tokens(pv.feat_ptr, pv.slots)
+    want = sorted((k, p, 0xFFFF if c is None else c) for k, row in enumerate(slots) for p, c in row)
+    assert sorted(got) == want
+    assert pv.feat_ptr[-1] == pv.slots.size and pv.feat_ptr[3] == pv.feat_ptr[2]
+
+
 def test_flatten_quirks(hm):
     # empty / bad slots, keypoints outside the grid, a point in two slots of one keyframe (SURVEY A.5.1), an outside keyframe
     view = make_view(2, [[(0, 0), (None, 3), (1, None), (2, 7), (2, 9)], [(2, 100), (3, 3071), (None, None)]],
