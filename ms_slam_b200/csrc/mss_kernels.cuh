@@ -1074,7 +1074,6 @@ __device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, int of
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
     const int cov0 = P.row_cov[R];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (n <= kThreads) row_prop_regs<1>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else if (n <= 2 * kThreads) row_prop_regs<2>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else if (n <= 4 * kThreads) row_prop_regs<4>(P, D, R, n, src, dst, need, cov0, par, tab, S);
@@ -1376,7 +1375,6 @@ __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int
     const uint8_t* st_w = P.st + D.var_base;
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int cin = 0, ccells = 0, z = 0;
     if (n > 0 && n <= kThreads) row_d1_regs<1>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0 && n <= 2 * kThreads) row_d1_regs<2>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
