@@ -1,5 +1,8 @@
 """ORACLE (test infrastructure, not product code) -- numpy emulation of the device algorithm, phase by phase.
 
+PARITY UNPINNED BY UPSTREAM (no tests / fixtures / golden vectors for this path; GUROBI is closed source and the reference
+cannot be built here, see oracle/ilp_model.py).  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+
 This is NOT the reference's algorithm (that is the ILP in oracle/ilp_model.py, solved by GUROBI upstream,
 /root/reference/src/MapSparsification.cc:153-157).  It restates, on the CPU and with identical integer arithmetic,
 tie-breaks and control flow, what ms_slam_b200/csrc/mss_kernels.cu does on the device, so that the GPU keep-bitmask can be

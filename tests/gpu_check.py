@@ -1,8 +1,8 @@
 """GPU-box check: every config through the C-ABI vs the CPU emulation (bit-exact) + quick timings.
-Writes gpurun_out/gpu_check.json.  Run: python tools/gpu_check.py [--big]"""
+Writes gpurun_out/gpu_check.json.  Run: python tests/gpu_check.py [--big]  (a checker, like the tests: it uses the oracle)"""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 from ms_slam_b200 import msgen
 from ms_slam_b200.engine import Engine, DeviceView

@@ -270,3 +270,39 @@ def test_round_cap_reports_noconverge_but_stays_feasible(build_native):
     model = om.build_model(view, N)
     assert om.rows_satisfied(model, om.keep_to_x(model, res.keep), N)[0]
     e.close()
+
+
+def long_row_window(seed=5, sizes=(5000, 2600, 300), M=6500, H=2):
+    """keyframes with more slots than the register-resident row paths hold (2048): exercises the two-pass fallbacks"""
+    rng = np.random.default_rng(seed)
+    slots = []
+    for n in sizes:
+        mps = rng.choice(M, size=n, replace=False)
+        cells = rng.integers(0, 3072, size=n)
+        off = rng.random(n) < 0.03
+        slots.append([(int(p), None if o else int(c)) for p, c, o in zip(mps, cells, off)])
+    nobs = rng.integers(3, 40, size=M).tolist()
+    outside = [rng.choice(M, size=400, replace=False).tolist() for _ in range(H)]
+    return make_view(len(sizes), slots, nobs, outside=outside, okf_total=[900] * H)
+
+
+@pytest.mark.parametrize("N", [100, 2700])
+def test_long_keyframe_rows_all_layouts(eng, N):
+    """Rows longer than 2048 entries take the two-pass paths of W1 / PROP / GREEDY / the sweeps; N = 2700 makes the long rows
+    deficient so that the greedy and budget phases see them too.  Same result in every layout, bit-exact vs the emulation."""
+    from ms_slam_b200.engine import DeviceView
+    from ms_slam_b200.window import pack_view
+    view = long_row_window()
+    eng.set_params(N, LAM, GLAM)
+    ref = em.solve(view, N, LAM, GLAM)
+    for v in (view, pack_view(view), pack_view(view, sort_slots=True), pack_view(view, tokens16=True)):
+        res = eng.solve(v)
+        check_against_cpu(view, N, res, ref)
+    dv = DeviceView(eng, pack_view(view, tokens16=True))
+    assert np.array_equal(eng.solve(dv).keep, ref["keep"])
+    dv.free()
+    from oracle import components as oc
+    want = oc.components(view)
+    for v in (view, pack_view(view, tokens16=True)):
+        rows, mps, nc, nmax = eng.components(v)
+        assert np.array_equal(rows, want[0]) and np.array_equal(mps, want[1]) and (nc, nmax) == (want[2], want[3])
