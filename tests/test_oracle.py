@@ -165,3 +165,17 @@ def test_property_dominance_rules_are_exact(case):
         f = om.objective(model, x, N, LAM, GLAM)
         best = f if best is None else min(best, f)
     assert best == pytest.approx(F_bf, abs=1e-9)
+
+
+@pytest.mark.parametrize("name,seed,over", [("c1", 0, {}), ("live", 0, {}), ("c4", 0, dict(M=3000)), ("live", 0, dict(M=1500, H=20))])
+def test_dual_bound_is_valid_and_tight(name, seed, over):
+    """The solver-free lower bound planned for mss_result.dual_bound (oracle/dual_bound.py): never above the LP optimum of
+    the reference model, and close enough to certify the 1 % bar on its own."""
+    from oracle import dual_bound as db
+    view, N = msgen.make_config(name, seed, **over)
+    b = db.dual_bound(view, N, LAM, GLAM)
+    lp = om.solve_lp(view, N, LAM, GLAM).objective
+    F = em.solve(view, N, LAM, GLAM)["objective"]
+    assert b["bound"] <= lp + 1e-6
+    assert F <= 1.01 * b["bound"]
+    assert b["bound"] >= 0.99 * lp
