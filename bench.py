@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- sparsification windows/sec on the KITTI-00-shaped 500 KF x 200k MP window (BASELINE.json metric).
 
-A "step" = one mss_solve_batch over a batch of B independent synthetic c2 windows per GPU (msgen-v1 seeds; the batch
-is larger than L2, so no flush is needed between steps).  With N GPUs the global batch is N*B windows, window w is
-solved by rank w % N and the result slots (keep bitmask + row coverage) are all-gathered with NCCL inside the call.
+A "step" = one mss_solve_batch over a batch of B independent synthetic c2 windows per GPU (msgen-v1 seeds, in the transport
+form FlattenWindow emits: valid slots only, map points in discovery order, MSS_LAYOUT_PACKED16; the batch is larger than L2,
+so no flush is needed between steps).  With N GPUs the global batch is N*B windows, window w is solved by rank w % N and the
+result slots (keep bitmask + row coverage) are all-gathered with NCCL inside the call.
 
-  value : whole-job windows/s, views and result buffers resident in HBM, CUDA events on the engine's stream, max over ranks
-  e2e   : the same call with HOST (pinned) views and results: H2D of every view + D2H of the results inside the timed region
-  roofline     : the persistent kernel (the only kernel): algorithmic bytes (view read once + result written once) / its
-                 CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  value : whole-job windows/s, views and result arrays resident in HBM, CUDA events on the engine's stream, max over ranks
+  e2e   : the same call with HOST views (one pinned blob per window) and host result arrays: the H2D of every view (it
+          overlaps the solve: the persistent kernel waits per window for a ready flag) + D2H of the results in the timed region
+  roofline     : the persistent kernel: algorithmic bytes / its CUDA-event duration, against the
+                 measured HBM copy bandwidth (MEASURED_PEAKS.json); traffic = ncu dram bytes of the same launch (profiles/)
   cpu_baseline : the oracle port (HiGHS) timed on this box's host cores on a bounded sample (rank 0, N=1)
   --impl reference : times the reference's CPU algorithm (oracle port: HiGHS, GUROBI is not installable) on the same metric
 """
