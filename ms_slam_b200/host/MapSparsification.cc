@@ -62,6 +62,28 @@ bool ReadSparsificationSettings(const std::string& path, SparsificationSettings&
 // ---------------------------------------------------------------------------------------------------------------------
 // flatten: pointer graph -> mss_window_view
 // ---------------------------------------------------------------------------------------------------------------------
+// Worker threads of the flatten pass: the accessors of the SLAM classes take per-object mutexes (KeyFrame.cc:434-444,
+// MapPoint.cc:215-225,325-331), so keyframes and map points can be read from several threads; everything that fixes an
+// ORDER (map-point numbering, outside-keyframe table) stays sequential.  MSS_FLATTEN_THREADS overrides the default.
+static int FlattenThreads() {
+    if (const char* e = std::getenv("MSS_FLATTEN_THREADS")) { const int n = std::atoi(e); if (n > 0) return std::min(n, 64); }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hw ? hw : 1u, 8u));
+}
+
+template <class F>
+static void ParallelChunks(size_t n, int nthreads, size_t min_per_thread, F f) {   // f(thread, begin, end), contiguous ascending chunks
+    nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads, (n + min_per_thread - 1) / min_per_thread));
+    if (nthreads <= 1) { f(0, (size_t)0, n); return; }
+    vector<std::thread> pool;
+    const size_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const size_t lo = std::min(n, per * t), hi = std::min(n, per * (t + 1));
+        pool.emplace_back([=, &f] { f(t, lo, hi); });
+    }
+    for (std::thread& th : pool) th.join();
+}
+
 WindowSnapshot::Blob::~Blob() {
     if (!p) return;
     if (pinned) mss_host_free(p); else std::free(p);
@@ -92,17 +114,21 @@ void WindowSnapshot::Pack() {
         slots[i] = feat_mp[i] < 0 ? MSS_SLOT_EMPTY : (((uint32_t)feat_mp[i] << 12) | cell);
     }
     std::vector<int32_t> tok_ptr(K + 1, 0);
-    for (int k = 0; k < K; ++k) {
-        std::sort(slots.begin() + feat_ptr[k], slots.begin() + feat_ptr[k + 1]);       // empty slots sort to the end
-        uint32_t prev = 0;
-        int32_t nt = 0;
-        for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
-            const uint32_t mp = slots[i] >> 12, units = (mp - prev) / 15u;
-            nt += 1 + (int32_t)((units + 4095u) / 4096u);
-            prev = mp;
+    const int nthreads = FlattenThreads();
+    ParallelChunks((size_t)K, nthreads, 4, [&](int, size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            std::sort(slots.begin() + feat_ptr[k], slots.begin() + feat_ptr[k + 1]);   // empty slots sort to the end
+            uint32_t prev = 0;
+            int32_t nt = 0;
+            for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
+                const uint32_t mp = slots[i] >> 12, units = (mp - prev) / 15u;
+                nt += 1 + (int32_t)((units + 4095u) / 4096u);
+                prev = mp;
+            }
+            tok_ptr[k + 1] = nt;
         }
-        tok_ptr[k + 1] = tok_ptr[k] + nt;
-    }
+    });
+    for (int k = 0; k < K; ++k) tok_ptr[k + 1] += tok_ptr[k];
     n_tokens = (size_t)tok_ptr[K];
     off_slots = up((size_t)(K + 1) * 4);
     off_nobs = off_slots + up(n_tokens * 2);
@@ -116,20 +142,22 @@ void WindowSnapshot::Pack() {
     if (!blob->p) return;
     memcpy(blob->p, tok_ptr.data(), (size_t)(K + 1) * 4);
     uint16_t* tok = reinterpret_cast<uint16_t*>(blob->p + off_slots);
-    size_t t = 0;
-    for (int k = 0; k < K; ++k) {
-        uint32_t prev = 0;
-        for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
-            const uint32_t mp = slots[i] >> 12, gap = mp - prev;
-            for (uint32_t units = gap / 15u; units > 0;) {                      // 15 * (low + 1) per escape token
-                const uint32_t u = std::min(units, 4096u);
-                tok[t++] = (uint16_t)((15u << 12) | (u - 1u));
-                units -= u;
+    ParallelChunks((size_t)K, nthreads, 4, [&](int, size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            size_t t = (size_t)tok_ptr[k];
+            uint32_t prev = 0;
+            for (int32_t i = feat_ptr[k]; i < feat_ptr[k + 1] && slots[i] != MSS_SLOT_EMPTY; ++i) {
+                const uint32_t mp = slots[i] >> 12, gap = mp - prev;
+                for (uint32_t units = gap / 15u; units > 0;) {                  // 15 * (low + 1) per escape token
+                    const uint32_t u = std::min(units, 4096u);
+                    tok[t++] = (uint16_t)((15u << 12) | (u - 1u));
+                    units -= u;
+                }
+                tok[t++] = (uint16_t)(((gap % 15u) << 12) | (slots[i] & 0xFFFu));
+                prev = mp;
             }
-            tok[t++] = (uint16_t)(((gap % 15u) << 12) | (slots[i] & 0xFFFu));
-            prev = mp;
         }
-    }
+    });
     uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
     for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
     uint32_t* pairs = reinterpret_cast<uint32_t*>(blob->p + off_pairs);
@@ -221,6 +249,9 @@ mss_window_view WindowSnapshot::View() const {
 void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int nId, WindowSnapshot& out) {
     const Clock::time_point t0 = Clock::now();
     const int K = (int)vpKFs.size();
+    const int nthreads = FlattenThreads();
+    const bool trace = std::getenv("MSS_FLATTEN_TRACE") != nullptr;
+    double tA = 0, tB = 0, tC = 0, tD = 0;
     out.K = K; out.H = 0;
     out.feat_ptr.assign(1, 0);
     out.feat_mp.clear(); out.feat_cell.clear(); out.mp_nobs.clear(); out.is_var.clear();
@@ -230,58 +261,87 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     // window membership first (the reference stamps inside its second pass, :81; observations are classified with it, :132)
     for (int k = 0; k < K; ++k) vpKFs[k]->mnMapSaprsificationId = nId;
 
-    // keyframe side: slots and cells (passes 1 and 2, :67-123).  Only valid slots are emitted (empty slots and bad points
-    // contribute nothing to the model, :70,90), which keeps the transport to the GPU small.
-    vector<int32_t> slotPos;
+    // keyframe side, parallel over keyframes: valid slots and their cells (passes 1 and 2, :67-123).  Only valid slots are
+    // kept (empty slots and bad points contribute nothing to the model, :70,90).
+    struct KfLocal { vector<shared_ptr<MapPoint>> mps; vector<uint16_t> cell; };
+    vector<KfLocal> local(K);
+    ParallelChunks((size_t)K, nthreads, 4, [&](int, size_t lo, size_t hi) {
+        vector<int32_t> slotPos;
+        for (size_t k = lo; k < hi; ++k) {
+            const vector<shared_ptr<MapPoint>> vMPs = vpKFs[k]->GetMapPointMatches();
+            const size_t n = vMPs.size();
+            KfLocal& L = local[k];
+            slotPos.assign(n, -1);
+            for (size_t i = 0; i < n; ++i) {
+                const shared_ptr<MapPoint>& pMP = vMPs[i];
+                if (!pMP || pMP->isBad()) continue;
+                slotPos[i] = (int32_t)L.mps.size();
+                L.mps.push_back(pMP);
+                L.cell.push_back((uint16_t)MSS_CELL_NONE);
+            }
+            const auto& grid = vpKFs[k]->GetFeatureGrids();
+            for (size_t col = 0; col < grid.size(); ++col)
+                for (size_t row = 0; row < grid[col].size(); ++row)
+                    for (size_t i : grid[col][row]) {
+                        if (i >= n || slotPos[i] < 0) continue;
+                        L.cell[slotPos[i]] = (uint16_t)(col * MSS_GRID_ROWS + row);
+                    }
+        }
+    });
+    tA = MsSince(t0);
+    // numbering, sequential: map points in discovery order = mnIndexForSparsification of the reference (:91-99)
     for (int k = 0; k < K; ++k) {
-        const vector<shared_ptr<MapPoint>> vMPs = vpKFs[k]->GetMapPointMatches();
-        const size_t n = vMPs.size();
-        slotPos.assign(n, -1);
-        for (size_t i = 0; i < n; ++i) {
-            const shared_ptr<MapPoint>& pMP = vMPs[i];
-            if (!pMP || pMP->isBad()) continue;
+        const KfLocal& L = local[k];
+        for (size_t i = 0; i < L.mps.size(); ++i) {
+            MapPoint* pMP = L.mps[i].get();
             if (pMP->mnMapSparsificationId != nId) {
                 pMP->mnMapSparsificationId = nId;
                 pMP->mnIndexForSparsification = out.vpMapPoints.size();
-                out.vpMapPoints.push_back(pMP);
-                out.mp_nobs.push_back(pMP->Observations());
+                out.vpMapPoints.push_back(L.mps[i]);
                 out.is_var.push_back(0);
             }
-            slotPos[i] = (int32_t)out.feat_mp.size();
             out.feat_mp.push_back((int32_t)pMP->mnIndexForSparsification);
-            out.feat_cell.push_back((uint16_t)MSS_CELL_NONE);
+            out.feat_cell.push_back(L.cell[i]);
+            if (L.cell[i] != (uint16_t)MSS_CELL_NONE) out.is_var[pMP->mnIndexForSparsification] = 1;
         }
-        const auto& grid = vpKFs[k]->GetFeatureGrids();
-        for (size_t col = 0; col < grid.size(); ++col)
-            for (size_t row = 0; row < grid[col].size(); ++row)
-                for (size_t i : grid[col][row]) {
-                    if (i >= n || slotPos[i] < 0) continue;
-                    out.feat_cell[slotPos[i]] = (uint16_t)(col * MSS_GRID_ROWS + row);
-                    out.is_var[out.feat_mp[slotPos[i]]] = 1;
-                }
         out.feat_ptr.push_back((int32_t)out.feat_mp.size());
     }
+    vector<KfLocal>().swap(local);
+    tB = MsSince(t0);
 
-    // map-point side: observations of the variables by keyframes OUTSIDE the window (pass 3, :125-142); observations by
-    // window keyframes are not emitted (the engine only needs the outside rows); outside keyframes in discovery order for now
-    std::unordered_map<const KeyFrame*, int> outsideIndex;
+    // map-point side, parallel over map points: Observations() of every point and, for the variables, their observations
+    // by keyframes OUTSIDE the window (pass 3, :125-142); observations by window keyframes are not needed (the engine only
+    // builds the outside rows).  Chunks are contiguous, so concatenating the threads' lists keeps map-point order.
     const size_t M = out.vpMapPoints.size();
-    for (size_t p = 0; p < M; ++p) {
-        if (out.is_var[p]) {
+    out.mp_nobs.assign(M, 0);
+    typedef std::pair<int32_t, shared_ptr<KeyFrame>> OutObs;
+    vector<vector<OutObs>> found((size_t)std::max(nthreads, 1));
+    ParallelChunks(M, nthreads, 1024, [&](int t, size_t lo, size_t hi) {
+        vector<OutObs>& mine = found[t];
+        for (size_t p = lo; p < hi; ++p) {
+            out.mp_nobs[p] = out.vpMapPoints[p]->Observations();
+            if (!out.is_var[p]) continue;
             const auto obs = out.vpMapPoints[p]->GetObservations();
-            for (const auto& kv : obs) {
-                if (kv.first->mnMapSaprsificationId == nId) continue;
-                const KeyFrame* pKF = kv.first.get();
-                auto it = outsideIndex.find(pKF);
-                if (it == outsideIndex.end()) {
-                    it = outsideIndex.emplace(pKF, (int)out.vpOutsideKFs.size()).first;
-                    out.vpOutsideKFs.push_back(kv.first);
-                }
-                out.mp_obs_kf.push_back(K + it->second);
-            }
+            for (const auto& kv : obs)
+                if (kv.first->mnMapSaprsificationId != nId) mine.emplace_back((int32_t)p, kv.first);
         }
-        out.mp_obs_ptr.push_back((int32_t)out.mp_obs_kf.size());
-    }
+    });
+    tC = MsSince(t0);
+    // outside-keyframe table, sequential (discovery order for now)
+    std::unordered_map<const KeyFrame*, int> outsideIndex;
+    vector<int32_t> cnt(M + 1, 0);
+    for (const vector<OutObs>& lst : found)
+        for (const OutObs& o : lst) {
+            auto it = outsideIndex.find(o.second.get());
+            if (it == outsideIndex.end()) {
+                it = outsideIndex.emplace(o.second.get(), (int)out.vpOutsideKFs.size()).first;
+                out.vpOutsideKFs.push_back(o.second);
+            }
+            out.mp_obs_kf.push_back(K + it->second);
+            ++cnt[o.first + 1];
+        }
+    out.mp_obs_ptr.assign(M + 1, 0);
+    for (size_t p = 0; p < M; ++p) out.mp_obs_ptr[p + 1] = out.mp_obs_ptr[p] + cnt[p + 1];
     // deterministic order of the outside rows: by keyframe id (the reference orders by pointer value, :125-126)
     const int H = (int)out.vpOutsideKFs.size();
     vector<int> order(H), rank(H);
@@ -293,9 +353,15 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     for (int32_t& kf : out.mp_obs_kf) if (kf >= K) kf = K + rank[kf - K];
     out.H = H;
     out.okf_total.resize(H);
-    for (int j = 0; j < H; ++j) out.okf_total[j] = out.vpOutsideKFs[j]->GetNumberMPs();      // :146
+    ParallelChunks((size_t)H, nthreads, 4, [&](int, size_t lo, size_t hi) {
+        for (size_t j = lo; j < hi; ++j) out.okf_total[j] = out.vpOutsideKFs[j]->GetNumberMPs();      // :146
+    });
+    tD = MsSince(t0);
     out.Pack();
     out.flatten_ms = MsSince(t0);
+    if (trace)
+        std::cerr << "FlattenWindow: " << nthreads << " threads, keyframes " << tA << " ms, numbering " << (tB - tA) << ", map points "
+                  << (tC - tB) << ", outside table " << (tD - tC) << ", pack " << (out.flatten_ms - tD) << ", total " << out.flatten_ms << std::endl;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ struct World {
     std::thread thread;
     bool running = false;
     WindowSnapshot flat;                               // msh_flatten_only
+    long unsigned int flat_id = 1000000;
     ~World() {
         if (running) { ms->RequestFinish(); thread.join(); }
         delete ms;
@@ -99,9 +100,11 @@ int msh_build_world(void* h, int K, int H, int M, const int32_t* feat_ptr, const
 int msh_flatten_only(void* h) {
     World* w = static_cast<World*>(h);
     std::vector<std::shared_ptr<KeyFrame>> win(w->kfs.begin(), w->kfs.begin() + w->K);
-    FlattenWindow(win, 1, w->flat);
+    FlattenWindow(win, ++w->flat_id, w->flat);         // a fresh window id per call, like Sparsifying() (mnId++)
     return 0;
 }
+// host time of the last msh_flatten_only in microseconds (FlattenWindow incl. packing; WindowSnapshot::flatten_ms)
+int msh_flatten_us(void* h) { return (int)(static_cast<World*>(h)->flat.flatten_ms * 1000.0); }
 
 static const WindowSnapshot& snap(World* w, int which) { return which == 0 ? w->flat : w->ms->LastSnapshot(); }
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "host", "libmss_host.so")
 SYMBOLS = ["msh_create", "msh_destroy", "msh_engine_ready", "msh_build_world", "msh_flatten_only", "msh_snapshot_sizes",
            "msh_snapshot_copy", "msh_start", "msh_feed", "msh_nonlocal_after", "msh_forwarded_count", "msh_wait_forwarded",
            "msh_stop_handshake", "msh_consume", "msh_finish", "msh_bad_flags", "msh_forwarded_ids", "msh_keyframe_state",
-           "msh_map_counts", "msh_reports", "msh_set_min_points"]
+           "msh_map_counts", "msh_reports", "msh_set_min_points", "msh_flatten_us"]
 _lib = None
 
 
@@ -79,6 +79,15 @@ class World:
     def flatten_only(self):
         self.lib.msh_flatten_only(self.h)
         return self.snapshot(0)
+
+    def flatten_ms(self, reps=3):
+        """host time of FlattenWindow (incl. packing into the pinned blob) on this world, best of reps, in ms"""
+        best = None
+        for _ in range(reps):
+            self.lib.msh_flatten_only(self.h)
+            t = self.lib.msh_flatten_us(self.h) / 1000.0
+            best = t if best is None else min(best, t)
+        return best
 
     def snapshot(self, which=1):
         """(WindowView, mp_ids, okf_ids, is_var) of the last flattened window"""
