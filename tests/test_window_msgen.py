@@ -144,3 +144,68 @@ def test_merge_views_is_block_diagonal():
             seg = seg[seg >= 0]
             kf_part[k] = int(seg[0] >= parts[0].M) if seg.size else 0
         assert np.array_equal(part_of_mp, kf_part[kf[ok]])
+
+
+# ---- property tests (hypothesis) ---------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.lists(st.tuples(st.integers(0, 300000), st.one_of(st.none(), st.integers(0, 3071))), max_size=40), min_size=1, max_size=5),
+       st.integers(0, 3))
+def test_token_coding_roundtrip_property(rows, extra):
+    """any set of slots (arbitrary gaps, duplicates, off-grid keypoints, empty keyframes) survives MSS_LAYOUT_PACKED16"""
+    from ms_slam_b200 import pack_view
+    M = 300001 + extra
+    v = make_view(len(rows), rows, [5] * M)
+    pv = pack_view(v, tokens16=True)
+    got = []
+    for k in range(pv.K):
+        mp = 0
+        for t in pv.slots[pv.feat_ptr[k]:pv.feat_ptr[k + 1]].tolist():
+            d, low = t >> 12, t & 0xFFF
+            if d < 15:
+                mp += d
+                got.append((k, mp, None if low == 0xFFF else low))
+            else:
+                mp += 15 * (low + 1)
+    want = sorted(((k, p, c) for k, row in enumerate(rows) for p, c in row), key=lambda x: (x[0], x[1], -1 if x[2] is None else x[2]))
+    assert sorted(got, key=lambda x: (x[0], x[1], -1 if x[2] is None else x[2])) == want
+    assert int(pv.feat_ptr[-1]) == pv.slots.size
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 6), st.integers(1, 30), st.integers(0, 2 ** 32 - 1))
+def test_components_oracle_vs_naive_union_find(K, M, seed):
+    """oracle/components.py (scipy) against a plain union-find over the same edges, canonical labels included"""
+    from oracle import components as oc
+    rng = np.random.default_rng(seed)
+    H = int(rng.integers(0, 3))
+    rows = [[(int(p), None if rng.random() < 0.2 else int(rng.integers(0, 3072))) for p in rng.choice(M, size=int(rng.integers(0, min(M, 6) + 1)), replace=False)]
+            for _ in range(K)]
+    outside = [rng.choice(M, size=int(rng.integers(0, min(M, 4) + 1)), replace=False).tolist() for _ in range(H)]
+    v = make_view(K, rows, [5] * M, outside=outside, okf_total=[9] * H if H else None)
+    rl, ml, nc, _ = oc.components(v)
+    parent = list(range(K + H + M))
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    isvar = [False] * M
+    for k, row in enumerate(rows):
+        for p, c in row:
+            if c is not None:
+                isvar[p] = True
+                a, b = find(k), find(K + H + p)
+                parent[max(a, b)] = min(a, b)
+    for j, lst in enumerate(outside):
+        for p in lst:
+            if isvar[p]:
+                a, b = find(K + j), find(K + H + p)
+                parent[max(a, b)] = min(a, b)
+    roots = sorted({find(r) for r in range(K + H)})
+    dense = {r: i for i, r in enumerate(roots)}
+    assert nc == len(roots)
+    assert rl.tolist() == [dense[find(r)] for r in range(K + H)]
+    assert ml.tolist() == [dense[find(K + H + p)] if isvar[p] else -1 for p in range(M)]
