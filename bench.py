@@ -137,32 +137,41 @@ def survey_alg_bytes(K, H, M, F, O, Z, G, I):
 # ------------------------------------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------------------------------
-def cpu_sample(ks, seed=12345):
-    """One bounded CPU sample: the reference's model (oracle/ilp_model.py) on a c2-shaped window scaled to ks keyframes,
-    assembled and solved by HiGHS as an LP relaxation -- the root node every MILP solve (GUROBI upstream) must at least
-    pay, i.e. an optimistic estimate of the reference's time."""
+def cpu_sample(seed=12345, workload="c2", milp=False, time_limit=None):
+    """One CPU sample: the reference's model (oracle/ilp_model.py restates MapSparsification.cc:58-157) of one full-size
+    window, assembled and solved by HiGHS (GUROBI is not installable here: no network, no licence).  milp=False: the LP
+    relaxation only -- the root node every MILP solve (GUROBI upstream) must at least pay, i.e. an optimistic estimate of
+    the reference's time; milp=True: the MILP at the reference's MIPGap 0.002 (MapSparsification.cc:155-156)."""
     from ms_slam_b200 import msgen
     from oracle import ilp_model as om
-    cfg = dict(msgen.CONFIGS["c2"])
-    cfg.update(K=ks, M=int(cfg["M"] * ks / C2_KF))
-    view = msgen.generate(seed=seed, **cfg)
+    view, N = msgen.make_config(workload, seed)
     t0 = time.perf_counter()
-    sol = om.solve_lp(view, cfg["N"], msgen.LAMBDA, msgen.GRID_LAMBDA)
+    if milp:
+        sol = om.solve_ilp(view, N, msgen.LAMBDA, msgen.GRID_LAMBDA, time_limit=time_limit)
+    else:
+        sol = om.solve_lp(view, N, msgen.LAMBDA, msgen.GRID_LAMBDA)
     dt = time.perf_counter() - t0
     return dt, sol
 
 
 def _cpu_worker(args):
-    ks, seed = args
-    dt, sol = cpu_sample(ks, seed)
+    seed, workload = args
+    dt, sol = cpu_sample(seed, workload)
     return dt
 
 
-def cpu_parallel_step(pool, ks, seeds):
-    """One CPU step: len(seeds) independent windows solved concurrently, one process (= one HiGHS thread) per window --
-    the way a multi-core host would run the reference over independent windows.  Returns wall seconds."""
+def _cpu_milp_worker(args):
+    seed, workload, limit = args
+    dt, sol = cpu_sample(seed, workload, milp=True, time_limit=limit)
+    return dict(workload=workload, seed=seed, seconds=dt, objective=float(sol.objective), status=int(sol.status),
+                mip_gap=None if sol.mip_gap is None else float(sol.mip_gap), time_limit_s=limit)
+
+
+def cpu_parallel_step(pool, seeds, workload="c2"):
+    """One CPU step: len(seeds) independent full-size windows solved concurrently, one process (= one HiGHS thread) per
+    window -- the way a multi-core host would run the reference over independent windows.  Returns wall seconds."""
     t0 = time.perf_counter()
-    list(pool.map(_cpu_worker, [(ks, s) for s in seeds]))
+    list(pool.map(_cpu_worker, [(s, workload) for s in seeds]))
     return time.perf_counter() - t0
 
 
@@ -174,40 +183,48 @@ def _cpu_pool():
 
 
 def cpu_baseline_leg():
-    """Bounded CPU sample next to the GPU number: every host core solves one full c2 window (LP relaxation of the
-    reference's model, see cpu_sample) at the same time."""
+    """Bounded CPU sample next to the GPU number: every host core solves one full c2 window (500 KF x 200k MP; LP relaxation
+    of the reference's model, see cpu_sample) at the same time; plus ONE MILP datapoint -- what GUROBI actually does
+    (MapSparsification.cc:153-157) -- on an EuRoC-shaped c3 window (100 KF x 30k MP) under a time limit."""
     pool, procs = _cpu_pool()
     with pool:
-        cpu_parallel_step(pool, 20, range(procs))                       # start the workers (imports, HiGHS start-up)
-        dt = cpu_parallel_step(pool, C2_KF, [12345 + i for i in range(procs)])
+        cpu_parallel_step(pool, range(procs), "c1")                     # start the workers (imports, HiGHS start-up)
+        milp_f = pool.submit(_cpu_milp_worker, (0, "c3", 100.0))        # alone first: its time is not shared with the LP step
+        try:
+            milp = milp_f.result(timeout=400)
+        except Exception as e:      # noqa: BLE001
+            milp = {"error": repr(e)}
+        dt = cpu_parallel_step(pool, [12345 + i for i in range(procs)], "c2")
     return {"value": procs / dt, "unit": UNIT, "cores": procs, "kind": "port",
             "sample": f"{procs} c2 windows of 500 KF x 200000 MP solved concurrently, one process per core: assemble + HiGHS LP "
                       f"relaxation only ({dt:.1f} s wall; the reference's GUROBI MILP at MIPGap 0.002 costs at least its root LP)",
-            "seconds": dt}
+            "seconds": dt,
+            "milp_datapoint": dict(milp, note="HiGHS MILP at the reference's MIPGap 0.002 on ONE c3 window (100 KF x 30k MP), one core; "
+                                              "the same solve at c2 size does not finish within minutes")}
 
 
 def reference_arm(args, rank):
+    """--impl reference: the reference's CPU algorithm on the stated config (full 500 KF x 200k MP windows, not scaled):
+    each step solves one window per host core concurrently."""
     if rank != 0:
         return 0
-    budget = 150.0
-    per_step = budget / max(args.steps, 1)
-    ks = int(min(C2_KF, max(20, per_step / 0.030)))           # ~30 ms per keyframe of LP time with every core busy
     pool, procs = _cpu_pool()
     times = []
     with pool:
         for w in range(max(args.warmup, 1)):
-            cpu_parallel_step(pool, 20, range(procs))          # warm-up: worker start, imports, HiGHS start-up
+            cpu_parallel_step(pool, range(procs), "c1")        # warm-up: worker start, imports, HiGHS start-up
         for s in range(args.steps):
-            times.append(cpu_parallel_step(pool, ks, [777 + 1000 * s + i for i in range(procs)]))
+            times.append(cpu_parallel_step(pool, [777 + 1000 * s + i for i in range(procs)], "c2"))
     total = float(np.sum(times))
-    value = procs * (ks / C2_KF) * args.steps / total
-    sample = (f"each step: {procs} c2-shaped windows of {ks} KF x {int(200000*ks/C2_KF)} MP solved concurrently (one process per "
-              f"core), assemble + HiGHS LP relaxation, scaled by {ks}/{C2_KF}")
+    value = procs * args.steps / total
+    sample = (f"each step: {procs} full c2 windows (500 KF x 200000 MP) solved concurrently (one process per core), assemble + HiGHS "
+              f"LP relaxation of the reference's ILP")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: KITTI-00-shaped window, msgen-v1", "sample_keyframes": ks, "windows_per_step": procs,
-                       "note": "HiGHS stand-in for GUROBI (not installable: no network/licence); LP relaxation only = optimistic"},
+            "config": {"workload": f"{WORKLOAD}: 500 KF x 200000 MP KITTI-00-shaped windows, msgen-v1", "windows_per_step": procs,
+                       "note": "HiGHS stand-in for GUROBI (not installable: no network/licence); LP relaxation only = optimistic "
+                               "(a lower bound of the reference's MILP time)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -216,6 +233,183 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------------
+def numa_bind(local_rank):
+    """Pin this process to the CPUs next to its GPU before any pinned allocation, so the pinned blobs land on the GPU's NUMA
+    node (first touch) and the N ranks of a box do not pull their H2D traffic through one socket.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to GPU {local_rank}"
+    except Exception as e:      # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+    return "not bound (single node)"
+
+
+class Batch:
+    """B windows per GPU of one workload, in both memory kinds, with the ctypes arrays of one mss_solve_batch call."""
+
+    def __init__(self, eng, E, workload, B, world, rank, layout="packed16", order="discovery", unsorted=False, host_arm=True):
+        from concurrent.futures import ThreadPoolExecutor
+        from ms_slam_b200 import msgen, dist as msd
+        from ms_slam_b200.window import pack_view
+        self.eng, self.E, self.workload = eng, E, workload
+        cfg = msgen.CONFIGS[workload]
+        self.cfg, self.N = cfg, cfg["N"]
+        self.nwin = B * world
+        self.mine = msd.local_windows(self.nwin, rank, world)
+
+        def make(w):
+            # transport form: what the C++ FlattenWindow emits (empty slots and window-keyframe observations left out; the
+            # window, the model and the result are the same -- tests/test_gpu_parity.py::test_compact_view_same_result)
+            v = msgen.make_config(workload, seed=w)[0].compact()
+            v = v.discovery_order() if order == "discovery" else v
+            if layout == "packed16":
+                return pack_view(v, tokens16=True)
+            return pack_view(v, sort_slots=not unsorted) if layout == "packed" else v
+        self.make = make
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:   # numpy releases the GIL in the heavy parts
+            self.views = dict(zip(self.mine, pool.map(make, self.mine)))
+        K, H, M = cfg["K"], cfg["H"], cfg["M"]
+        self.K, self.H, self.M = K, H, M
+        self.words, self.rows = (M + 31) // 32, K + H
+        self.in_bytes = sum(v.input_bytes() for v in self.views.values())
+        nwin = self.nwin
+        self.pins = []
+        # ---- `value` arm: views resident in HBM; the keep bitmask (+ row coverage) of every OWNED window comes back to a
+        #      pinned host buffer inside the timed call (SURVEY 8d); windows of other ranks: header only, their bitmasks
+        #      stay in the all-gathered device buffer
+        self.dviews = {w: E.DeviceView(eng, self.views[w]) for w in self.mine}
+        self.cv = (E.mss_window_view * nwin)()
+        self.cr = (E.mss_result * nwin)()
+        self.keep_dev_arm = {}
+        for w in range(nwin):
+            if w in self.dviews:
+                self.cv[w] = self.dviews[w].c_view()
+                self.cv[w].result_memory = E.RESULT_HOST
+                kb = self.pin_zeros(self.words, np.uint32)
+                self.keep_dev_arm[w] = kb
+                self.cr[w].keep_bits = kb.ctypes.data
+            else:
+                self.cv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
+        # ---- `e2e` arm: pinned host blobs in, pinned host results out (owned windows)
+        self.hv = (E.mss_window_view * nwin)()
+        self.hr = (E.mss_result * nwin)()
+        self.keep_host_arm = {}
+        for w in range(nwin):
+            if w in self.views and host_arm:
+                v = self.views[w]
+                if layout in ("packed", "packed16"):
+                    self.hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
+                                                 *self.pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]),
+                                                 tokens16=layout == "packed16")
+                else:
+                    self.hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
+                                                   *self.pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr,
+                                                                   v.mp_obs_kf, v.okf_total]))
+                kb = self.pin_zeros(self.words, np.uint32)
+                self.keep_host_arm[w] = kb
+                self.hr[w].keep_bits = kb.ctypes.data
+                self.hr[w].kf_cov = self.pin_zeros(self.rows, np.int32).ctypes.data
+                self.hr[w].kf_slack = self.pin_zeros(self.rows, np.int32).ctypes.data
+            else:
+                self.hv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
+
+    def pin_zeros(self, n, dtype):
+        p = self.eng.pinned((max(n, 1),), dtype)
+        p.array[...] = 0
+        self.pins.append(p)
+        return p.array
+
+    def pin_blob(self, arrays):
+        """one pinned blob per window, arrays back to back at 16-byte boundaries (what FlattenWindow lays out): the engine
+        moves such a view with a single copy"""
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 15) // 16 * 16
+        p = self.eng.pinned((max(total, 16),), np.uint8)
+        self.pins.append(p)
+        for a, o in zip(arrays, offs):
+            p.array[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+        return [p.array.ctypes.data + o for o in offs]
+
+    def free(self):
+        for d in self.dviews.values():
+            d.free()
+        for p in self.pins:
+            p.free()
+        self.dviews, self.pins = {}, []
+
+
+def roofline_of(batch, kern_ms, st, peak):
+    """roofline numbers of one launch of the persistent kernel over `batch` (this rank's windows)"""
+    views, cr, mine = batch.views, batch.cr, batch.mine
+    fb = sum(view_floor_bytes(v) for v in views.values())
+    sb = sum(survey_alg_bytes(views[w].K, views[w].H, views[w].M, views[w].F, views[w].O, cr[w].nnz, cr[w].n_cells, cr[w].rounds)
+             for w in mine)
+    s0 = sum(survey_alg_bytes(views[w].K, views[w].H, views[w].M, views[w].F, views[w].O, cr[w].nnz, cr[w].n_cells, 0) for w in mine)
+    ab = kernel_alg_bytes([views[w] for w in mine], [cr[w] for w in mine], st["last_row_entries"], st["last_var_visits"])
+    sec = kern_ms * 1e-3
+    rounds = [int(cr[w].rounds) for w in mine]
+    return {"bound": "hbm", "achieved": ab / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": ab / sec / 1e9 / peak,
+            "traffic": None, "kernel": "mss_persistent_kernel", "kernel_ms": kern_ms, "windows_per_launch": len(mine),
+            "alg_bytes_per_launch": ab,
+            "alg_bytes_definition": "DESIGN.md section 4 (lower bound of what THIS kernel moves): views read once + outside "
+                                    "observations streamed twice + 39 B/map point + 12 B/incidence (build) + 5 B per entry read by "
+                                    f"later row phases ({int(st['last_row_entries'])} entries, device counter) + 17 B per later "
+                                    f"variable visit ({int(st['last_var_visits'])}) + result slots",
+            "survey_floor_I0": {"bytes_per_launch": s0, "achieved": s0 / sec / 1e9, "frac": s0 / sec / 1e9 / peak,
+                                "ms_at_peak": s0 / (peak * 1e9) * 1e3,
+                                "definition": "SURVEY 8(d) ALG_BYTES(I=0) = B_build + 3*B_iter + B_out: the solver-independent "
+                                              "compulsory traffic of build + round/repair/verify; comparable across rounds"},
+            "survey_formula": {"bytes_per_launch": sb, "achieved": sb / sec / 1e9,
+                               "definition": "SURVEY 8(d) planning formula B_build + (I+3)*B_iter + B_out with I = rounds executed "
+                                             f"(mean {float(np.mean(rounds)):.1f}, max {max(rounds)}); it assumes every round "
+                                             "streams the whole CSR, which this work-efficient kernel does not do"},
+            "io_floor": {"bytes_per_launch": fb, "achieved": fb / sec / 1e9, "frac": fb / sec / 1e9 / peak,
+                         "definition": "every view read once + result slots written once"}}
+
+
+def host_api_leg(N, lam, glam):
+    """What the reference-facing C++ API costs around the solve: ORB_SLAM3::MapSparsification (libmss_host.so) over a
+    c2-sized final flush and over a live 30-keyframe window driven through Run(): flatten_ms (pointer graph -> view, host),
+    solve_ms (C-ABI call incl. copies), apply_ms (SetBadFlag fan-out + forwarding, host)."""
+    from ms_slam_b200 import msgen
+    from ms_slam_b200.host_mirror import World
+    out = {}
+    for label, name, seed, kw in (("c2_flush", "c2", 0, {}), ("live_window", "live", 0, dict(window_length=30))):
+        try:
+            view, Nw = msgen.make_config(name, seed)
+            w = World(view, N=Nw, lam=lam, grid_lam=glam, **kw)
+            w.start()
+            if label == "live_window":
+                w.feed(0, view.K)                   # LocalMapping's hook: > 10 queued keyframes trigger a window
+                w.wait_forwarded(view.K, 60000)
+            w.finish(120000)
+            reps = w.reports()
+            r = max(reps, key=lambda x: x["M"]) if reps else {}
+            out[label] = {k: r.get(k) for k in ("K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "components", "flatten_ms",
+                                                "solve_ms", "apply_ms", "status")}
+            out[label]["mirror"] = w.mirror_report() if hasattr(w, "mirror_report") else None
+            w.close()
+        except Exception as e:      # noqa: BLE001
+            out[label] = {"error": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +420,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip latency / host-API / c3 / c5 sub-entries (N=1, rank 0)")
     ap.add_argument("--order", default="discovery", choices=["generated", "discovery"],
                     help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
                          "(mnIndexForSparsification, MapSparsification.cc:91-99) or as msgen draws them (random)")
@@ -245,11 +440,11 @@ def main():
     import torch.distributed as dist
     from ms_slam_b200 import msgen, dist as msd
     from ms_slam_b200 import engine as E
-    from ms_slam_b200.window import pack_view
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = numa_bind(local_rank) if world > 1 else "single process"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -262,77 +457,8 @@ def main():
         eng.comm_init(uid, rank, world)
 
     B = args.batch
-    nwin = B * world
-    mine = msd.local_windows(nwin, rank, world)
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # numpy releases the GIL in the heavy parts
-        # transport form: what the C++ FlattenWindow emits (empty slots and window-keyframe observations left out; the
-        # window, the model and the result are the same -- tests/test_gpu_parity.py::test_compact_view_same_result)
-        def make(w):
-            v = msgen.make_config(args.workload, seed=w)[0].compact()
-            v = v.discovery_order() if args.order == "discovery" else v
-            if args.layout == "packed16":
-                return pack_view(v, tokens16=True)
-            return pack_view(v, sort_slots=not args.unsorted_slots) if args.layout == "packed" else v
-        views = dict(zip(mine, pool.map(make, mine)))
-    K, H, M = cfg["K"], cfg["H"], cfg["M"]
-    words, rows = (M + 31) // 32, K + H
-    in_bytes = sum(v.input_bytes() for v in views.values())
-
-    # ---- device-resident arm (value) -------------------------------------------------------------------------------------
-    dviews = {w: E.DeviceView(eng, views[w]) for w in mine}
-    cv = (E.mss_window_view * nwin)()
-    cr = (E.mss_result * nwin)()
-    host_keep = {}
-    for w in range(nwin):
-        if w in dviews:
-            d = dviews[w]
-            cv[w] = d.c_view()
-            cr[w].keep_bits, cr[w].kf_cov, cr[w].kf_slack = d.d_keep, d.d_cov, d.d_slack
-        else:
-            # a window of another rank: its bitmask arrives in the all-gathered device buffer; no host array is asked for
-            # in this arm (results stay in HBM like the inputs), only the header (status, counters) comes back
-            cv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
-    # ---- host arm (e2e): pinned views + pinned results --------------------------------------------------------------------
-    pins = []
-    hv = (E.mss_window_view * nwin)()
-    hr = (E.mss_result * nwin)()
-
-    def pin(a):
-        p = eng.pinned(a.shape, a.dtype)
-        p.array[...] = a
-        pins.append(p)
-        return p.array.ctypes.data
-
-    def pin_blob(arrays):
-        """one pinned blob per window, arrays back to back at 16-byte boundaries (what FlattenWindow lays out): the engine
-        moves such a view with a single copy"""
-        offs, total = [], 0
-        for a in arrays:
-            offs.append(total)
-            total += (a.nbytes + 15) // 16 * 16
-        p = eng.pinned((max(total, 16),), np.uint8)
-        pins.append(p)
-        for a, o in zip(arrays, offs):
-            p.array[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
-        return [p.array.ctypes.data + o for o in offs]
-
-    for w in range(nwin):
-        if w in views and not args.no_e2e:
-            v = views[w]
-            if args.layout in ("packed", "packed16"):
-                hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
-                                        *pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]),
-                                        tokens16=args.layout == "packed16")
-            else:
-                hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
-                                          *pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr, v.mp_obs_kf, v.okf_total]))
-        else:
-            hv[w] = E.mss_window_view(K, H, M, 0, 0, E.MEM_HOST)
-        hr[w].keep_bits = pin(np.zeros(words, np.uint32))
-        hr[w].kf_cov = pin(np.zeros(rows, np.int32))
-        hr[w].kf_slack = pin(np.zeros(rows, np.int32))
-
+    batch = Batch(eng, E, args.workload, B, world, rank, args.layout, args.order, args.unsorted_slots, host_arm=not args.no_e2e)
+    nwin, mine, views, K, H, M = batch.nwin, batch.mine, batch.views, batch.K, batch.H, batch.M
     stream = torch.cuda.ExternalStream(eng.lib.mss_stream(eng.handle), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -340,56 +466,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(cviews, cres, steps, warmup):
+    def run(cviews, cres, steps, warmup, n=None, e=None, stream=stream):
+        e, n = e or eng, n or nwin
         for _ in range(warmup):
-            rc = eng.solve_batch_raw(cviews, cres, nwin)
-            assert rc == 0, eng.lib.mss_last_error(eng.handle)
+            rc = e.solve_batch_raw(cviews, cres, n)
+            assert rc == 0, e.lib.mss_last_error(e.handle)
         barrier()
-        l0 = eng.stats()["kernel_launches"]
+        l0 = e.stats()["kernel_launches"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kern_ms = []
         e0.record(stream)
         for _ in range(steps):
-            rc = eng.solve_batch_raw(cviews, cres, nwin)
-            kern_ms.append(eng.stats()["last_device_ms"])
+            rc = e.solve_batch_raw(cviews, cres, n)
+            kern_ms.append(e.stats()["last_device_ms"])
         e1.record(stream)
         barrier()
-        assert rc == 0, eng.lib.mss_last_error(eng.handle)
+        assert rc == 0, e.lib.mss_last_error(e.handle)
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, float(np.mean(kern_ms)), eng.stats()["kernel_launches"] - l0
+        return ms, float(np.mean(kern_ms)), e.stats()["kernel_launches"] - l0
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, kern_ms, launches = run(cv, cr, args.steps, args.warmup)
+    ms_dev, kern_ms, launches = run(batch.cv, batch.cr, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     st_dev = eng.stats()
     e2e = None
     if not args.no_e2e:
-        ms_host, _, _ = run(hv, hr, args.steps, args.warmup)
+        ms_host, _, _ = run(batch.hv, batch.hr, args.steps, args.warmup)
         st_host = eng.stats()
         e2e = {"value": nwin * args.steps / (ms_host * 1e-3), "unit": UNIT, "ms_per_step": ms_host / args.steps,
-               "h2d_bytes_per_step": int(st_host["last_h2d_bytes"]), "d2h_bytes_per_step": int(st_host["last_d2h_bytes"])}
+               "h2d_bytes_per_step": int(st_host["last_h2d_bytes"]), "d2h_bytes_per_step": int(st_host["last_d2h_bytes"]),
+               "what": "mss_solve_batch with one pinned host blob per window in, pinned host keep bits + row coverage of the "
+                       "owned windows out; copies inside the timed call"}
 
-    # ---- sanity of what was timed: every owned window solved, rows satisfied (cheap device-reported counters) --------------
+    # ---- what was timed is right: every owned window solved; both arms returned the same bitmask -----------------------
+    cr = batch.cr
     for w in mine:
         assert cr[w].status == 0 and cr[w].n_kept > 0 and cr[w].rounds > 0
+        if not args.no_e2e:
+            assert np.array_equal(batch.keep_dev_arm[w], batch.keep_host_arm[w]), f"window {w}: device-view and host-view arms differ"
     r0 = cr[mine[0]]
     quality = {"objective_w0": r0.objective, "kept_w0": r0.n_kept, "vars_w0": r0.n_vars, "rounds_w0": r0.rounds}
 
+    # ---- cross-rank parity: the all-gathered bitmasks of windows solved by OTHER ranks, fetched to the host in one extra call,
+    #      against a local re-solve of the same windows on this GPU without a communicator (>= 8 foreign windows per rank)
+    cross = None
+    if world > 1:
+        av = (E.mss_window_view * nwin)()
+        ar = (E.mss_result * nwin)()
+        keep_all = {}
+        for w in range(nwin):
+            av[w] = batch.cv[w]
+            if w not in batch.dviews:
+                av[w].result_memory = E.RESULT_HOST
+            keep_all[w] = batch.pin_zeros(batch.words, np.uint32)
+            ar[w].keep_bits = keep_all[w].ctypes.data
+        rc = eng.solve_batch_raw(av, ar, nwin)
+        assert rc == 0, eng.lib.mss_last_error(eng.handle)
+        foreign = [w for w in range(nwin) if w not in batch.dviews]
+        pick = foreign[rank::max(1, len(foreign) // 8)][:8] if foreign else []
+        solo = E.Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+        ok = True
+        for w in pick:
+            r = solo.solve(batch.make(w))
+            ok = ok and np.array_equal(r.keep_bits, keep_all[w]) and r.objective == ar[w].objective and r.n_kept == ar[w].n_kept
+        for w in mine:
+            ok = ok and np.array_equal(keep_all[w], batch.keep_dev_arm[w])
+        solo.close()
+        flag = torch.tensor([1 if ok else 0, len(pick)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        cross = bool(flag[0].item())
+        if not cross:
+            raise SystemExit(f"bench.py: rank {rank}: an all-gathered bitmask differs from the local re-solve")
+        cross_n = int(flag[1].item())
+
     if rank == 0:
         peak, peak_src = peaks()
-        fb = sum(view_floor_bytes(v) for v in views.values())       # per launch on this rank
-        sb = sum(survey_alg_bytes(views[w].K, views[w].H, views[w].M, views[w].F, views[w].O, cr[w].nnz, cr[w].n_cells, cr[w].rounds)
-                 for w in mine)
-        ab = kernel_alg_bytes([views[w] for w in mine], [cr[w] for w in mine], st_dev["last_row_entries"], st_dev["last_var_visits"])
-        achieved = ab / (kern_ms * 1e-3) / 1e9
-        floor_achieved = fb / (kern_ms * 1e-3) / 1e9
-        rounds = [int(cr[w].rounds) for w in mine]
+        roof = roofline_of(batch, kern_ms, st_dev, peak)
+        roof["peak_source"] = peak_src
+        roof["note"] = ("the solve is bound by dependent latency (spread-address state gathers and 64-bit reductions per undecided "
+                        "entry per round, block and group barriers), not by DRAM bandwidth; `traffic` is the ncu dram read+write "
+                        "of the same launch (profiles/)")
         line = {
             "metric": METRIC, "value": nwin * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -401,35 +563,61 @@ def main():
                        "windows_per_gpu_per_step": B, "global_windows_per_step": nwin,
                        "N": N, "lambda": msgen.LAMBDA, "grid_lambda": msgen.GRID_LAMBDA,
                        "parallelism": f"window w -> rank w % {world}; one NCCL all-gather of result slots" if world > 1 else "single GPU",
-                       "l2": f"per-step inputs {in_bytes/1e6:.0f} MB per GPU > 126 MB L2: no flush needed" if in_bytes > 126e6
-                             else f"per-step inputs {in_bytes/1e6:.0f} MB per GPU (< L2)",
-                       "kernel_ms_per_step": kern_ms, "grid_ctas": st_dev["grid_ctas"], "quality": quality},
+                       "value_includes": "views resident in HBM; D2H of the owned windows' keep bitmask + row coverage inside the timed call",
+                       "l2": f"per-step inputs {batch.in_bytes/1e6:.0f} MB per GPU > 126 MB L2: no flush needed" if batch.in_bytes > 126e6
+                             else f"per-step inputs {batch.in_bytes/1e6:.0f} MB per GPU (< L2)",
+                       "kernel_ms_per_step": kern_ms, "grid_ctas": st_dev["grid_ctas"], "quality": quality, "numa": numa},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mss_persistent_kernel",
-                         "alg_bytes_per_launch": ab,
-                         "alg_bytes_definition": "DESIGN.md section 5 (lower bound): views read once + observations streamed twice + "
-                                                 "39 B/map point + 12 B/incidence (build) + 5 B per entry read by later row phases "
-                                                 f"({int(st_dev['last_row_entries'])} entries, device counter) + 17 B per later variable "
-                                                 f"visit ({int(st_dev['last_var_visits'])}) + result slots",
-                         "survey_formula": {"bytes_per_launch": sb, "achieved": sb / (kern_ms * 1e-3) / 1e9,
-                                            "definition": "SURVEY 8(d) planning formula B_build + (I+3)*B_iter + B_out with I = rounds executed "
-                                                          f"(mean {float(np.mean(rounds)):.1f}, max {max(rounds)}); it assumes every round "
-                                                          "streams the whole CSR, which this kernel does not do"},
-                         "floor": {"bytes_per_launch": fb, "achieved": floor_achieved, "frac": floor_achieved / peak,
-                                   "definition": "solver-independent: every view read once + result slots written once"},
-                         "note": "the solve is bound by spread-address LSU operations (one state gather + one 64-bit reduction "
-                                 "per undecided entry per round) and by per-window round latency, not by DRAM bandwidth; "
-                                 "`traffic` is the ncu dram read+write of the same launch (profiles/)"},
+            "roofline": roof,
         }
+        if cross is not None:
+            line["cross_rank_parity"] = cross
+            line["cross_rank_windows_checked_per_rank"] = cross_n
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
                 line["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 pass
+        if world == 1 and not args.no_extras:
+            # ---- single-window latency (what the live SLAM thread sees): device-resident view, kernel time of one launch ----
+            lat = {}
+            for name in ("c2", "live"):
+                from ms_slam_b200.window import pack_view
+                vv = pack_view(msgen.make_config(name, 0)[0].compact().discovery_order(), tokens16=True)
+                e1 = E.Engine(N=msgen.CONFIGS[name]["N"], lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+                dv = E.DeviceView(e1, vv)
+                ks, hs = [], []
+                for i in range(25):
+                    t0 = time.perf_counter()
+                    e1.solve(dv)
+                    hs.append((time.perf_counter() - t0) * 1e3)
+                    ks.append(e1.stats()["last_device_ms"])
+                lat[name] = {"kernel_us_median": float(np.median(ks[5:]) * 1e3), "call_us_median": float(np.median(hs[5:]) * 1e3),
+                             "grid_ctas": e1.stats()["grid_ctas"]}
+                dv.free(); e1.close()
+            line["single_window_latency"] = lat
+            # ---- the other single-GPU configs: roofline sub-entries (c3 EuRoC-shaped; c5 4Seasons-shaped, HBM-bound) ----------
+            batch.free()
+            sub = {}
+            for name, nb, steps in (("c3", 512, 10), ("c5", 16, 5)):
+                try:
+                    e1 = E.Engine(N=msgen.CONFIGS[name]["N"], lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+                    b1 = Batch(e1, E, name, nb, 1, 0, args.layout, args.order, args.unsorted_slots, host_arm=False)
+                    s1 = torch.cuda.ExternalStream(e1.lib.mss_stream(e1.handle), device=torch.device("cuda", local_rank))
+                    ms1, k1, _ = run(b1.cv, b1.cr, steps, 3, n=b1.nwin, e=e1, stream=s1)
+                    r1 = roofline_of(b1, k1, e1.stats(), peak)
+                    sub[name] = {"windows_per_s": b1.nwin * steps / (ms1 * 1e-3), "ms_per_step": ms1 / steps, "windows_per_step": b1.nwin,
+                                 "inputs_mb_per_step": b1.in_bytes / 1e6,
+                                 "roofline": {k: r1[k] for k in ("achieved", "frac", "kernel_ms", "alg_bytes_per_launch", "survey_floor_I0", "io_floor")}}
+                    b1.free(); e1.close()
+                except Exception as e:      # noqa: BLE001
+                    sub[name] = {"error": repr(e)}
+            line["other_configs"] = sub
+            # ---- the reference-facing C++ API around the solve -----------------------------------------------------------------
+            line["host_api"] = host_api_leg(N, msgen.LAMBDA, msgen.GRID_LAMBDA)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)

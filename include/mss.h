@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define MSS_VERSION 130            /* 0.1.3: packed transport layouts (u32 slots / u16 tokens + pair list), components */
+#define MSS_VERSION 200            /* 0.2.0: result_memory, persistent device mirror (mss_mirror_*), keyframe compaction,
+                                      single-process multi-device handles; 0.1.3: packed transport layouts, components */
 
 #define MSS_GRID_COLS 64           /* FRAME_GRID_COLS, /root/reference/include/Frame.h:45 */
 #define MSS_GRID_ROWS 48           /* FRAME_GRID_ROWS, /root/reference/include/Frame.h:44 */
@@ -49,6 +50,13 @@ typedef enum mss_memory {
 
 /* How a view's arrays are encoded.  SOA is the plain form; PACKED is the transport form for views that travel over
  * PCIe every call (about 0.6x the bytes): FlattenWindow can emit either at the same host cost. */
+/* Where the result arrays of a window live (mss_window_view::result_memory). */
+typedef enum mss_result_memory {
+    MSS_RESULT_SAME = 0,     /* same kind as the view's arrays (the default of a zero-initialised view) */
+    MSS_RESULT_HOST = 1,     /* host buffers although the view is device-resident: "inputs in HBM, bitmask back to the host" */
+    MSS_RESULT_DEVICE = 2    /* device buffers although the view travels from the host */
+} mss_result_memory;
+
 typedef enum mss_layout {
     MSS_LAYOUT_SOA = 0,      /* feat_mp i32 + feat_cell u16, mp_nobs i32, mp_obs_kf i32 */
     MSS_LAYOUT_PACKED = 1,   /* slots u32 = (map point << 12) | cell, mp_nobs16 u16, obs_pairs u32 = (map point << 12) | outside kf */
@@ -112,9 +120,12 @@ typedef struct mss_window_view {
     const uint16_t* slots16;   /* [F]   tokens */
     const uint32_t* obs_pairs; /* [O]   observations of the window's map points by OUTSIDE keyframes only, in any order:
                                         (map-point table index << 12) | j, j = 0..H-1 the outside keyframe (KF-table index K + j) */
+    int32_t result_memory;     /* mss_result_memory of keep_bits / kf_cov / kf_slack of this window's mss_result */
+    int32_t reserved_;         /* 0 */
 } mss_window_view;
 
-/* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view) or NULL. */
+/* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view unless the view's
+ * result_memory says otherwise) or NULL. */
 typedef struct mss_result {
     uint32_t* keep_bits;       /* [(M+31)/32] bit p = 1 keep map point p, 0 = SetBadFlag() it (MapSparsification.cc:162-165);
                                   map points that are not variables of the window are always 1 */

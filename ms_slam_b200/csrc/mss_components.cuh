@@ -55,7 +55,7 @@ __global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, un
     const int R = D.K + D.H;
     int nmax = 0;
     for (int k = blockIdx.x; k < D.K; k += gridDim.x) {
-        const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
+        const int beg = ldv(D.feat_ptr + k), end = ldv(D.feat_ptr + k + 1);
         if (beg < 0 || end < beg || end > D.F) { if (threadIdx.x == 0) atomicOr(err, ERR_PTR); continue; }
         if (D.packed == 2) {
             // 16-bit tokens: the map-point index is a running sum over the keyframe's tokens (block scan per chunk)
@@ -71,7 +71,7 @@ __global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, un
                 int adv = 0;
                 bool slot = false;
                 unsigned c = kCellNone;
-                if (i < end) adv = tok_decode(__ldg(tk + i), slot, c);
+                if (i < end) adv = tok_decode(ldv(tk + i), slot, c);
                 int x = adv;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -87,7 +87,7 @@ __global__ void cc_slots_kernel(const WinDesc D, int* parent, uint8_t* isvar, un
                 if (threadIdx.x == 0) s_carry += tot;
                 __syncthreads();
                 if (!slot) continue;
-                if (mp >= D.M) { atomicOr(err, ERR_INDEX); continue; }
+                if ((unsigned)mp >= (unsigned)D.M) { atomicOr(err, ERR_INDEX); continue; }     // (a wrapped running index is negative)
                 nmax = max(nmax, ld_nobs(D, mp));
                 if (c == kCellNone) continue;
                 if (c >= (unsigned)kCells) { atomicOr(err, ERR_INDEX); continue; }
@@ -118,7 +118,7 @@ __global__ void cc_pairs_kernel(const WinDesc D, int* parent, const uint8_t* isv
     const int R = D.K + D.H;
     const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < D.O; o += gridDim.x * blockDim.x) {
-        const uint32_t pr = __ldg(pairs + o);
+        const uint32_t pr = ldv(pairs + o);
         const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
         if (mp >= D.M || j >= D.H) { atomicOr(err, ERR_INDEX); continue; }
         if (isvar[mp]) cc_union(parent, D.K + j, R + mp);
@@ -130,7 +130,7 @@ __global__ void cc_outside_kernel(const WinDesc D, int* parent, const uint8_t* i
     const int R = D.K + D.H;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.M || !isvar[p]) return;
-    const int beg = __ldg(D.mp_obs_ptr + p), end = __ldg(D.mp_obs_ptr + p + 1);
+    const int beg = ldv(D.mp_obs_ptr + p), end = ldv(D.mp_obs_ptr + p + 1);
     if (beg < 0 || end < beg || end > D.O) { atomicOr(err, ERR_PTR); return; }
     for (int o = beg; o < end; ++o) {
         const int kf = ld_obs_kf(D, o);

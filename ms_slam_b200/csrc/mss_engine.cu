@@ -20,7 +20,6 @@
 
 namespace {
 
-constexpr int kMaxChunks = 8;
 using mss::Ctrl;
 using mss::Params;
 using mss::WinDesc;
@@ -173,6 +172,11 @@ inline const void* slots_ptr(const mss_window_view& v) {
 inline size_t slots_bytes(const mss_window_view& v) { return (size_t)v.F * (v.layout == MSS_LAYOUT_PACKED16 ? 2 : 4); }
 inline int packed_code(const mss_window_view& v) { return v.layout == MSS_LAYOUT_PACKED16 ? 2 : v.layout == MSS_LAYOUT_PACKED ? 1 : 0; }
 
+// where a window's result arrays live: by default where its view lives; mss_window_view::result_memory overrides
+inline bool res_on_device(const mss_window_view& v) {
+    return v.result_memory == MSS_RESULT_DEVICE || (v.result_memory == MSS_RESULT_SAME && v.memory == MSS_MEM_DEVICE);
+}
+
 struct SlotLayout { int words_keep, rows, total; };
 inline SlotLayout slot_of(const mss_window_view& v) {
     SlotLayout s;
@@ -207,6 +211,7 @@ int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
     if (!owned) return MSS_OK;
     if (v.F < 0 || v.O < 0) { h->err = "view: negative F/O"; return MSS_E_BADARG; }
     if (v.memory != MSS_MEM_HOST && v.memory != MSS_MEM_DEVICE) { h->err = "view: bad memory kind"; return MSS_E_BADARG; }
+    if (v.result_memory != MSS_RESULT_SAME && v.result_memory != MSS_RESULT_HOST && v.result_memory != MSS_RESULT_DEVICE) { h->err = "view: bad result_memory"; return MSS_E_BADARG; }
     if (v.layout != MSS_LAYOUT_SOA && v.layout != MSS_LAYOUT_PACKED && v.layout != MSS_LAYOUT_PACKED16) { h->err = "view: bad layout"; return MSS_E_BADARG; }
     const bool pkv = v.layout != MSS_LAYOUT_SOA;
     const void* pk_slots = v.layout == MSS_LAYOUT_PACKED16 ? (const void*)v.slots16 : (const void*)v.slots;
@@ -236,11 +241,24 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     std::vector<int> local;                 // windows solved on this rank
     std::vector<int> out_off(nwin, 0);
     int slot_stride = 0;
+    std::vector<int> rejected;              // owned windows whose view failed host-side validation (multi-rank only)
+    std::string first_reject;
     for (int w = 0; w < nwin; ++w) {
         const bool owned = (w % nranks) == rank;
-        const int rc = validate_view(h, views[w], owned);
-        if (rc != MSS_OK) return rc;
-        if (owned) local.push_back(w);
+        int rc = validate_view(h, views[w], owned);
+        // size limits depend on K / H / M only, which every rank knows: all ranks fail alike, before anything collective
+        if (rc == MSS_OK && views[w].M > mss::kMaxWindowMps) { h->err = "view: more than 2^20 map points in one window"; return MSS_E_BADARG; }
+        if (rc == MSS_OK && views[w].K + views[w].H > mss::kMaxWindowRows) { h->err = "view: more than 65535 keyframe rows in one window"; return MSS_E_BADARG; }
+        if (rc != MSS_OK) {
+            // single rank: nothing has been started, fail the call.  With a communicator the other ranks are already on their
+            // way into the all-gather: this rank must follow, so the window is only left out (its slot stays unwritten and
+            // every rank reports MSS_E_BADARG for it, all map points kept).  Sizes must be sane on every rank, though.
+            if (nranks == 1 || !owned || views[w].K < 0 || views[w].H < 0 || views[w].M < 0) return rc;
+            rejected.push_back(w);
+            if (first_reject.empty()) first_reject = h->err;
+        } else if (owned) {
+            local.push_back(w);
+        }
         slot_stride = std::max(slot_stride, slot_of(views[w]).total);
     }
     const int spr = (nwin + nranks - 1) / nranks;          // slots per rank
@@ -256,11 +274,10 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     size_t stage_bytes = 0;
     for (int w : local) {
         const mss_window_view& v = views[w];
-        if (v.M > mss::kMaxWindowMps) { h->err = "view: more than 2^20 map points in one window"; return MSS_E_BADARG; }
-        if (v.K + v.H > mss::kMaxWindowRows) { h->err = "view: more than 65535 keyframe rows in one window"; return MSS_E_BADARG; }
         Ktot += v.K; Htot += v.H; Mpad += (long long)align_up((size_t)std::max(v.M, 1), mss::kVarTile); Ftot += v.F; Otot += v.O;
         if (v.memory == MSS_MEM_HOST) {
             const bool pk = v.layout != MSS_LAYOUT_SOA;
+            stage_bytes = align_up(stage_bytes, 128);     // a window's staging region starts on its own cache line (see `stage`)
             stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up(slots_bytes(v), 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
                            align_up((size_t)v.M * (pk ? 2 : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
                            align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16);
@@ -275,50 +292,44 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     bool any_host = false;
     for (int w : local) any_host = any_host || views[w].memory == MSS_MEM_HOST;
     const bool gated = any_host && h->overlap_copy && nl > 1;
-    const int nchunks = 1, csize = std::max(nl, 1);
-    // ---- groups (per chunk): the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest
-    //      first), so a group that draws a short solve simply takes the next window.  One window -> one group, whole grid. --
+    // ---- groups: the grid is cut into equal groups of CTAs; every group pulls windows from one queue (largest first), so a
+    //      group that draws a short solve simply takes the next window.  One window -> one group, whole grid. --------------
     const int max_grid = std::max(1, h->max_ctas_per_sm * h->sm_count);
     auto work = [&](int i) { const mss_window_view& v = views[local[i]]; return 1.0 + (double)v.F + (double)v.O + 0.25 * (double)v.M; };
-    struct Chunk { int first, count, gsize, ngroups, grid; size_t off_grp, off_cta, off_gwin, sync_off; std::vector<int> order; };
-    std::vector<Chunk> chunks(nchunks);
+    struct Plan { int gsize, ngroups, grid; size_t off_grp, off_cta, off_gwin; std::vector<int> order; } plan;
     size_t meta_bytes = align_up((size_t)std::max(nl, 1) * sizeof(WinDesc), 16), sync_words = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        Chunk& ch = chunks[c];
-        ch.first = c * csize;
-        ch.count = std::max(0, std::min(csize, nl - ch.first));
-        ch.order.resize(ch.count);
-        for (int i = 0; i < ch.count; ++i) ch.order[i] = ch.first + i;
-        std::stable_sort(ch.order.begin(), ch.order.end(), [&](int x, int y) { return work(x) > work(y); });
+    {
+        plan.order.resize(nl);
+        for (int i = 0; i < nl; ++i) plan.order[i] = i;
+        std::stable_sort(plan.order.begin(), plan.order.end(), [&](int x, int y) { return work(x) > work(y); });
         int cap = 1;        // a window cannot use more CTAs than it has rows or variable tiles
-        for (int i : ch.order) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
-        int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(ch.count, 1));
+        for (int i : plan.order) { const mss_window_view& v = views[local[i]]; cap = std::max(cap, std::max(v.K + v.H, (v.M + mss::kVarTile - 1) / mss::kVarTile)); }
+        int gsize = h->group_ctas > 0 ? h->group_ctas : std::max(16, max_grid / std::max(nl, 1));
         gsize = std::max(1, std::min(std::min(gsize, cap), max_grid));
-        int ngroups = std::max(1, std::min(std::max(ch.count, 1), max_grid / gsize));
-        if (h->group_ctas <= 0 && ch.count > ngroups) {
+        int ngroups = std::max(1, std::min(std::max(nl, 1), max_grid / gsize));
+        if (h->group_ctas <= 0 && nl > ngroups) {
             // several windows per group: even out the number of windows per group, then give the groups all the CTAs
-            const int waves = (ch.count + ngroups - 1) / ngroups;
-            ngroups = (ch.count + waves - 1) / waves;
+            const int waves = (nl + ngroups - 1) / ngroups;
+            ngroups = (nl + waves - 1) / waves;
             gsize = std::max(1, std::min(cap, max_grid / ngroups));
         }
-        ch.gsize = gsize;
-        ch.ngroups = ngroups;
-        ch.grid = ch.ngroups * ch.gsize;
-        ch.off_grp = meta_bytes;
-        ch.off_cta = ch.off_grp + align_up((size_t)ch.ngroups * sizeof(mss::GroupDesc), 16);
-        ch.off_gwin = ch.off_cta + align_up((size_t)ch.grid * 4, 16);
-        meta_bytes = ch.off_gwin + align_up((size_t)std::max(ch.count, 1) * 4, 16);
-        ch.sync_off = sync_words;
-        sync_words += 32 + (size_t)ch.ngroups * 32;
+        plan.gsize = gsize;
+        plan.ngroups = ngroups;
+        plan.grid = ngroups * gsize;
+        plan.off_grp = meta_bytes;
+        plan.off_cta = plan.off_grp + align_up((size_t)ngroups * sizeof(mss::GroupDesc), 16);
+        plan.off_gwin = plan.off_cta + align_up((size_t)plan.grid * 4, 16);
+        meta_bytes = plan.off_gwin + align_up((size_t)std::max(nl, 1) * 4, 16);
+        sync_words = 32 + (size_t)ngroups * 32;
     }
     const size_t ready_off = sync_words;
     sync_words += align_up((size_t)std::max(nl, 1), 32);
-    int grid = chunks[0].grid;
+    int grid = plan.grid;
 
     // result scatter table (device-resident result arrays), appended to the descriptor blob
     int n_dev_res = 0;
     for (int w = 0; w < nwin; ++w)
-        if (views[w].memory == MSS_MEM_DEVICE && (results[w].keep_bits || results[w].kf_cov || results[w].kf_slack)) ++n_dev_res;
+        if (res_on_device(views[w]) && (results[w].keep_bits || results[w].kf_cov || results[w].kf_slack)) ++n_dev_res;
     const size_t off_res = meta_bytes;
     meta_bytes += align_up((size_t)std::max(n_dev_res, 1) * sizeof(ResCopy), 16);
     int rc;
@@ -342,8 +353,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if ((rc = ensure_pinned(h, (void**)&h->h_out, &h->h_out_cap, (out_words + 16) * 4))) return rc;
 
     // ---- descriptors -----------------------------------------------------------------------------------------------------
-    // with one chunk everything runs on the compute stream; with several, copies go to the copy stream and each launch
-    // waits for the event recorded after its chunk's copies
+    // Staging: the arrays of a window lie back to back at 16-byte boundaries (so a blob travels with one copy); every
+    // window's region starts at a 128-byte boundary, so no cache line holds data of two windows -- in the gated mode a
+    // window may still be in flight while the kernel already reads its neighbour.
     cudaStream_t cstream = gated ? h->copy_stream : h->stream;
     WinDesc* hd = reinterpret_cast<WinDesc*>(h->h_meta);
     int64_t h2d = 0;
@@ -363,6 +375,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         d.packed = packed_code(v);
         d.n_max_floor = v.n_max_floor;
         if (v.memory == MSS_MEM_HOST) {
+            soff = align_up(soff, 128);
             d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
             d.feat_mp = (const int*)stage(slots_ptr(v), slots_bytes(v));
             d.feat_cell = pk ? nullptr : (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
@@ -384,16 +397,16 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         row_base += v.K + v.H; slot_base += v.F; obs_base += v.O;
         var_base += (int)align_up((size_t)std::max(v.M, 1), mss::kVarTile);
     }
-    for (const Chunk& ch : chunks) {
-        mss::GroupDesc* h_grp = reinterpret_cast<mss::GroupDesc*>(h->h_meta + ch.off_grp);
-        int* h_cta_grp = reinterpret_cast<int*>(h->h_meta + ch.off_cta);
-        int* h_gwin = reinterpret_cast<int*>(h->h_meta + ch.off_gwin);
+    {
+        mss::GroupDesc* h_grp = reinterpret_cast<mss::GroupDesc*>(h->h_meta + plan.off_grp);
+        int* h_cta_grp = reinterpret_cast<int*>(h->h_meta + plan.off_cta);
+        int* h_gwin = reinterpret_cast<int*>(h->h_meta + plan.off_gwin);
         int cta = 0;
-        for (int g = 0; g < ch.ngroups; ++g) {
-            h_grp[g].cta0 = cta; h_grp[g].ncta = ch.gsize; h_grp[g].pad_[0] = h_grp[g].pad_[1] = 0;
-            for (int k = 0; k < ch.gsize; ++k) h_cta_grp[cta++] = g;
+        for (int g = 0; g < plan.ngroups; ++g) {
+            h_grp[g].cta0 = cta; h_grp[g].ncta = plan.gsize; h_grp[g].pad_[0] = h_grp[g].pad_[1] = 0;
+            for (int k = 0; k < plan.gsize; ++k) h_cta_grp[cta++] = g;
         }
-        for (int i = 0; i < ch.count; ++i) h_gwin[i] = ch.order[i];
+        for (int i = 0; i < nl; ++i) h_gwin[i] = plan.order[i];
     }
     // descriptors first, on the compute stream (the kernel needs them at once)
     {
@@ -401,7 +414,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         int q = 0;
         for (int w = 0; w < nwin; ++w) {
             const mss_result& r = results[w];
-            if (views[w].memory != MSS_MEM_DEVICE || !(r.keep_bits || r.kf_cov || r.kf_slack)) continue;
+            if (!res_on_device(views[w]) || !(r.keep_bits || r.kf_cov || r.kf_slack)) continue;
             const SlotLayout sl = slot_of(views[w]);
             hr[q++] = ResCopy{h->out.p + out_off[w], r.keep_bits, r.kf_cov, r.kf_slack, sl.words_keep, sl.rows};
         }
@@ -409,17 +422,22 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
     h2d += (int64_t)meta_bytes;
     MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
+    for (int w : rejected) MSS_CUDA(h, cudaMemsetAsync(h->out.p + out_off[w], 0, (size_t)mss::kHdrWords * 4, h->stream));
     if (gated) {
         MSS_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
         MSS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
     }
     // ---- staging copies, in queue order ------------------------------------------------------------------------------------
+    cudaError_t copy_err = cudaSuccess;
     auto copy_window = [&](int i) {
         const mss_window_view& v = views[local[i]];
         if (v.memory != MSS_MEM_HOST) return;
         const WinDesc& d = hd[i];
         const bool pk = v.layout != MSS_LAYOUT_SOA;
-        auto put = [&](const void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream); };
+        auto put = [&](const void* dst, const void* src, size_t bytes) {
+            if (!bytes || copy_err != cudaSuccess) return;
+            copy_err = cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, cstream);
+        };
         // a view whose arrays lie back to back on the host, in staging order and each at the next 16-byte boundary (one
         // pinned blob per window, as FlattenWindow lays them out), travels with ONE copy
         {
@@ -446,9 +464,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         put(d.mp_obs_kf, pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
         put(d.okf_total, v.okf_total, (size_t)v.H * 4);
     };
-    const Chunk& ch0 = chunks[0];
     unsigned* d_ready = h->sync.p + ready_off;
-    if (!gated) for (int q = 0; q < ch0.count; ++q) copy_window(ch0.order[q]);
+    if (!gated) for (int q = 0; q < nl; ++q) copy_window(plan.order[q]);
+    MSS_CUDA(h, copy_err);
     MSS_CUDA(h, cudaGetLastError());
 
     // ---- launch -----------------------------------------------------------------------------------------------------------
@@ -475,28 +493,49 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     P.tail_vars = std::min(h->tail_vars, mss::kTailVars); P.tail_ents = std::min(h->tail_ents, mss::kTailEnts);
     P.ready = gated ? d_ready : nullptr;
 
+    // Once the persistent kernel is launched it may be spinning on ready flags that a failed copy will never set: any
+    // error after the launch raises the device-side abort flag from the host and drains both streams before returning
+    // (the staging buffers and pinned mirrors are reused by the next call).
+    bool launched = false;
+    auto abort_launch = [&]() {
+        if (!launched) return;
+        cudaMemcpyAsync(&h->ctrl->abort, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream);
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+    };
+#define MSS_CUDA_LAUNCHED(h, expr)                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            abort_launch();                                                                        \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                         \
+            return MSS_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
     float dev_ms = 0.f;
     if (nl > 0) {
         if (h->trace_on) MSS_CUDA(h, cudaMemsetAsync(h->trace.p, 0, (size_t)nl * mss::kTraceCap * sizeof(uint2), h->stream));
         MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + ch0.off_grp);
-        P.cta_grp = reinterpret_cast<const int*>(h->meta.p + ch0.off_cta);
-        P.gwin = reinterpret_cast<const int*>(h->meta.p + ch0.off_gwin);
-        P.ctrl = reinterpret_cast<Ctrl*>(h->sync.p + ch0.sync_off);
-        P.gbar = h->sync.p + ch0.sync_off + 32;
-        P.nwin = ch0.count; P.ngroups = ch0.ngroups;
+        P.grp = reinterpret_cast<const mss::GroupDesc*>(h->meta.p + plan.off_grp);
+        P.cta_grp = reinterpret_cast<const int*>(h->meta.p + plan.off_cta);
+        P.gwin = reinterpret_cast<const int*>(h->meta.p + plan.off_gwin);
+        P.ctrl = h->ctrl;
+        P.gbar = h->sync.p + 32;
+        P.nwin = nl; P.ngroups = plan.ngroups;
         void* args[] = {(void*)&P};
-        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(ch0.grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
+        MSS_CUDA(h, cudaLaunchCooperativeKernel((const void*)mss::mss_persistent_kernel, dim3(plan.grid), dim3(mss::kThreads), args, mss::kSmemBytes, h->stream));
         h->stats.kernel_launches += 1;
-        grid = ch0.grid;
-        MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        launched = true;
+        MSS_CUDA_LAUNCHED(h, cudaEventRecord(h->ev1, h->stream));
         if (gated) {
             // the kernel is running (or queued); feed it: window after window in queue order, flag after data
-            for (int q = 0; q < ch0.count; ++q) {
-                copy_window(ch0.order[q]);
-                MSS_CUDA(h, cudaMemcpyAsync(d_ready + q, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream));
+            for (int q = 0; q < nl && copy_err == cudaSuccess; ++q) {
+                copy_window(plan.order[q]);
+                if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(d_ready + q, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream);
             }
-            h2d += 4ll * ch0.count;
+            MSS_CUDA_LAUNCHED(h, copy_err);
+            h2d += 4ll * nl;
         }
     } else {
         grid = 0;
@@ -505,7 +544,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     if (nranks > 1) {
         const size_t count = (size_t)spr * slot_stride;
         const int nrc = g_nccl.AllGather(h->out.p + (size_t)rank * count, h->out.p, count, kNcclUint32, h->comm, h->stream);
-        if (nrc != 0) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(nrc); return MSS_E_NCCL; }
+        if (nrc != 0) { abort_launch(); h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(nrc); return MSS_E_NCCL; }
     }
     // ---- hand-back ------------------------------------------------------------------------------------------------------
     // Only what the caller asked for crosses PCIe: the whole slot of a window whose result arrays are host buffers, the
@@ -517,7 +556,7 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         bool uniform = true;
         for (int w = 0; w < nwin; ++w) {
             const mss_result& r = results[w];
-            if (views[w].memory != MSS_MEM_DEVICE && (r.keep_bits || r.kf_cov || r.kf_slack)) ++n_full;
+            if (!res_on_device(views[w]) && (r.keep_bits || r.kf_cov || r.kf_slack)) ++n_full;
             if (w > 0 && out_off[w] - out_off[w - 1] != out_off[1] - out_off[0]) uniform = false;
         }
         if (nranks > 1) uniform = true;                        // rank-major slots with one stride
@@ -525,14 +564,14 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         const size_t nslots = nranks > 1 ? (size_t)nranks * spr : (size_t)nwin;
         auto wants_full = [&](int w) {
             const mss_result& r = results[w];
-            return views[w].memory != MSS_MEM_DEVICE && (r.keep_bits || r.kf_cov || r.kf_slack);
+            return !res_on_device(views[w]) && (r.keep_bits || r.kf_cov || r.kf_slack);
         };
         if (n_full == nwin) {
-            MSS_CUDA(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
+            MSS_CUDA_LAUNCHED(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
             d2h += (int64_t)(out_words * 4);
         } else {
             if (uniform) {      // headers of all slots in one strided copy
-                MSS_CUDA(h, cudaMemcpy2DAsync(h->h_out, stride * 4, h->out.p, stride * 4, (size_t)mss::kHdrWords * 4, nslots,
+                MSS_CUDA_LAUNCHED(h, cudaMemcpy2DAsync(h->h_out, stride * 4, h->out.p, stride * 4, (size_t)mss::kHdrWords * 4, nslots,
                                               cudaMemcpyDeviceToHost, h->stream));
                 d2h += (int64_t)(nslots * mss::kHdrWords * 4);
             }
@@ -540,28 +579,27 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
                 const bool full = wants_full(w);
                 if (!full && uniform) continue;
                 const size_t words = full ? (size_t)slot_of(views[w]).total : (size_t)mss::kHdrWords;
-                MSS_CUDA(h, cudaMemcpyAsync(h->h_out + out_off[w], h->out.p + out_off[w], words * 4, cudaMemcpyDeviceToHost, h->stream));
+                MSS_CUDA_LAUNCHED(h, cudaMemcpyAsync(h->h_out + out_off[w], h->out.p + out_off[w], words * 4, cudaMemcpyDeviceToHost, h->stream));
                 d2h += (int64_t)(words * 4);
             }
         }
     }
-    for (int c = 0; c < nchunks; ++c)
-        MSS_CUDA(h, cudaMemcpyAsync(&h->h_ctrl[c], h->sync.p + chunks[c].sync_off, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
-    d2h += (int64_t)((size_t)nchunks * sizeof(Ctrl));
+    MSS_CUDA_LAUNCHED(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    d2h += (int64_t)sizeof(Ctrl);
     bool aborted = false;
     if (n_dev_res > 0) {                   // device-resident result buffers are filled device-to-device, all windows in one launch
         scatter_results_kernel<<<n_dev_res, 256, 0, h->stream>>>(reinterpret_cast<const ResCopy*>(h->meta.p + off_res));
-        MSS_CUDA(h, cudaGetLastError());
+        MSS_CUDA_LAUNCHED(h, cudaGetLastError());
         h->stats.kernel_launches += 1;
     }
-    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (gated) MSS_CUDA(h, cudaStreamSynchronize(h->copy_stream));     // (only an aborted launch can finish before its copies)
+    MSS_CUDA_LAUNCHED(h, cudaStreamSynchronize(h->stream));
+    if (gated) MSS_CUDA_LAUNCHED(h, cudaStreamSynchronize(h->copy_stream));     // (only an aborted launch can finish before its copies)
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
     unsigned long long row_entries = 0, var_visits = 0;
-    for (int c = 0; c < nchunks && nl > 0; ++c) {
-        aborted = aborted || h->h_ctrl[c].abort != 0;
-        row_entries += h->h_ctrl[c].row_entries;
-        var_visits += h->h_ctrl[c].var_visits;
+    if (nl > 0) {
+        aborted = h->h_ctrl->abort != 0;
+        row_entries = h->h_ctrl->row_entries;
+        var_visits = h->h_ctrl->var_visits;
     }
     if (h->trace_on && nl > 0) {
         h->h_trace.resize((size_t)nl * mss::kTraceCap);
@@ -577,16 +615,16 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
         mss_result& r = results[w];
         const SlotLayout s = slot_of(v);
         const uint32_t* slot = h->h_out + out_off[w];
-        const bool host_mem = v.memory != MSS_MEM_DEVICE;
+        const bool host_mem = !res_on_device(v);
         if (aborted) {
             fill_failsafe(v, r, MSS_E_INTERNAL, host_mem, h);
             ret = MSS_E_INTERNAL;
-            h->err = "device watchdog: a group barrier waited longer than the limit; launch aborted, all map points kept";
+            h->err = "device watchdog: a group barrier or ready-flag wait exceeded the limit (MSS_WATCHDOG_MS); launch aborted, all map points kept";
             continue;
         }
         if (slot[14] != 0x4D535331u) {
             fill_failsafe(v, r, MSS_E_BADARG, host_mem, h);
-            if (ret == MSS_OK) { ret = MSS_E_BADARG; h->err = "window " + std::to_string(w) + ": view failed device-side validation (index out of range, bad pointer table or > 1023 points in one grid cell); all map points kept"; }
+            if (ret == MSS_OK) { ret = MSS_E_BADARG; h->err = "window " + std::to_string(w) + ": view failed validation (index out of range, bad pointer table or more than 65535 points in one grid cell); all map points kept"; }
             continue;
         }
         if (host_mem) {
@@ -677,7 +715,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if (const char* tv = getenv("MSS_TAIL_VARS")) h->tail_vars = atoi(tv);
     if (const char* te = getenv("MSS_TAIL_ENTS")) h->tail_ents = atoi(te);
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
-    if ((e = cudaHostAlloc((void**)&h->h_ctrl, kMaxChunks * sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void**)&h->h_one, 64, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);

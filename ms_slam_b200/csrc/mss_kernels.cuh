@@ -111,7 +111,7 @@ struct GroupDesc {
 
 struct Ctrl {
     unsigned long long t_start, t_build, t_end;
-    int abort;           // set by the watchdog: a barrier waited longer than watchdog_ns
+    int abort;           // set by the watchdog (one barrier / ready-flag wait longer than watchdog_ns) or by the host (failed copy)
     unsigned queue;      // next position of gwin[] to hand out
     unsigned long long row_entries;   // list / CSR entries read by the row phases of this launch (work accounting)
     unsigned long long var_visits;    // map points visited by the variable phases of this launch
@@ -171,6 +171,12 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Loads of VIEW data (the caller's arrays, possibly staged from the host while this kernel already runs: Params::ready).
+// Plain ld.global, not ld.global.nc: the non-coherent path requires data that is read-only for the whole kernel, which a
+// window still in flight is not; the ready flag's acquire + the group barrier order these loads after the copy.
+template <class T>
+__device__ __forceinline__ T ldv(const T* p) { return *p; }
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
     unsigned v;
@@ -210,7 +216,6 @@ struct GroupCtx {
     int ncta;
     int cta;        // index of this CTA inside the group
     int* s_abort;   // shared flag
-    unsigned long long t0;   // this CTA's start time (watchdog reference)
 };
 
 // Barrier of the CTAs of one group.  Thread 0 publishes the CTA's writes with a release add and waits with acquire
@@ -225,11 +230,13 @@ __device__ __forceinline__ bool group_sync(const Params& P, GroupCtx& G) {
             red_release_add_u32(G.bar, 1u);
             const unsigned target = G.gen * (unsigned)G.ncta;
             unsigned spins = 0;
+            unsigned long long t_wait = 0ull;          // taken at the first check: the limit is per wait, not per launch
             while (ld_acquire_u32(G.bar) < target) {
                 if (spins > 64u) __nanosleep(64);
                 if ((++spins & 0xFFu) == 0u) {
                     if (*(volatile int*)&P.ctrl->abort) { ab = 1; break; }
-                    if (globaltimer_ns() - G.t0 > P.watchdog_ns) {
+                    if (t_wait == 0ull) t_wait = globaltimer_ns();
+                    else if (globaltimer_ns() - t_wait > P.watchdog_ns) {
                         atomicExch(&P.ctrl->abort, 1);
                         ab = 1;
                         break;
@@ -357,9 +364,9 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
 // View accessors: the SoA layout carries i32 / u16 arrays, the packed transport layout u32 slots and u16 tables
 // (include/mss.h, mss_layout); the branch is uniform per window.
 __device__ __forceinline__ int ld_nobs(const WinDesc& D, int mp) {
-    return D.packed ? (int)__ldg(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : __ldg(D.mp_nobs + mp);
+    return D.packed ? (int)ldv(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : ldv(D.mp_nobs + mp);
 }
-__device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) { return __ldg(D.mp_obs_kf + o); }      // SoA layout only
+__device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) { return ldv(D.mp_obs_kf + o); }      // SoA layout only
 // MSS_LAYOUT_PACKED16: the slots of a keyframe, sorted by map-point index, as 16-bit tokens.  d = t >> 12, low = t & 0xFFF:
 //   d < 15  a slot: map point = previous map point + d (0 at the start of the keyframe), cell = low (0xFFF = not in mGrid)
 //   d == 15 no slot: the running map-point index advances by 15 * (low + 1)
@@ -374,14 +381,14 @@ __device__ __forceinline__ int tok_decode(unsigned t, bool& slot, unsigned& cell
 // slot i of the view -> (map point or -1, cell or kCellNone)  [SoA and MSS_LAYOUT_PACKED; tokens are decoded by their readers]
 __device__ __forceinline__ void ld_slot(const WinDesc& D, int i, int& mp, unsigned& c) {
     if (D.packed) {
-        const uint32_t s = __ldg(reinterpret_cast<const uint32_t*>(D.feat_mp) + i);
+        const uint32_t s = ldv(reinterpret_cast<const uint32_t*>(D.feat_mp) + i);
         if (s == kEntInvalid) { mp = -1; c = kCellNone; return; }
         mp = (int)(s >> kCellBits);
         c = s & kCellCov;
         if (c == kCellCov) c = kCellNone;
     } else {
-        mp = __ldg(D.feat_mp + i);
-        c = __ldg(D.feat_cell + i);
+        mp = ldv(D.feat_mp + i);
+        c = ldv(D.feat_cell + i);
     }
 }
 
@@ -417,7 +424,7 @@ __device__ __forceinline__ void load_row(RowRegs<EPT>& X, const uint32_t* __rest
 // ---------------------------------------------------------------------------------------------------------------
 __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, int par, unsigned* tab, BlockScratch& S) {
     const int R = D.row_base + k;
-    const int beg = __ldg(D.feat_ptr + k), end = __ldg(D.feat_ptr + k + 1);
+    const int beg = ldv(D.feat_ptr + k), end = ldv(D.feat_ptr + k + 1);
     if (beg < 0 || end < beg || end > D.F) {
         if (threadIdx.x == 0) {
             atomicOr(&ws.error, ERR_PTR);
@@ -451,7 +458,7 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
                 int adv = 0;
                 bool slot = false;
                 unsigned c = kCellNone;
-                if (b < nb && idx < nslots) adv = tok_decode(__ldg(tk + idx), slot, c);
+                if (b < nb && idx < nslots) adv = tok_decode(ldv(tk + idx), slot, c);
                 int x = adv;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -556,7 +563,7 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
             unsigned c;
             if (tok) {                                                  // pass 1 needs the cells only
                 bool slot;
-                tok_decode(__ldg(tk + i), slot, c);
+                tok_decode(ldv(tk + i), slot, c);
                 if (!slot || c == kCellNone) continue;
             } else {
                 ld_slot(D, beg + i, mp, c);
@@ -578,12 +585,12 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
                 int adv = 0;
                 bool slot = false;
                 unsigned c = kCellNone;
-                if (i < nslots) adv = tok_decode(__ldg(tk + i), slot, c);
+                if (i < nslots) adv = tok_decode(ldv(tk + i), slot, c);
                 int tot;
                 const int mp = mp_carry + block_excl_scan(S, adv, tot) + adv;       // running map-point index, token order
                 mp_carry += tot;
                 if (slot) {
-                    if (mp >= D.M) err |= ERR_INDEX;
+                    if ((unsigned)mp >= (unsigned)D.M) err |= ERR_INDEX;       // (a wrapped running index is negative)
                     else if (c == kCellNone) seen_w[mp] = 1;
                     else if (c < (unsigned)kCells) e = ((uint32_t)mp << kCellBits) | c;
                 }
@@ -642,8 +649,8 @@ __device__ __forceinline__ int obs_owner(const ObsTile& O, int o) {
 __device__ __forceinline__ bool obs_tile_load(const WinDesc& D, WinState& ws, int base, ObsTile& O) {
     bool bad = false;
 #pragma unroll
-    for (int j = 0; j < kVpt; ++j) O.ptr[j * kVarTile + threadIdx.x] = __ldg(D.mp_obs_ptr + min(base + j * kVarTile + (int)threadIdx.x, D.M));
-    if (threadIdx.x == 0) O.ptr[kSuper] = __ldg(D.mp_obs_ptr + min(base + kSuper, D.M));
+    for (int j = 0; j < kVpt; ++j) O.ptr[j * kVarTile + threadIdx.x] = ldv(D.mp_obs_ptr + min(base + j * kVarTile + (int)threadIdx.x, D.M));
+    if (threadIdx.x == 0) O.ptr[kSuper] = ldv(D.mp_obs_ptr + min(base + kSuper, D.M));
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kVpt; ++j) {
@@ -718,7 +725,7 @@ __device__ void w2_pairs(const Params& P, const WinDesc& D, WinState& ws, int gt
     const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
     unsigned err = 0;
     for (int o = gt; o < D.O; o += gsz) {
-        const uint32_t pr = __ldg(pairs + o);
+        const uint32_t pr = ldv(pairs + o);
         const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
         if (mp >= D.M || j >= D.H) { err |= ERR_INDEX; continue; }
         if (P.acc[D.var_base + mp] != 0ull) atomicAdd(&P.ent_n[D.row_base + D.K + j], 1);
@@ -731,7 +738,7 @@ __device__ void w2_pairs(const Params& P, const WinDesc& D, WinState& ws, int gt
 __device__ void w4_pairs(const Params& P, const WinDesc& D, int gt, int gsz) {
     const uint32_t* pairs = reinterpret_cast<const uint32_t*>(D.mp_obs_kf);
     for (int o = gt; o < D.O; o += gsz) {
-        const uint32_t pr = __ldg(pairs + o);
+        const uint32_t pr = ldv(pairs + o);
         const int mp = (int)(pr >> kCellBits), j = (int)(pr & kCellCov);
         const int g = D.var_base + mp;
         if (P.st[g] != ST_FREE) continue;                   // (indices were validated by w2_pairs)
@@ -833,7 +840,7 @@ __device__ void w3_scan_outside(const Params& P, const WinDesc& D, BlockScratch&
             const int off = P.Ftot + D.obs_base + excl;
             P.row_off[R] = off;
             P.ocursor[R] = off;
-            P.row_need[R] = outside_need(v, __ldg(D.okf_total + j), P.N);
+            P.row_need[R] = outside_need(v, ldv(D.okf_total + j), P.N);
             P.row_cov[R] = 0;
             P.row_ncell[R] = 0;
             P.live_n[R] = 0;
@@ -2120,7 +2127,7 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     // ---- W1: keyframe rows ---------------------------------------------------------------------------------------
     for (int k = G.cta; k < D.K; k += G.ncta) {
         if (k + G.ncta < D.K) {                  // next row of this CTA: pull its slots towards L1 while this one is processed
-            const int nb = __ldg(D.feat_ptr + k + G.ncta), ne = __ldg(D.feat_ptr + k + G.ncta + 1);
+            const int nb = ldv(D.feat_ptr + k + G.ncta), ne = ldv(D.feat_ptr + k + G.ncta + 1);
             if (nb >= 0 && ne <= D.F) {
                 if (D.packed == 2) {
                     const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp);
@@ -2308,7 +2315,6 @@ __global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Param
     G.ncta = gd.ncta;
     G.cta = (int)blockIdx.x - gd.cta0;
     G.s_abort = &s_abort;
-    G.t0 = globaltimer_ns();
     if (threadIdx.x == 0) s_abort = 0;
     __syncthreads();
     // dynamic window queue: a group that finishes early takes the next window (largest windows are queued first)
@@ -2319,11 +2325,13 @@ __global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Param
                 // host views are copied while the kernel runs: wait for this window's flag (written by a copy that is
                 // stream-ordered after the copies of its arrays); the group barrier publishes it to the other CTAs
                 unsigned spins = 0;
+                unsigned long long t_wait = 0ull;
                 while (ld_acquire_sys_u32(P.ready + q) == 0u) {
                     __nanosleep(200);
                     if ((++spins & 0x3FFu) == 0u) {
                         if (*(volatile int*)&P.ctrl->abort) break;
-                        if (globaltimer_ns() - G.t0 > P.watchdog_ns) { atomicExch(&P.ctrl->abort, 1); break; }
+                        if (t_wait == 0ull) t_wait = globaltimer_ns();
+                        else if (globaltimer_ns() - t_wait > P.watchdog_ns) { atomicExch(&P.ctrl->abort, 1); break; }
                     }
                 }
             }

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmss.so")
 
 MSS_OK, MSS_E_BADARG, MSS_E_CUDA, MSS_E_NCCL, MSS_E_NOMEM, MSS_E_NOCONVERGE, MSS_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
+RESULT_SAME, RESULT_HOST, RESULT_DEVICE = 0, 1, 2
 LAYOUT_SOA, LAYOUT_PACKED, LAYOUT_PACKED16 = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 
@@ -39,7 +40,8 @@ class mss_window_view(C.Structure):
                 ("feat_ptr", C.c_void_p), ("feat_mp", C.c_void_p), ("feat_cell", C.c_void_p), ("mp_nobs", C.c_void_p),
                 ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
                 ("layout", C.c_int32), ("n_max_floor", C.c_int32),
-                ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("slots16", C.c_void_p), ("obs_pairs", C.c_void_p)]
+                ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("slots16", C.c_void_p), ("obs_pairs", C.c_void_p),
+                ("result_memory", C.c_int32), ("reserved_", C.c_int32)]
 
 
 def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total, n_max_floor=0, tokens16=False) -> "mss_window_view":

@@ -121,5 +121,45 @@ def main():
     print("wrote fixtures")
 
 
+def _extra_job(job):
+    """one window of the round-2 additions: LP bound of the reference model + checksum of the CPU emulation"""
+    name, seed, over = job
+    view, N = msgen.make_config(name, seed, **over)
+    model = om.build_model(view, N)
+    lp = om.solve_lp(view, N, LAM, GLAM, model=model)
+    r = em.solve(view, N, LAM, GLAM)
+    bits = em.pack_bits(r["keep"])
+    key = f"{name}:{seed}:{json.dumps(over, sort_keys=True)}"
+    bound = dict(N=N, lp=lp.objective, lp_seconds=lp.seconds, ilp=None, n_vars=int(model.var_mp.size), G=model.G,
+                 nnz=int(model.ent_var.size))
+    emu = dict(N=N, objective=r["objective"], n_kept=r["n_kept"], n_vars=r["n_vars"], n_cells=r["n_cells"], nnz=r["nnz"],
+               rounds=r["rounds"], n_max=r["n_max"], keep_sha256=hashlib.sha256(bits.tobytes()).hexdigest(),
+               view_sha256=hashlib.sha256(view.feat_mp.tobytes() + view.feat_cell.tobytes() + view.mp_nobs.tobytes()
+                                          + view.mp_obs_kf.tobytes() + view.okf_total.tobytes()).hexdigest())
+    return key, bound, emu
+
+
+def extra(procs=6):
+    """seeds 0-4 of c2 and c3, and all 64 windows of config 4 (seeds 1000..1063): LP bound + emulation
+    checksum each, merged into config_bounds.json / emulation.json.  Run: python tests/golden/make_golden.py --extra"""
+    from concurrent.futures import ProcessPoolExecutor
+    bounds_path, emu_path = os.path.join(HERE, "config_bounds.json"), os.path.join(HERE, "emulation.json")
+    bounds, emu = json.load(open(bounds_path)), json.load(open(emu_path))
+    jobs = [("c4", 1000 + w, {}) for w in range(64)] + [("c3", s, {}) for s in range(1, 5)] + [("c2", s, {}) for s in range(1, 5)]
+    jobs = [j for j in jobs if f"{j[0]}:{j[1]}:{json.dumps(j[2], sort_keys=True)}" not in emu
+            or f"{j[0]}:{j[1]}:{json.dumps(j[2], sort_keys=True)}" not in bounds]
+    with ProcessPoolExecutor(max_workers=procs) as pool:
+        for key, b, e in pool.map(_extra_job, jobs):
+            if key not in bounds:
+                bounds[key] = b
+            emu[key] = e
+            print(key, b["lp"], e["objective"], f"gap {e['objective']/b['lp']-1:.5f}", flush=True)
+            json.dump(bounds, open(bounds_path, "w"), indent=1)
+            json.dump(emu, open(emu_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if "--extra" in sys.argv:
+        extra()
+    else:
+        main()

@@ -75,9 +75,10 @@ def test_config_parity(eng, config_bounds, name, seed, over):
     assert rec["lp"] - 1e-6 <= F <= (1.0 + REL_TOL) * bound
 
 
-@pytest.mark.parametrize("name,seed", [("c2", 0), ("c2", 7), ("c2", 14), ("c2", 176), ("c5", 0)])
+@pytest.mark.parametrize("name,seed", [("c2", 0), ("c2", 1), ("c2", 2), ("c2", 3), ("c2", 4), ("c2", 7), ("c2", 14), ("c2", 176),
+                                       ("c3", 1), ("c3", 2), ("c3", 3), ("c3", 4), ("c5", 0)])
 def test_full_size_windows(eng, config_bounds, emulation_golden, name, seed):
-    """North-star window (500 KF x 200k MP; three ordinary seeds and seed 176, whose nMax outlier leaves ~500 keyframe rows
+    """SURVEY 8(d) seeds 0-4 of c2 and c3 (c3:0 is in test_config_parity with its ILP optimum).  North-star window (500 KF x 200k MP; ordinary seeds and seed 176, whose nMax outlier leaves ~500 keyframe rows
     deficient after round 1 so that the stall-triggered greedy step matters) and the 4Seasons-shaped stress window
     (2000 KF x 1M MP): bit-exact vs the committed emulation checksum + CPU re-evaluation of every row + LP bound of the
     reference ILP."""
@@ -306,3 +307,116 @@ def test_long_keyframe_rows_all_layouts(eng, N):
     for v in (view, pack_view(view, tokens16=True)):
         rows, mps, nc, nmax = eng.components(v)
         assert np.array_equal(rows, want[0]) and np.array_equal(mps, want[1]) and (nc, nmax) == (want[2], want[3])
+
+
+def _check_c4_window(view, N, r, gold, bound):
+    """one window of BASELINE config 4: checksum of the CPU emulation, CPU re-evaluation of every row, LP bound"""
+    import hashlib
+    assert r.status == 0
+    assert hashlib.sha256(r.keep_bits.tobytes()).hexdigest() == gold["keep_sha256"]
+    assert (r.objective, r.n_kept, r.rounds, r.n_vars, r.nnz) == (gold["objective"], gold["n_kept"], gold["rounds"], gold["n_vars"], gold["nnz"])
+    model = om.build_model(view, N)
+    x = om.keep_to_x(model, r.keep)
+    F, parts = om.objective(model, x, N, LAM, GLAM, parts=True)
+    assert F == r.objective and np.array_equal(parts["kf_cov"], r.kf_cov[:view.K]) and np.array_equal(parts["kf_slack"], r.kf_slack[:view.K])
+    assert om.rows_satisfied(model, x, N)[0]
+    assert bound["lp"] - 1e-6 <= F <= (1.0 + REL_TOL) * bound["lp"]
+
+
+def test_config4_batch_of_64_windows(eng, config_bounds, emulation_golden):
+    """BASELINE config 4 as specified: 64 independent 100-KF windows (seeds 1000..1063) in ONE mss_solve_batch; every window
+    against the committed emulation checksum, the CPU re-evaluation of its rows and the LP bound of the reference model."""
+    N = msgen.CONFIGS["c4"]["N"]
+    eng.set_params(N, LAM, GLAM)
+    views = [msgen.make_config("c4", 1000 + w)[0] for w in range(64)]
+    l0 = eng.stats()["kernel_launches"]
+    res = eng.solve_batch(views)
+    assert eng.stats()["kernel_launches"] == l0 + 1            # one persistent launch for the whole batch
+    for w, (v, r) in enumerate(zip(views, res)):
+        key = fixture_key("c4", 1000 + w)
+        _check_c4_window(v, N, r, emulation_golden[key], config_bounds[key])
+
+
+_RANK_SCRIPT = r"""
+import hashlib, json, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["MSS_ROOT"])
+import torch, torch.distributed as dist
+from ms_slam_b200 import msgen, dist as msd
+from ms_slam_b200.engine import Engine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+N = msgen.CONFIGS["c4"]["N"]
+views = [msgen.make_config("c4", 1000 + w)[0] for w in range(64)]
+eng = Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=rank)
+eng.comm_init(msd.broadcast_unique_id(eng, rank), rank, world)
+res = eng.solve_batch(views)          # window w on rank w % world, results all-gathered: every rank holds all 64
+out = [dict(sha=hashlib.sha256(r.keep_bits.tobytes()).hexdigest(), F=r.objective, kept=r.n_kept, rounds=r.rounds, status=r.status,
+            cov=hashlib.sha256(r.kf_cov.tobytes() + r.kf_slack.tobytes()).hexdigest()) for r in res]
+json.dump(out, open(os.path.join(os.environ["MSS_OUT"], f"rank{rank}.json"), "w"))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_config4_sharded_over_two_ranks_matches_one_gpu(eng, emulation_golden, tmp_path):
+    """Config 4 over NCCL: two processes, one per GPU, window w -> rank w % 2, one all-gather of the result slots; every
+    rank must end up with all 64 results, bit-identical to the one-GPU batch (and hence to the emulation checksums)."""
+    import hashlib, os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    from conftest import ROOT
+    script = tmp_path / "rank.py"
+    script.write_text(_RANK_SCRIPT)
+    env = dict(os.environ, MSS_ROOT=ROOT, MSS_OUT=str(tmp_path))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29517", str(script)], check=True, env=env, timeout=900)
+    N = msgen.CONFIGS["c4"]["N"]
+    eng.set_params(N, LAM, GLAM)
+    solo = eng.solve_batch([msgen.make_config("c4", 1000 + w)[0] for w in range(64)])
+    for rank in range(2):
+        got = json.load(open(tmp_path / f"rank{rank}.json"))
+        assert len(got) == 64
+        for w, (g, r) in enumerate(zip(got, solo)):
+            assert g["status"] == 0 and g["sha"] == hashlib.sha256(r.keep_bits.tobytes()).hexdigest(), (rank, w)
+            assert g["sha"] == emulation_golden[fixture_key("c4", 1000 + w)]["keep_sha256"]
+            assert (g["F"], g["kept"], g["rounds"]) == (r.objective, r.n_kept, r.rounds)
+            assert g["cov"] == hashlib.sha256(r.kf_cov.tobytes() + r.kf_slack.tobytes()).hexdigest()
+
+
+def test_gated_batch_of_tiny_ragged_windows(build_native):
+    """Host views travel while the kernel runs.  Many tiny windows of odd sizes: their staging regions end at addresses
+    that are not multiples of 32 bytes, so neighbouring windows would share a sector / cache line if the engine did not
+    start every window's region on its own 128-byte line.  Result must equal the copy-first path and the emulation, call
+    after call (the staging buffer is reused)."""
+    import os
+    from ms_slam_b200.engine import Engine
+    from ms_slam_b200.window import pack_view
+    rng = np.random.default_rng(11)
+    views, plain = [], []
+    for i in range(48):
+        K = int(rng.integers(1, 4))
+        M = int(rng.integers(3, 40))
+        slots = [[(int(p), int(rng.integers(0, 3072))) for p in rng.choice(M, size=int(rng.integers(1, M + 1)), replace=False)]
+                 for _ in range(K)]
+        H = int(rng.integers(0, 3))
+        outside = [rng.choice(M, size=int(rng.integers(1, M + 1)), replace=False).tolist() for _ in range(H)]
+        v = make_view(K, slots, rng.integers(3, 30, M).tolist(), outside=outside, okf_total=[int(rng.integers(1, 60)) for _ in range(H)])
+        plain.append(v)
+        views.append(v if i % 3 == 0 else pack_view(v, tokens16=(i % 3 == 2)))
+    N = 2
+    e1 = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    os.environ["MSS_OVERLAP_COPY"] = "0"
+    try:
+        e2 = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    finally:
+        del os.environ["MSS_OVERLAP_COPY"]
+    for rep in range(4):
+        order = rng.permutation(len(views))                # a different packing of the staging buffer every call
+        r1 = e1.solve_batch([views[i] for i in order])
+        r2 = e2.solve_batch([views[i] for i in order])
+        for i, a, b in zip(order, r1, r2):
+            assert np.array_equal(a.keep_bits, b.keep_bits) and a.objective == b.objective and a.rounds == b.rounds
+            if rep == 0:
+                check_against_cpu(plain[i], N, a)
+    e1.close(); e2.close()
