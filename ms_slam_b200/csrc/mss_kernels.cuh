@@ -53,7 +53,10 @@ constexpr unsigned kEntInvalid = 0xFFFFFFFFu;
 constexpr unsigned kTabCov = 0x80000000u;   // cell table: bit 31 = cell has an IN point, low 16 bits = FREE count
 constexpr int kEpt = 8;                     // entries per thread held in registers (rows up to 2048 entries)
 constexpr int kRegRow = kThreads * kEpt;
-constexpr int kWarpRow = 32;                // lists up to this long are handled by one warp
+constexpr int kWarpRow = 32;                // lists up to this long are handled by one warp, cells matched with match.any
+constexpr int kWarpTabRow = 256;            // lists up to this long are handled by one warp with its own nibble cell table
+constexpr int kWarpTabWords = kCells / 8;   // 4 bits per cell: 1536 B per warp, the eight tables fill the CTA's cell table
+constexpr int kWarpEpt = kWarpTabRow / 32;  // entries per lane
 constexpr int kTraceCap = 256;
 // shared-memory tail solver: capacity of the residual problem one CTA finishes on its own
 constexpr int kTailEnts = 2048;
@@ -998,8 +1001,7 @@ __device__ void w4_fill_and_round1(const Params& P, const WinDesc& D, WinState& 
 // PROP: counts on the current state, contributions to the FREE variables, and the row's new live list.
 // Source list: the CSR (first PROP row phase of the window) or the previous live list.  Entries found IN are added to the
 // running coverage exactly once (they are not copied to the new list); entries found OUT are dropped.
-// PROP on a list held in registers (EPT entries per thread): three block barriers per row; the scratch is double-buffered
-// by row parity, so no protective barriers are needed
+// PROP on a list held in registers (EPT entries per thread)
 template <int EPT>
 __device__ __forceinline__ void row_prop_regs(const Params& P, const WinDesc& D, int R, int n, const uint32_t* src, uint32_t* dst,
                                               int need, int cov0, int par, unsigned* tab, BlockScratch& S) {
@@ -1007,7 +1009,8 @@ __device__ __forceinline__ void row_prop_regs(const Params& P, const WinDesc& D,
     unsigned long long* acc_w = P.acc + D.var_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    // three block barriers per row; the scratch is double-buffered by row parity, so no protective barriers are needed
+    // two block barriers per row: the cell table and the scratch are double-buffered by row parity (the caller alternates
+    // `tab` between two tables), so neither the lazy zeroing of the next row nor its partial sums can overtake a slow warp
     RowRegs<EPT> X;
     load_row(X, src, n, st_w);
 #pragma unroll
@@ -1015,29 +1018,33 @@ __device__ __forceinline__ void row_prop_regs(const Params& P, const WinDesc& D,
         if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
     __syncthreads();
     int cin = 0, cfree = 0;
-#pragma unroll
-    for (int b = 0; b < EPT; ++b) {
-        if (X.e[b] == kEntInvalid) continue;
-        const unsigned cell = X.e[b] & kCellCov;
-        if (X.s[b] == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
-        else if (X.s[b] == ST_FREE) { ++cfree; if (cell != kCellCov) atomicAdd(&tab[cell], 1u); }
-    }
-    cin = __reduce_add_sync(0xFFFFFFFFu, cin);
-    cfree = __reduce_add_sync(0xFFFFFFFFu, cfree);
-    if (lane == 0) { S.pred[par][0][wid] = cin; S.pred[par][1][wid] = cfree; }
-    __syncthreads();                                    // publishes the cell table and the partial sums
-    cin = 0; cfree = 0;
-#pragma unroll
-    for (int q = 0; q < kWarps; ++q) { cin += S.pred[par][0][q]; cfree += S.pred[par][1][q]; }
-    const int cov = cov0 + cin;
-    const int d = max(0, need - cov);
-    const bool defi = d > 0, critr = defi && d >= cfree;
-    int wcnt = 0;
     unsigned m[EPT];
 #pragma unroll
     for (int b = 0; b < EPT; ++b) {
-        const bool fr = (X.e[b] != kEntInvalid) && X.s[b] == ST_FREE;
-        if (fr) {
+        const bool fr = X.e[b] != kEntInvalid && X.s[b] == ST_FREE;
+        m[b] = __ballot_sync(0xFFFFFFFFu, fr);
+        if (X.e[b] == kEntInvalid) continue;
+        const unsigned cell = X.e[b] & kCellCov;
+        if (X.s[b] == ST_IN) { ++cin; if (cell != kCellCov) atomicOr(&tab[cell], kTabCov); }
+        else if (fr && cell != kCellCov) atomicAdd(&tab[cell], 1u);
+    }
+    cin = __reduce_add_sync(0xFFFFFFFFu, cin);
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) cfree += __popc(m[b]);                 // this warp's FREE entries = its share of the new list
+    if (lane == 0) { S.pred[par][0][wid] = cin; S.pred[par][1][wid] = cfree; }
+    __syncthreads();                                    // publishes the cell table and the partial sums
+    int pos = 0;
+    cin = 0; cfree = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) { if (q < wid) pos += S.pred[par][1][q]; cin += S.pred[par][0][q]; cfree += S.pred[par][1][q]; }
+    const int cov = cov0 + cin;
+    const int d = max(0, need - cov);
+    const bool defi = d > 0, critr = defi && d >= cfree;
+    const unsigned lt = (1u << lane) - 1u;
+    // every entry of src is in registers (load_row precedes the first barrier), so the in-place compaction can start at once
+#pragma unroll
+    for (int b = 0; b < EPT; ++b) {
+        if ((m[b] >> lane) & 1u) {
             const unsigned cell = X.e[b] & kCellCov;
             unsigned long long add = 0;
             bool covered = true;
@@ -1049,20 +1056,8 @@ __device__ __forceinline__ void row_prop_regs(const Params& P, const WinDesc& D,
             if (defi) add |= 1ull << 32;
             if (critr) add |= 1ull << 48;
             if (add) atomicAdd(&acc_w[X.e[b] >> kCellBits], add);
-            if (covered) X.e[b] |= kCellCov;
+            dst[pos + __popc(m[b] & lt)] = covered ? (X.e[b] | kCellCov) : X.e[b];
         }
-        m[b] = __ballot_sync(0xFFFFFFFFu, fr);
-        wcnt += __popc(m[b]);
-    }
-    if (lane == 0) S.pscan[par][wid] = wcnt;
-    __syncthreads();                                    // every read of src and of the cell table precedes what follows
-    int pos = 0;
-#pragma unroll
-    for (int q = 0; q < kWarps; ++q) if (q < wid) pos += S.pscan[par][q];
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int b = 0; b < EPT; ++b) {
-        if ((m[b] >> lane) & 1u) dst[pos + __popc(m[b] & lt)] = X.e[b];
         pos += __popc(m[b]);
     }
     if (threadIdx.x == 0) {
@@ -1316,6 +1311,153 @@ __device__ __forceinline__ void warp_row_greedy(const Params& P, const WinDesc& 
         }
     }
     if (flags) atomicOr(&P.acc[D.var_base + v], flags);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-row variants for lists of 33..256 entries (eight entries per lane, lane-strided: coalesced, list order =
+// (chunk, lane) order).  Each warp owns a 4-bit-per-cell table in shared memory (the eight tables alias the CTA's cell
+// table): bit 0 = "at least one", bit 1 = "at least two" (set by the second atomicOr that finds bit 0), bit 2 = "has an
+// IN entry" -- exactly what the dominance rules read (a count matters only as 0 / 1 / more).  No block barrier: eight
+// such rows are in flight per CTA.  Same arithmetic as the block versions; list order is preserved.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned nib_of(const unsigned* wt, unsigned cell) { return (wt[cell >> 3] >> ((cell & 7u) * 4u)) & 0xFu; }
+// returns true when this call was the first to mark the cell
+__device__ __forceinline__ bool nib_count(unsigned* wt, unsigned cell) {
+    const unsigned sh = (cell & 7u) * 4u;
+    const unsigned old = atomicOr(&wt[cell >> 3], 1u << sh);
+    if ((old >> sh) & 1u) { atomicOr(&wt[cell >> 3], 2u << sh); return false; }
+    return true;
+}
+
+__device__ __forceinline__ void warp_tab_load(uint32_t (&e)[kWarpEpt], uint8_t (&st)[kWarpEpt], const uint32_t* src, int n,
+                                              const uint8_t* st_w) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < kWarpEpt; ++b) {
+        const int idx = b * 32 + lane;
+        e[b] = idx < n ? src[idx] : kEntInvalid;
+    }
+#pragma unroll
+    for (int b = 0; b < kWarpEpt; ++b) st[b] = e[b] != kEntInvalid ? st_w[e[b] >> kCellBits] : (uint8_t)ST_NOTVAR;
+}
+
+__device__ __forceinline__ void warp_tab_prop(const Params& P, const WinDesc& D, int R, int n, bool from_csr, unsigned* wt,
+                                              unsigned& rows_live) {
+    const int lane = threadIdx.x & 31;
+    const int off = P.row_off[R];
+    const uint32_t* src = (from_csr ? P.ent : P.live) + off;
+    uint32_t* dst = P.live + off;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int need = P.row_need[R], cov0 = P.row_cov[R];
+    uint32_t e[kWarpEpt];
+    uint8_t st[kWarpEpt];
+    warp_tab_load(e, st, src, n, P.st + D.var_base);
+#pragma unroll
+    for (int b = 0; b < kWarpEpt; ++b)
+        if (e[b] != kEntInvalid && (e[b] & kCellCov) != kCellCov) wt[(e[b] & kCellCov) >> 3] = 0u;
+    __syncwarp();
+    int cin = 0, cfree = 0;
+    unsigned mfr[kWarpEpt];
+#pragma unroll
+    for (int b = 0; b < kWarpEpt; ++b) {
+        const unsigned cell = e[b] & kCellCov;
+        const bool in = st[b] == ST_IN, fr = st[b] == ST_FREE;          // (invalid lanes carry ST_NOTVAR)
+        if (in && cell != kCellCov) atomicOr(&wt[cell >> 3], 4u << ((cell & 7u) * 4u));
+        if (fr && cell != kCellCov) nib_count(wt, cell);
+        cin += __popc(__ballot_sync(0xFFFFFFFFu, in));
+        mfr[b] = __ballot_sync(0xFFFFFFFFu, fr);
+        cfree += __popc(mfr[b]);
+    }
+    __syncwarp();
+    const int cov = cov0 + cin;
+    const int d = max(0, need - cov);
+    const bool defi = d > 0, critr = defi && d >= cfree;
+    const unsigned lt = (1u << lane) - 1u;
+    int pos = 0;
+#pragma unroll
+    for (int b = 0; b < kWarpEpt; ++b) {
+        if ((mfr[b] >> lane) & 1u) {
+            const unsigned cell = e[b] & kCellCov;
+            unsigned long long add = 0;
+            bool covered = true;
+            if (cell != kCellCov) {
+                const unsigned t = nib_of(wt, cell);
+                covered = (t & 4u) != 0u;
+                if (!covered) { add |= 1ull; if (!(t & 2u)) add |= 1ull << 16; }
+            }
+            if (defi) add |= 1ull << 32;
+            if (critr) add |= 1ull << 48;
+            if (add) atomicAdd(&acc_w[e[b] >> kCellBits], add);
+            dst[pos + __popc(mfr[b] & lt)] = covered ? (e[b] | kCellCov) : e[b];   // every lane holds its entries in registers
+        }
+        pos += __popc(mfr[b]);
+    }
+    if (lane == 0) {
+        if (cin) P.row_cov[R] = cov;
+        P.live_n[R] = cfree;
+        if (cfree) rows_live += 1u;
+    }
+}
+
+// sweep (D1 / EVAL) of a list of at most 256 entries: see row_d1_regs / row_d1_eval
+__device__ __forceinline__ void warp_tab_d1(const Params& P, const WinDesc& D, RoundCnt& rc, int R, int n, bool accumulate, bool from_in,
+                                            unsigned* wt) {
+    const int lane = threadIdx.x & 31;
+    const int off = P.row_off[R];
+    const uint32_t* src = (from_in ? P.live : P.ent) + off;
+    uint32_t* dst = P.live + off;
+    unsigned long long* acc_w = P.acc + D.var_base;
+    const int need = P.row_need[R];
+    int cin = 0, ccells = 0;
+    if (n > 0) {
+        uint32_t e[kWarpEpt];
+        uint8_t st[kWarpEpt];
+        warp_tab_load(e, st, src, n, P.st + D.var_base);
+#pragma unroll
+        for (int b = 0; b < kWarpEpt; ++b)
+            if (e[b] != kEntInvalid && (e[b] & kCellCov) != kCellCov) wt[(e[b] & kCellCov) >> 3] = 0u;
+        __syncwarp();
+        unsigned m[kWarpEpt];
+#pragma unroll
+        for (int b = 0; b < kWarpEpt; ++b) {
+            const bool in = st[b] == ST_IN;
+            const unsigned cell = e[b] & kCellCov;
+            if (in && cell != kCellCov && nib_count(wt, cell)) ++ccells;
+            m[b] = __ballot_sync(0xFFFFFFFFu, in);
+            cin += __popc(m[b]);
+        }
+        ccells = __reduce_add_sync(0xFFFFFFFFu, ccells);
+        __syncwarp();
+        const bool critr = cin <= need;
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = 0;
+#pragma unroll
+        for (int b = 0; b < kWarpEpt; ++b) {
+            if ((m[b] >> lane) & 1u) {
+                dst[pos + __popc(m[b] & lt)] = e[b];                      // the row's IN list
+                if (accumulate) {
+                    const unsigned cell = e[b] & kCellCov;
+                    unsigned long long add = 0;
+                    if (cell != kCellCov && nib_of(wt, cell) == 1u) add |= 1ull;
+                    if (critr) add |= 1ull << 32;
+                    if (add) atomicAdd(&acc_w[e[b] >> kCellBits], add);
+                }
+            }
+            pos += __popc(m[b]);
+        }
+    }
+    if (lane == 0) {
+        const int slack = max(0, need - cin);
+        const int local = R - D.row_base;
+        const int words = (D.M + 31) >> 5;
+        uint32_t* slot = P.out + D.out_off + kHdrWords + words;
+        slot[local] = (uint32_t)cin;
+        slot[D.K + D.H + local] = (uint32_t)slack;
+        P.live_n[R] = cin;
+        const int unc = P.row_ncell[R] - ccells;
+        if (unc) atomicAdd(&rc.uncovered, (unsigned)unc);
+        if (slack) atomicAdd(&rc.slack, (unsigned)slack);
+    }
 }
 
 // D1 (and EVAL): one sweep of the row's CSR segment: IN counts per cell and per row; D1 adds the criticality counters
@@ -2046,8 +2188,11 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
             const int n = listn[R];
             S.rown[threadIdx.x] = n;
             S.rowoff[threadIdx.x] = P.row_off[R];
-            if (n > kWarpRow || sweep) S.rowq[atomicAdd(&S.qn[0], 1)] = (unsigned short)threadIdx.x;
-            else if (n > 0) S.rowq[kThreads - 1 - atomicAdd(&S.qn[1], 1)] = (unsigned short)threadIdx.x;
+            // whole CTA: long lists, and GREEDY lists above the match.any size (it needs a 64-bit key per cell); one warp:
+            // lists of up to 256 entries (PROP and the sweeps; a sweep also visits empty rows: they report their slack)
+            const bool cta_row = n > kWarpTabRow || (mode == MODE_GREEDY && n > kWarpRow);
+            if (cta_row) S.rowq[atomicAdd(&S.qn[0], 1)] = (unsigned short)threadIdx.x;
+            else if (n > 0 || sweep) S.rowq[kThreads - 1 - atomicAdd(&S.qn[1], 1)] = (unsigned short)threadIdx.x;
         }
         __syncthreads();
         const int nlong = S.qn[0], nshort = S.qn[1];
@@ -2064,15 +2209,27 @@ __device__ void row_phase_lists(const Params& P, const WinDesc& D, RoundCnt& rc,
                 const int ns = S.rowq[q + 1];
                 if ((int)threadIdx.x * 32 < S.rown[ns]) prefetch_l1(lists + S.rowoff[ns] + threadIdx.x * 32);
             }
-            if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], S.rowoff[slot], q & 1, from_csr, tab, S);
-            else if (sweep) { row_d1_eval(P, D, rc, R, S.rown[slot], S.rowoff[slot], q & 1, mode == MODE_D1, from_in, tab, S); __syncthreads(); }
+            // PROP and the sweeps alternate between two cell tables (the second one lies in the key table, which only GREEDY
+            // and D2 use): a row needs no barrier to protect its table from the next row's lazy zeroing
+            unsigned* t = (q & 1) ? reinterpret_cast<unsigned*>(keytab) : tab;
+            if (mode == MODE_PROP) row_prop(P, D, R, S.rown[slot], S.rowoff[slot], q & 1, from_csr, t, S);
+            else if (sweep) row_d1_eval(P, D, rc, R, S.rown[slot], S.rowoff[slot], q & 1, mode == MODE_D1, from_in, t, S);
             else { row_greedy(P, D, R, S.rown[slot], keytab, S); __syncthreads(); }
         }
+        if (nlong > 0 && nshort > 0 && mode != MODE_GREEDY) __syncthreads();     // the warps' tables alias the CTA's
+        unsigned* wt = tab + wid * kWarpTabWords;          // this warp's nibble table (the CTA rows are done with `tab`)
         for (int q = wid; q < nshort; q += kWarps) {
             const int slot = S.rowq[kThreads - 1 - q];
             const int R = D.row_base + G.cta + (base + slot) * G.ncta;
-            if (mode == MODE_PROP) warp_row_prop(P, D, R, S.rown[slot], from_csr, rows_live);
-            else warp_row_greedy(P, D, R, S.rown[slot]);
+            const int n = S.rown[slot];
+            if (mode == MODE_PROP) {
+                if (n <= kWarpRow) warp_row_prop(P, D, R, n, from_csr, rows_live);
+                else warp_tab_prop(P, D, R, n, from_csr, wt, rows_live);
+            } else if (sweep) {
+                warp_tab_d1(P, D, rc, R, n, mode == MODE_D1, from_in, wt);
+            } else {
+                warp_row_greedy(P, D, R, n);
+            }
         }
         __syncthreads();
     }
@@ -2138,8 +2295,8 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
                 if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
             }
         }
-        w1_build_row(P, D, ws, k, (k / G.ncta) & 1, tab, S);
-        __syncthreads();
+        const int par = (k / G.ncta) & 1;              // cell table and scratch alternate: no barrier between rows
+        w1_build_row(P, D, ws, k, par, par ? reinterpret_cast<unsigned*>(keytab) : tab, S);
     }
     if (!group_sync(P, G)) return false;
     trace_mark(P, G, w, tn, 11, 0, t_win);
