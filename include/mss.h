@@ -199,6 +199,98 @@ void  mss_device_free(mss_handle* h, void* p);
 int   mss_memcpy_h2d(mss_handle* h, void* dst_device, const void* src_host, size_t bytes);
 int   mss_memcpy_d2h(mss_handle* h, void* dst_host, const void* src_device, size_t bytes);
 
+/* ---- Persistent device mirror of the keyframe x map-point incidence -------------------------------------------
+ * Instead of re-walking the pointer graph for every window (MapSparsification.cc:67-151: one copy of mvpMapPoints and of
+ * mGrid per keyframe, one copy of mObservations per variable), the incidence lives in HBM and follows the map through small
+ * deltas recorded where the map changes:
+ *   KeyFrame::mvpMapPoints[idx]   AddMapPoint / EraseMapPointMatch / ReplaceMapPointMatch (src/KeyFrame.cc:299-309)   -> MSS_MOP_SLOT
+ *   MapPoint::mObservations       AddObservation / EraseObservation / SetBadFlag / Replace (src/MapPoint.cc:133-255)    -> MSS_MOP_OBS
+ *   MapPoint::nObs, mbBad         the same calls                                                                        -> MSS_MOP_MP
+ *   KeyFrame::EraseBadDescriptor  compaction of a sparsified keyframe (src/KeyFrame.cc:311-361)                         -> MSS_MOP_KF_COMPACT
+ *   a new keyframe (mvpMapPoints, mGrid; src/LocalMapping.cc ProcessNewKeyFrame)                                        -> mss_mirror_add_keyframe
+ * A window is then K keyframe handles (4 K bytes over PCIe instead of the whole flattened view): the view -- map points in
+ * discovery order = mnIndexForSparsification (MapSparsification.cc:91-99), outside keyframes ordered by their sort key
+ * (KeyFrame::mnId) -- is assembled on the device and solved in place; what comes back is a bitmask over map-point HANDLES.
+ * Handles are small dense integers chosen by the caller (keyframes: 0, 1, 2, ... ; map points likewise); the mirror grows on
+ * demand.  Layout: keyframe-major, `slots_per_kf` slots per keyframe:
+ *   slot_mp[kf][i]   handle of mvpMapPoints[i] or -1          slot_cell[kf][i]  col*48+row of the keypoint, MSS_CELL_NONE = not in mGrid
+ *   obs_mp[kf][i]    handle of the map point whose mObservations holds (kf -> i) (left index; right index for a right-only
+ *                    observation), or -1.  mObservations is mirrored on its own: it is what pass 3 reads (:125-142) and it is
+ *                    not always equal to mvpMapPoints (a keyframe LocalMapping has not processed yet holds tracked points
+ *                    that do not observe it back). */
+typedef struct mss_mirror mss_mirror;
+
+typedef enum mss_mirror_op_kind {
+    MSS_MOP_SLOT = 1,        /* a = keyframe, b = slot index, c = map-point handle or -1 */
+    MSS_MOP_OBS = 2,         /* a = keyframe, b = slot index, c = map-point handle or -1 */
+    MSS_MOP_MP = 3,          /* a = map point, b = Observations(), c = isBad() ? 1 : 0 */
+    MSS_MOP_KF_COMPACT = 4   /* a = keyframe: drop its empty slots, keep order; every kept slot's point observes it at the new index */
+} mss_mirror_op_kind;
+
+typedef struct mss_mirror_op { int32_t kind, a, b, c; } mss_mirror_op;
+
+typedef struct mss_mirror_stats {
+    int32_t n_keyframes;       /* highest keyframe handle seen + 1 */
+    int32_t n_map_points;      /* highest map-point handle seen + 1 */
+    int32_t slots_per_kf;
+    int32_t reserved_;
+    int64_t device_bytes;
+    int64_t ops_applied;
+    int64_t windows_built;
+    double  last_build_ms;     /* device time of the view assembly of the last mss_mirror_solve (CUDA events) */
+    double  last_solve_ms;     /* device time of the solve kernel of the last mss_mirror_solve */
+    double  last_total_ms;     /* host wall time of the last mss_mirror_solve */
+    int64_t last_h2d_bytes, last_d2h_bytes;
+} mss_mirror_stats;
+
+/* One window of a mirror solve.  Windows of one call must be independent (no shared map point, no shared outside
+ * keyframe that sees variables of both): they are, being disjoint covisibility components. */
+typedef struct mss_mirror_window {
+    int32_t        K;            /* window keyframes */
+    int32_t        n_max_floor;  /* as mss_window_view::n_max_floor */
+    const int32_t* kf;           /* [K] keyframe handles in window order (host memory) */
+    uint32_t*      del_bits;     /* out, host memory, indexed by map-point handle: [(del_words)] bit h = 1 <=> map point h is a
+                                    variable the selection dropped (SetBadFlag() it); only the words [h_lo/32, h_hi/32] are written */
+    int32_t        del_words;    /* capacity of del_bits in 32-bit words (>= (mss_mirror_stats.n_map_points + 31) / 32) */
+    int32_t        h_lo, h_hi;   /* out: handle range [h_lo, h_hi) of the window's map points (h_lo = h_hi = 0 when it has none) */
+    int32_t        M, H, F, O;   /* out: sizes of the view assembled on the device */
+    int32_t        n_deleted;    /* out */
+    int32_t        apply;        /* in: 1 = also apply the deletion to the mirror itself (what SetBadFlag does to the map,
+                                    src/MapPoint.cc:227-255: the points become bad, their slots and observations are cleared),
+                                    so that the hand-back does not have to travel back as deltas */
+    int32_t*       mp_handle;    /* optional out, host memory, [mp_cap]: map-point handle of every table index (bit order of
+                                    mss_result::keep_bits) */
+    int32_t        mp_cap;
+    int32_t        reserved_;
+} mss_mirror_window;
+
+int  mss_mirror_create(mss_handle* h, int32_t slots_per_kf, mss_mirror** out);
+void mss_mirror_destroy(mss_mirror* m);
+/* new keyframe `kf` (or a full refresh of an existing one): n_slots <= slots_per_kf; cells / slot_mp / obs_mp are host
+ * arrays of n_slots (obs_mp may be NULL: no observation yet) */
+int  mss_mirror_add_keyframe(mss_mirror* m, int32_t kf, uint32_t sort_key, int32_t n_slots, const uint16_t* cells,
+                             const int32_t* slot_mp, const int32_t* obs_mp);
+/* many keyframes at once (bulk load of an existing map): handles kf0 .. kf0 + n - 1, arrays of n * slots_per_kf (unused
+ * tail slots: -1 / MSS_CELL_NONE), n_slots[n], sort_key[n] */
+int  mss_mirror_add_keyframes(mss_mirror* m, int32_t kf0, int32_t n, const uint32_t* sort_key, const int32_t* n_slots,
+                              const uint16_t* cells, const int32_t* slot_mp, const int32_t* obs_mp);
+/* bulk load of map-point attributes: handles mp0 .. mp0 + n - 1 */
+int  mss_mirror_set_map_points(mss_mirror* m, int32_t mp0, int32_t n, const int32_t* nobs, const uint8_t* bad);
+/* apply ops in array order (a later op on the same address wins) */
+int  mss_mirror_apply(mss_mirror* m, const mss_mirror_op* ops, int32_t n);
+/* assemble and solve nwin windows; results[w] as in mss_solve_batch (keep_bits / kf_cov / kf_slack host buffers or NULL,
+ * keep_bits in table order = discovery order).  Synchronous. */
+int  mss_mirror_solve(mss_mirror* m, int32_t nwin, mss_mirror_window* windows, mss_result* results);
+/* debug / tests: copy the view the mirror assembles for one window into caller-sized host arrays (MSS_LAYOUT_PACKED, slots
+ * sorted by value inside each keyframe).  Pass NULL arrays to get the sizes (K, H, M, F, O) only. */
+int  mss_mirror_build_view(mss_mirror* m, const mss_mirror_window* window, int32_t* sizes5, int32_t* feat_ptr, uint32_t* slots,
+                           uint16_t* mp_nobs16, uint32_t* obs_pairs, int32_t* okf_total, int32_t* mp_handle, int32_t* okf_handle);
+/* connected components of one window (see mss_components): kf_label[K] (host) receives the component of every window
+ * keyframe, numbered in order of first appearance; n_max the window-wide nMaxObservation.  The final flush of the sparsifier
+ * solves the components as one batch of independent windows (n_max_floor = n_max). */
+int  mss_mirror_components(mss_mirror* m, const mss_mirror_window* window, int32_t* kf_label, int32_t* ncomp, int32_t* n_max);
+int  mss_mirror_get_stats(const mss_mirror* m, mss_mirror_stats* out);
+
 int   mss_get_stats(const mss_handle* h, mss_stats* out);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
 void* mss_stream(mss_handle* h);

@@ -4,8 +4,7 @@
 //
 // Replaces the GUROBI environment/model objects of the reference (GRBEnv mGRBEnv, GRBModel model:
 // /root/reference/include/MapSparsification.h:59, /root/reference/src/MapSparsification.cc:6,20,61,153-157).
-#include "../../include/mss.h"
-#include "mss_kernels.cuh"
+#include "mss_internal.h"
 #include "mss_components.cuh"
 
 #include <dlfcn.h>
@@ -24,10 +23,15 @@ using mss::Ctrl;
 using mss::Params;
 using mss::WinDesc;
 using mss::WinState;
+using mssi::DevBuf;
+using mssi::align_up;
+using mssi::ensure;
+using mssi::ensure_pinned;
+using mssi::release;
 
 // ---- NCCL through dlopen: no link-time dependency, single-GPU users never touch it ------------------------------------
 struct NcclUniqueId { char internal[128]; };
-typedef void* NcclComm;
+using mssi::NcclComm;
 struct NcclApi {
     void* lib = nullptr;
     int (*GetUniqueId)(NcclUniqueId*) = nullptr;
@@ -58,14 +62,6 @@ bool load_nccl(std::string& err) {
     return g_nccl.ok;
 }
 
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;     // elements
-};
-
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
 }  // namespace
 
 // device-resident result arrays are filled by one small kernel (one CTA per window) instead of three copies per window
@@ -84,87 +80,7 @@ __global__ void scatter_results_kernel(const ResCopy* rc) {
     if (r.slack) for (int i = threadIdx.x; i < r.rows; i += blockDim.x) r.slack[i] = (int32_t)src[r.words_keep + r.rows + i];
 }
 
-struct mss_handle {
-    mss_config cfg{};
-    int device = 0;
-    int sm_count = 0;
-    int max_ctas_per_sm = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_ready = nullptr;  // compute stream -> copy stream: the ready flags of this call have been zeroed
-    int overlap_copy = 1;            // host views: copy on the copy stream while the kernel runs (per-window ready flags); 0 = copy first
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    // device arena
-    DevBuf<uint8_t> meta;            // WinDesc[] | GroupDesc[] | cta_grp[] | gwin[]
-    DevBuf<WinState> ws;
-    DevBuf<uint8_t> st;
-    DevBuf<unsigned long long> acc;
-    DevBuf<float> gain;
-    DevBuf<unsigned> deg;
-    DevBuf<uint8_t> seen;
-    DevBuf<int> vlist;               // [2][Mpad] FREE lists
-    DevBuf<uint2> trace;             // [nwin][kTraceCap], only when tracing is on
-    bool trace_on = false;
-    std::vector<uint2> h_trace;
-    int h_trace_nwin = 0;
-    DevBuf<uint32_t> ent, live;      // CSR entries / live lists (keyframe-row segments, then outside-row segments)
-    DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
-    DevBuf<uint32_t> out;
-    DevBuf<uint8_t> stage;           // host views staged here
-    DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart | ready flags
-    unsigned* h_one = nullptr;       // pinned constant 1: source of the ready-flag copies
-    DevBuf<int> cc;                  // mss_components: parent[R + M] | row_label[R] | mp_label[M] | ncomp, n_max, err
-    Ctrl* ctrl = nullptr;            // = sync.p
-    // pinned host mirrors
-    uint8_t* h_meta = nullptr; size_t h_meta_cap = 0;
-    uint32_t* h_out = nullptr; size_t h_out_cap = 0;
-    Ctrl* h_ctrl = nullptr;
-    // comm
-    NcclComm comm = nullptr;
-    int rank = 0, nranks = 1;
-    unsigned long long watchdog_ns = 20000000000ull;
-    int tail_vars = 64, tail_ents = 256;
-    int group_ctas = 0;              // CTAs per window group; 0 = heuristic
-    // stats
-    mss_stats stats{};
-    int64_t device_bytes = 0;
-};
-
 namespace {
-
-#define MSS_CUDA(h, expr)                                                                          \
-    do {                                                                                           \
-        cudaError_t e_ = (expr);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                         \
-            return MSS_E_CUDA;                                                                     \
-        }                                                                                          \
-    } while (0)
-
-template <class T>
-int ensure(mss_handle* h, DevBuf<T>& b, size_t n) {
-    if (n <= b.cap && b.p) return MSS_OK;
-    size_t ncap = b.cap ? b.cap : 1024;
-    while (ncap < n) ncap = ncap + ncap / 2 + 1024;
-    if (b.p) { MSS_CUDA(h, cudaFree(b.p)); h->device_bytes -= (int64_t)(b.cap * sizeof(T)); b.p = nullptr; b.cap = 0; }
-    MSS_CUDA(h, cudaMalloc((void**)&b.p, ncap * sizeof(T)));
-    b.cap = ncap;
-    h->device_bytes += (int64_t)(ncap * sizeof(T));
-    return MSS_OK;
-}
-
-int ensure_pinned(mss_handle* h, void** p, size_t* cap, size_t bytes) {
-    if (bytes <= *cap && *p) return MSS_OK;
-    size_t ncap = *cap ? *cap : 4096;
-    while (ncap < bytes) ncap = ncap + ncap / 2 + 4096;
-    if (*p) { MSS_CUDA(h, cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
-    MSS_CUDA(h, cudaHostAlloc(p, ncap, cudaHostAllocDefault));
-    *cap = ncap;
-    return MSS_OK;
-}
-
-template <class T>
-void release(DevBuf<T>& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
 inline const void* slots_ptr(const mss_window_view& v) {
     return v.layout == MSS_LAYOUT_PACKED16 ? (const void*)v.slots16 : v.layout == MSS_LAYOUT_PACKED ? (const void*)v.slots : (const void*)v.feat_mp;
@@ -228,7 +144,9 @@ int validate_view(mss_handle* h, const mss_window_view& v, bool owned) {
     return MSS_OK;
 }
 
-int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_result* results) {
+}  // namespace
+
+int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_result* results) {
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     h->err.clear();
@@ -659,10 +577,9 @@ int solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views, mss_
     h->stats.last_row_entries = (int64_t)row_entries;
     h->stats.last_var_visits = (int64_t)var_visits;
     h->stats.last_total_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
+    h->last_out_off = out_off;
     return ret;
 }
-
-}  // namespace
 
 // =====================================================================================================================
 // C-ABI
@@ -756,7 +673,7 @@ int mss_set_params(mss_handle* h, int32_t min_points, float lambda, float grid_l
 int mss_solve(mss_handle* h, const mss_window_view* view, mss_result* result) {
     if (!h) return MSS_E_BADARG;
     if (h->nranks > 1) { h->err = "mss_solve on a handle with a communicator: use mss_solve_batch"; return MSS_E_BADARG; }
-    return solve_batch_impl(h, 1, view, result);
+    return mssi::solve_batch_impl(h, 1, view, result);
 }
 
 int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_label, int32_t* mp_label, int32_t* ncomp, int32_t* n_max) {
@@ -832,7 +749,7 @@ int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_labe
 
 int mss_solve_batch(mss_handle* h, int32_t nwin, const mss_window_view* views, mss_result* results) {
     if (!h) return MSS_E_BADARG;
-    return solve_batch_impl(h, nwin, views, results);
+    return mssi::solve_batch_impl(h, nwin, views, results);
 }
 
 int mss_comm_unique_id(void* out_id128) {

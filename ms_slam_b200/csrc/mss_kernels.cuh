@@ -157,6 +157,7 @@ struct Params {
                                  // of that window have landed in the staging buffer; nullptr = everything is resident
 };
 
+#ifndef MSS_KERNELS_TYPES_ONLY      // (translation units that only need the descriptors define this: mss_mirror.cu)
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -2501,5 +2502,7 @@ __global__ void __launch_bounds__(kThreads, 4) mss_persistent_kernel(const Param
     }
     if (G.cta == 0 && threadIdx.x == 0) atomicMax(&P.ctrl->t_end, globaltimer_ns());
 }
+
+#endif  // MSS_KERNELS_TYPES_ONLY
 
 }  // namespace mss

@@ -73,7 +73,10 @@ class mss_stats(C.Structure):
 SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_set_params", "mss_solve",
            "mss_solve_batch", "mss_comm_unique_id", "mss_comm_init", "mss_comm_destroy", "mss_host_alloc",
            "mss_host_free", "mss_device_alloc", "mss_device_free", "mss_memcpy_h2d", "mss_memcpy_d2h",
-           "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace", "mss_components"]
+           "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace", "mss_components",
+           # persistent device mirror (bound in ms_slam_b200/mirror.py)
+           "mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
+           "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components"]
 
 _lib = None
 

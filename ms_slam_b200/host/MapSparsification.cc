@@ -356,6 +356,10 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     ParallelChunks((size_t)H, nthreads, 4, [&](int, size_t lo, size_t hi) {
         for (size_t j = lo; j < hi; ++j) out.okf_total[j] = out.vpOutsideKFs[j]->GetNumberMPs();      // :146
     });
+    out.mp_ids.resize(M);
+    for (size_t p = 0; p < M; ++p) out.mp_ids[p] = out.vpMapPoints[p]->mnId;
+    out.okf_ids.resize(H);
+    for (int j = 0; j < H; ++j) out.okf_ids[j] = out.vpOutsideKFs[j]->mnId;
     tD = MsSince(t0);
     out.Pack();
     out.flatten_ms = MsSince(t0);
@@ -397,9 +401,29 @@ MapSparsification::MapSparsification(const std::string& strSettingsFile, Atlas* 
         std::cerr << "MapSparsification: mss_create failed (" << rc << "): no usable CUDA device; windows will be forwarded "
                      "unsparsified (there is no CPU solver)" << std::endl;
     }
+    // Persistent device mirror (MSS_MIRROR=0 turns it off: every window is then flattened from the pointer graph).  The
+    // recorder is attached to the map before any other thread runs (System constructs the sparsifier before it starts the
+    // threads, src/System.cc:159-160); keyframes already in the map are registered here.
+    if (const char* bh = std::getenv("MSS_BATCHED_HANDBACK")) mbBatchedHandback = std::atoi(bh) != 0;
+    const char* mir = std::getenv("MSS_MIRROR");
+    if (mpEngine && mpAtlas && !(mir && std::atoi(mir) == 0)) {
+        const char* sl = std::getenv("MSS_MIRROR_SLOTS");
+        const int slots = sl && std::atoi(sl) > 0 ? std::atoi(sl) : 2048;
+        if (mss_mirror_create(mpEngine, slots, &mpMirror) == MSS_OK) {
+            mpRecorder = new MirrorRecorder(slots);
+            mpAtlas->GetCurrentMap()->SetMirror(mpRecorder);
+            for (const shared_ptr<KeyFrame>& pKF : mpAtlas->GetAllKeyFrames()) mpRecorder->OnKeyFrameAdded(pKF);
+        } else {
+            mpMirror = nullptr;
+            std::cerr << "MapSparsification: device mirror unavailable: " << mss_last_error(mpEngine) << std::endl;
+        }
+    }
 }
 
 MapSparsification::~MapSparsification() {
+    if (mpAtlas && mpRecorder) mpAtlas->GetCurrentMap()->SetMirror(nullptr);
+    if (mpMirror) mss_mirror_destroy(mpMirror);
+    delete mpRecorder;
     if (mpEngine) mss_destroy(mpEngine);
 }
 
@@ -437,9 +461,129 @@ void MapSparsification::Run() {
     SetFinish();
 }
 
+int MapSparsification::EraseBatched(vector<shared_ptr<MapPoint>>& vpDrop) {
+    // first half of SetBadFlag for every point (bad, observations dropped), collecting the slots they sat in ...
+    vector<std::pair<KeyFrame*, int>> vSlots;
+    vSlots.reserve(vpDrop.size() * 4);
+    vector<shared_ptr<MapPoint>> vDone;
+    vDone.reserve(vpDrop.size());
+    for (shared_ptr<MapPoint>& pMP : vpDrop)
+        if (pMP && pMP->SetBadFlagBatched(vSlots)) vDone.emplace_back(std::move(pMP));
+    // ... then one lock per keyframe for all of its slots, and one lock of the map for its sets
+    std::sort(vSlots.begin(), vSlots.end());
+    vector<int> idx;
+    for (size_t i = 0; i < vSlots.size();) {
+        size_t j = i;
+        idx.clear();
+        while (j < vSlots.size() && vSlots[j].first == vSlots[i].first) idx.push_back(vSlots[j++].second);
+        vSlots[i].first->EraseMapPointMatches(idx);
+        i = j;
+    }
+    if (!vDone.empty() && vDone[0]->GetMap()) vDone[0]->GetMap()->EraseMapPoints(vDone);
+    return (int)vDone.size();
+}
+
+bool MapSparsification::SparsifyingFromMirror(vector<shared_ptr<KeyFrame>>& vpKFs, WindowReport& rep) {
+    const int K = (int)vpKFs.size();
+    vector<int32_t> handles(K);
+    for (int k = 0; k < K; ++k) {
+        handles[k] = vpKFs[k]->mnMirrorHandle;
+        if (handles[k] < 0) return false;                  // a keyframe the mirror does not hold (too many slots): flatten path
+    }
+    Clock::time_point t0 = Clock::now();
+    int rc = mpRecorder->Flush(mpMirror);
+    rep.flatten_ms = MsSince(t0);
+    rep.delta_ops = mpRecorder->LastFlushOps();
+    if (rc != MSS_OK) {
+        std::cerr << "MapSparsification: device mirror out of sync (" << mss_last_error(mpEngine) << "): switched off" << std::endl;
+        mpAtlas->GetCurrentMap()->SetMirror(nullptr);
+        mss_mirror_destroy(mpMirror);
+        mpMirror = nullptr;
+        return false;
+    }
+    for (int k = 0; k < K; ++k) vpKFs[k]->mnMapSaprsificationId = mnId;       // window membership stamp (:81)
+    t0 = Clock::now();
+    mss_set_params(mpEngine, mnMinNum, mfLambda, mfGridLambda);
+    // the final flush (:38-47) is block diagonal along the connected components: one independent window each
+    vector<vector<int32_t>> groups;
+    int32_t nmax = 0;
+    if (mbFlushing && K > 1) {
+        vector<int32_t> label(K);
+        int32_t ncomp = 0;
+        mss_mirror_window whole{};
+        whole.K = K; whole.kf = handles.data();
+        if (mss_mirror_components(mpMirror, &whole, label.data(), &ncomp, &nmax) == MSS_OK && ncomp > 1) {
+            // only components that hold a window keyframe become windows (an outside keyframe that sees no variable is a
+            // component of its own and constrains nothing); order of first appearance
+            vector<int> dense(ncomp, -1);
+            for (int k = 0; k < K; ++k) {
+                if (label[k] < 0 || label[k] >= ncomp) { groups.clear(); break; }
+                if (dense[label[k]] < 0) { dense[label[k]] = (int)groups.size(); groups.emplace_back(); }
+                groups[dense[label[k]]].push_back(handles[k]);
+            }
+            if (groups.size() <= 1) groups.clear();
+        }
+    }
+    if (groups.empty()) { groups.emplace_back(handles); nmax = 0; }
+    const size_t n = groups.size();
+    const size_t words = ((size_t)mpRecorder->MapPointHandles() + 31) / 32 + 1;
+    vector<mss_mirror_window> wins(n);
+    vector<mss_result> results(n);
+    vector<vector<uint32_t>> bits(n);
+    for (size_t i = 0; i < n; ++i) {
+        wins[i] = mss_mirror_window{};
+        wins[i].K = (int32_t)groups[i].size();
+        wins[i].kf = groups[i].data();
+        wins[i].n_max_floor = nmax;
+        wins[i].apply = 1;                                // the device performs the deletion on its own copy of the map
+        bits[i].assign(words, 0u);
+        wins[i].del_bits = bits[i].data();
+        wins[i].del_words = (int32_t)words;
+        results[i] = mss_result{};
+    }
+    rc = mss_mirror_solve(mpMirror, (int32_t)n, wins.data(), results.data());
+    rep.status = rc;
+    rep.solve_ms = MsSince(t0);
+    rep.components = (int)n;
+    rep.mirror = 1;
+    mss_mirror_stats ms{};
+    if (mss_mirror_get_stats(mpMirror, &ms) == MSS_OK) { rep.build_ms = ms.last_build_ms; rep.h2d_bytes = (long)ms.last_h2d_bytes; rep.d2h_bytes = (long)ms.last_d2h_bytes; }
+    if (rc != MSS_OK && rc != MSS_E_NOCONVERGE)
+        std::cerr << "MapSparsification: window " << mnId << " not (fully) sparsified: " << mss_last_error(mpEngine) << std::endl;
+    // hand-back: whatever bits came back were applied on the device; do the same to the map, without echoing it as deltas
+    t0 = Clock::now();
+    vector<shared_ptr<MapPoint>> vpDrop;
+    for (size_t i = 0; i < n; ++i) {
+        rep.H += wins[i].H; rep.M += wins[i].M;
+        rep.n_vars += results[i].n_vars; rep.n_kept += results[i].n_kept; rep.objective += results[i].objective;
+        rep.rounds = std::max(rep.rounds, results[i].rounds);
+        for (int32_t wd = wins[i].h_lo >> 5; wd < ((wins[i].h_hi + 31) >> 5); ++wd)
+            for (uint32_t b = bits[i][wd]; b; b &= b - 1u) {
+                shared_ptr<MapPoint> pMP = mpRecorder->PointOf(wd * 32 + __builtin_ctz(b));
+                if (pMP) vpDrop.emplace_back(std::move(pMP));
+            }
+    }
+    {
+        MirrorRecorder::Suppress quiet;
+        rep.n_deleted = EraseBatched(vpDrop);
+    }
+    rep.K = K;
+    if (mpLoopClosing)
+        for (const shared_ptr<KeyFrame>& pKF : vpKFs) mpLoopClosing->InsertSparsifiedKeyFrame(pKF);
+    rep.apply_ms = MsSince(t0);
+    return true;
+}
+
 void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
     mnId++;
     WindowReport rep;
+    if (mpMirror && mpRecorder && !vpKFs.empty() && SparsifyingFromMirror(vpKFs, rep)) {
+        std::unique_lock<std::mutex> lock(mMutexReports);
+        if (mReports.size() >= kMaxReports) mReports.erase(mReports.begin());
+        mReports.push_back(rep);
+        return;
+    }
+    rep = WindowReport();
     FlattenWindow(vpKFs, mnId, mLast);
     const size_t M = mLast.vpMapPoints.size();
     rep.K = mLast.K; rep.H = mLast.H; rep.M = (int)M; rep.flatten_ms = mLast.flatten_ms;
@@ -505,17 +649,29 @@ void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
 
     // hand-back: delete what the selection dropped (only variables can have a 0 bit)
     t0 = Clock::now();
-    for (size_t p = 0; p < M; ++p) {
-        if (!mLast.is_var[p]) continue;
-        if (!((mKeepBits[p >> 5] >> (p & 31)) & 1u)) {
-            mLast.vpMapPoints[p]->SetBadFlag();
-            ++rep.n_deleted;
+    if (!mbBatchedHandback) {
+        for (size_t p = 0; p < M; ++p) {                 // the reference's loop (:159-166): one SetBadFlag fan-out per point
+            if (!mLast.is_var[p]) continue;
+            if (!((mKeepBits[p >> 5] >> (p & 31)) & 1u)) {
+                mLast.vpMapPoints[p]->SetBadFlag();
+                ++rep.n_deleted;
+            }
         }
+    } else {
+        vector<shared_ptr<MapPoint>> vpDrop;
+        for (size_t p = 0; p < M; ++p)
+            if (mLast.is_var[p] && !((mKeepBits[p >> 5] >> (p & 31)) & 1u)) vpDrop.push_back(mLast.vpMapPoints[p]);
+        rep.n_deleted = EraseBatched(vpDrop);          // (with a mirror attached the hooks record the erasures as deltas)
     }
     if (mpLoopClosing)
         for (const shared_ptr<KeyFrame>& pKF : vpKFs) mpLoopClosing->InsertSparsifiedKeyFrame(pKF);
     rep.apply_ms = MsSince(t0);
+    // nothing of the window is kept alive between calls (the reference holds no state either): only the flat arrays stay
+    // for LastSnapshot()
+    vector<shared_ptr<MapPoint>>().swap(mLast.vpMapPoints);
+    vector<shared_ptr<KeyFrame>>().swap(mLast.vpOutsideKFs);
     std::unique_lock<std::mutex> lock(mMutexReports);
+    if (mReports.size() >= kMaxReports) mReports.erase(mReports.begin());
     mReports.push_back(rep);
 }
 

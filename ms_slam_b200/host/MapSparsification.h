@@ -21,6 +21,7 @@
 #else
 #include "SlamShims.h"
 #endif
+#include "MirrorRecorder.h"
 
 namespace ORB_SLAM3 {
 
@@ -31,6 +32,7 @@ struct WindowSnapshot {
     std::vector<uint8_t> is_var;                              // map point reachable through a grid cell (an ILP variable)
     std::vector<std::shared_ptr<MapPoint>> vpMapPoints;       // table order = mnIndexForSparsification = bit position
     std::vector<std::shared_ptr<KeyFrame>> vpOutsideKFs;      // ordered by KeyFrame::mnId
+    std::vector<long unsigned int> mp_ids, okf_ids;           // mnId of the above (stay valid after the objects are released)
     int K = 0, H = 0;
     double flatten_ms = 0.0;
     // MSS_LAYOUT_PACKED16 transport form of the same arrays in ONE host blob (pinned when a CUDA device is present), laid
@@ -99,13 +101,24 @@ public:
         int K = 0, H = 0, M = 0, n_vars = 0, n_kept = 0, n_deleted = 0, rounds = 0;
         int components = 1;             // independent sub-windows the window was solved as (one batch launch)
         double objective = 0.0, flatten_ms = 0.0, solve_ms = 0.0, apply_ms = 0.0;
+        int mirror = 0;                 // 1 = solved from the device mirror (flatten_ms is then the delta drain, not a graph walk)
+        long delta_ops = 0;             // records drained into the mirror before this window
+        double build_ms = 0.0;          // device time of the view assembly (mirror) inside solve_ms
+        long h2d_bytes = 0, d2h_bytes = 0;
     };
-    std::vector<WindowReport> GetReports();
+    std::vector<WindowReport> GetReports();           // the last kMaxReports windows
+    static constexpr size_t kMaxReports = 256;
+    bool MirrorActive() const { return mpMirror != nullptr; }
     const WindowSnapshot& LastSnapshot() const { return mLast; }      // valid while the thread is stopped
     bool EngineReady() const { return mpEngine != nullptr; }
 
 private:
     void Sparsifying(std::vector<std::shared_ptr<KeyFrame>>& vpKFs);
+    // Sparsifying() from the device mirror: K keyframe handles up, bitmask over map-point handles down
+    bool SparsifyingFromMirror(std::vector<std::shared_ptr<KeyFrame>>& vpKFs, WindowReport& rep);
+    // hand-back of many map points at once: one lock per keyframe and one for the map instead of the per-point
+    // SetBadFlag fan-out (src/MapSparsification.cc:159-166, src/MapPoint.cc:227-255, src/Map.cc:109-113)
+    int EraseBatched(std::vector<std::shared_ptr<MapPoint>>& vpDrop);
     bool CheckFinish();
     void SetFinish();
 
@@ -119,6 +132,9 @@ private:
     bool mbFlushing = false;            // Sparsifying() is running the final flush
 
     mss_handle* mpEngine;               // replaces GRBEnv mGRBEnv (include/MapSparsification.h:59)
+    mss_mirror* mpMirror = nullptr;     // persistent device mirror of the incidence (include/mss.h), fed by mpRecorder
+    MirrorRecorder* mpRecorder = nullptr;
+    bool mbBatchedHandback = true;      // MSS_BATCHED_HANDBACK=0: per-point SetBadFlag like the reference (flatten path only)
     float mfLambda;
     float mfGridLambda;
     int mnWindowLength;

@@ -8,6 +8,7 @@
 //     grid and marks the keyframe sparsified                         (/root/reference/src/KeyFrame.cc:311-361)
 //   * a keyframe becomes "non-local" after mnNonLocalKF consecutive updates in which it was not local  (:980-1016)
 #include "SlamShims.h"
+#include "MirrorRecorder.h"
 
 #include <algorithm>
 
@@ -29,20 +30,56 @@ int MapPoint::Observations() {
     return nObs;
 }
 
+// ---- device-mirror hooks (MirrorRecorder.h): one line where the map changes, under the object's own mutex ------------------
+static inline MirrorRecorder* Rec(Map* pMap) { return pMap ? pMap->mpMirror : nullptr; }
+
 void MapPoint::AddObservation(shared_ptr<KeyFrame> pKF, int idx) {
     const bool stereo = pKF->GetuRight(idx) >= 0.f;
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     auto it = mObservations.find(pKF);
+    int old = -1;
     if (it == mObservations.end()) mObservations.emplace(pKF, std::make_tuple(idx, -1));
-    else std::get<0>(it->second) = idx;
+    else { old = std::get<0>(it->second); std::get<0>(it->second) = idx; }
     nObs += stereo ? 2 : 1;
+    if (MirrorRecorder* r = Rec(mpMap)) {
+        if (old != -1 && old != idx) r->OnObservation(pKF.get(), old, nullptr);
+        r->OnObservation(pKF.get(), idx, this);
+        r->OnMapPoint(this, nObs, mbBad);
+    }
 }
 
 void MapPoint::UpdateObservation(shared_ptr<KeyFrame> pKF, int idx) {
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     auto it = mObservations.find(pKF);
+    int old = -1;
     if (it == mObservations.end()) mObservations.emplace(pKF, std::make_tuple(idx, -1));
-    else std::get<0>(it->second) = idx;
+    else { old = std::get<0>(it->second); std::get<0>(it->second) = idx; }
+    if (MirrorRecorder* r = Rec(mpMap)) {
+        if (old != -1 && old != idx) r->OnObservation(pKF.get(), old, nullptr);
+        r->OnObservation(pKF.get(), idx, this);
+    }
+}
+
+std::tuple<int, int> MapPoint::GetIndexInKeyFrame(shared_ptr<KeyFrame> pKF) {
+    std::unique_lock<std::mutex> lock(mMutexFeatures);
+    auto it = mObservations.find(pKF);
+    return it == mObservations.end() ? std::make_tuple(-1, -1) : it->second;
+}
+
+bool MapPoint::SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots) {
+    std::map<shared_ptr<KeyFrame>, std::tuple<int, int>> obs;
+    {
+        std::unique_lock<std::mutex> lock(mMutexFeatures);
+        if (mbBad) return false;
+        mbBad = true;
+        obs.swap(mObservations);
+        if (MirrorRecorder* r = Rec(mpMap)) r->OnMapPoint(this, nObs, true);        // (suppressed by the batched hand-back)
+    }
+    for (auto& kv : obs) {
+        if (std::get<0>(kv.second) != -1) vSlots.emplace_back(kv.first.get(), std::get<0>(kv.second));
+        if (std::get<1>(kv.second) != -1) vSlots.emplace_back(kv.first.get(), std::get<1>(kv.second));
+    }
+    return true;
 }
 
 void MapPoint::EraseObservation(shared_ptr<KeyFrame> pKF) {
@@ -54,6 +91,10 @@ void MapPoint::EraseObservation(shared_ptr<KeyFrame> pKF) {
         const int left = std::get<0>(it->second);
         if (left != -1) nObs -= (pKF->GetuRight(left) >= 0.f) ? 2 : 1;
         if (std::get<1>(it->second) != -1) nObs -= 1;
+        if (MirrorRecorder* r = Rec(mpMap)) {
+            r->OnObservation(pKF.get(), left != -1 ? left : std::get<1>(it->second), nullptr);
+            r->OnMapPoint(this, nObs, mbBad);
+        }
         mObservations.erase(it);
         discard = nObs <= 2;
     }
@@ -67,9 +108,11 @@ void MapPoint::SetBadFlag() {
         if (mbBad) return;
         mbBad = true;
         obs.swap(mObservations);
+        if (MirrorRecorder* r = Rec(mpMap)) r->OnMapPoint(this, nObs, true);
     }
     for (auto& kv : obs) {
         const int left = std::get<0>(kv.second), right = std::get<1>(kv.second);
+        if (MirrorRecorder* r = Rec(mpMap)) r->OnObservation(kv.first.get(), left != -1 ? left : right, nullptr);
         if (left != -1) kv.first->EraseMapPointMatch(left);
         if (right != -1) kv.first->EraseMapPointMatch(right);
     }
@@ -99,11 +142,29 @@ int KeyFrame::GetNumberMPs() {
 void KeyFrame::AddMapPoint(shared_ptr<MapPoint> pMP, const size_t& idx) {
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     mvpMapPoints[idx] = pMP;
+    if (MirrorRecorder* r = Rec(mpMap)) r->OnSlot(this, (int)idx, pMP.get());
 }
 
 void KeyFrame::EraseMapPointMatch(const int& idx) {
     std::unique_lock<std::mutex> lock(mMutexFeatures);
-    if (idx >= 0 && idx < (int)mvpMapPoints.size()) mvpMapPoints[idx].reset();
+    if (idx >= 0 && idx < (int)mvpMapPoints.size()) {
+        mvpMapPoints[idx].reset();
+        if (MirrorRecorder* r = Rec(mpMap)) r->OnSlot(this, idx, nullptr);
+    }
+}
+
+void KeyFrame::EraseMapPointMatches(const std::vector<int>& vIdx) {
+    std::vector<shared_ptr<MapPoint>> released;            // the last references die outside the lock
+    released.reserve(vIdx.size());
+    {
+        std::unique_lock<std::mutex> lock(mMutexFeatures);
+        for (int idx : vIdx)
+            if (idx >= 0 && idx < (int)mvpMapPoints.size() && mvpMapPoints[idx]) {
+                released.emplace_back(std::move(mvpMapPoints[idx]));
+                mvpMapPoints[idx].reset();
+                if (MirrorRecorder* r = Rec(mpMap)) r->OnSlot(this, idx, nullptr);
+            }
+    }
 }
 
 std::vector<shared_ptr<MapPoint>> KeyFrame::GetMapPointMatches() {
@@ -126,6 +187,8 @@ void KeyFrame::SetGridCell(int col, int row, size_t idx) {
 
 void KeyFrame::EraseBadDescriptor() {
     shared_ptr<KeyFrame> self = shared_from_this();
+    // the mirror gets ONE compaction record instead of one observation update per surviving slot
+    struct Note { KeyFrame* kf; MirrorRecorder::Suppress quiet; ~Note() { if (MirrorRecorder* r = Rec(kf->GetMap())) r->OnCompact(kf); } } note{this, {}};
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     ++mnEraseBadDescriptorCalls;
     std::vector<shared_ptr<MapPoint>> kept;
@@ -166,13 +229,27 @@ bool KeyFrame::isNonLocal() {
 }
 
 // ---- Map / Atlas ------------------------------------------------------------------------------------------------------
-void Map::AddKeyFrame(shared_ptr<KeyFrame> pKF) { std::unique_lock<std::mutex> l(mMutexMap); mspKeyFrames.insert(pKF); }
+void Map::AddKeyFrame(shared_ptr<KeyFrame> pKF) {
+    {
+        std::unique_lock<std::mutex> l(mMutexMap);
+        mspKeyFrames.insert(pKF);
+    }
+    if (mpMirror) mpMirror->OnKeyFrameAdded(pKF);
+}
 void Map::AddMapPoint(shared_ptr<MapPoint> pMP) { std::unique_lock<std::mutex> l(mMutexMap); mspMapPoints.insert(pMP); }
 
 void Map::EraseMapPoint(shared_ptr<MapPoint> pMP) {
     std::unique_lock<std::mutex> l(mMutexMap);
     mspMapPoints.erase(pMP);
     mspSparsifiedMapPoints.erase(pMP);
+}
+
+void Map::EraseMapPoints(const std::vector<shared_ptr<MapPoint>>& vpMPs) {
+    std::unique_lock<std::mutex> l(mMutexMap);
+    for (const shared_ptr<MapPoint>& p : vpMPs) {
+        mspMapPoints.erase(p);
+        mspSparsifiedMapPoints.erase(p);
+    }
 }
 
 void Map::AddSparsifiedMapPoint(shared_ptr<MapPoint> pMP) {

@@ -14,6 +14,7 @@
 // No OpenCV / Eigen / DBoW2: descriptors, poses and the BoW vocabulary do not influence the selection.
 #pragma once
 
+#include <atomic>
 #include <cstddef>
 #include <list>
 #include <map>
@@ -33,6 +34,8 @@ constexpr int FRAME_GRID_COLS = 64;   // include/Frame.h:45
 class KeyFrame;
 class MapPoint;
 class Map;
+class MirrorRecorder;      // MirrorRecorder.h: the map tells the device mirror what changed (hooks in SlamShims.cc = the
+                           // patch INTEGRATION.md lists for MapPoint.cc / KeyFrame.cc / Map.cc of an MS-SLAM checkout)
 
 typedef std::vector<std::vector<std::vector<size_t>>> FeatureGrid;   // [col][row] -> slot indices (KeyFrame::mGrid)
 
@@ -48,9 +51,15 @@ public:
     void SetBadFlag();
     bool isBad();
     Map* GetMap() { return mpMap; }
+    std::tuple<int, int> GetIndexInKeyFrame(shared_ptr<KeyFrame> pKF);       // src/MapPoint.cc:437-444
+    // Batched hand-back (not upstream): the first half of SetBadFlag (src/MapPoint.cc:227-243) -- mark bad, drop
+    // the observations -- returning the (keyframe, slot) pairs instead of erasing them one by one; the caller clears the
+    // slots with one lock per keyframe (KeyFrame::EraseMapPointMatches) and the map sets with one lock (Map::EraseMapPoints).
+    bool SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots);
 
     long unsigned int mnId;
     int nObs;
+    std::atomic<int> mnMirrorHandle{-1};          // handle in the device mirror (MirrorRecorder), -1 = none yet
     long unsigned int mnMapSparsificationId;      // window stamp (include/MapPoint.h:118)
     long unsigned int mnIndexForSparsification;   // bit position in the keep mask (include/MapPoint.h:122)
 
@@ -69,6 +78,7 @@ public:
     int GetNumberMPs();
     void AddMapPoint(shared_ptr<MapPoint> pMP, const size_t& idx);
     void EraseMapPointMatch(const int& idx);
+    void EraseMapPointMatches(const std::vector<int>& vIdx);      // batched hand-back: one lock for all of them (not upstream)
     void EraseBadDescriptor();
     std::vector<shared_ptr<MapPoint>> GetMapPointMatches();
     shared_ptr<MapPoint> GetMapPoint(const size_t& idx);
@@ -84,6 +94,7 @@ public:
 
     long unsigned int mnId;
     int N;
+    std::atomic<int> mnMirrorHandle{-1};         // handle in the device mirror (MirrorRecorder), -1 = not registered
     long unsigned int mnMapSaprsificationId;     // [sic] include/KeyFrame.h:191
     bool mbSparsified;                           // include/KeyFrame.h:272
     static int mnNonLocalKF;                     // include/KeyFrame.h:274
@@ -105,6 +116,9 @@ public:
     void AddKeyFrame(shared_ptr<KeyFrame> pKF);
     void AddMapPoint(shared_ptr<MapPoint> pMP);
     void EraseMapPoint(shared_ptr<MapPoint> pMP);
+    void EraseMapPoints(const std::vector<shared_ptr<MapPoint>>& vpMPs);     // batched hand-back: one lock (not upstream)
+    void SetMirror(MirrorRecorder* pRec) { mpMirror = pRec; }
+    MirrorRecorder* mpMirror = nullptr;          // set once, before the threads start
     void AddSparsifiedMapPoint(shared_ptr<MapPoint> pMP);
     void AddSparsifiedKeyFrame(shared_ptr<KeyFrame> pKF);
     std::vector<shared_ptr<KeyFrame>> GetAllKeyFrames();

@@ -92,7 +92,10 @@ int msh_build_world(void* h, int K, int H, int M, const int32_t* feat_ptr, const
         w->kfs.push_back(kf);
         map->AddKeyFrame(kf);
     }
-    for (int p = 0; p < M; ++p) w->mps[p]->nObs = mp_nobs[p];      // the view's Observations(), whatever the stereo mix was
+    for (int p = 0; p < M; ++p) {
+        w->mps[p]->nObs = mp_nobs[p];      // the view's Observations(), whatever the stereo mix was
+        if (map->mpMirror) map->mpMirror->OnMapPoint(w->mps[p].get(), mp_nobs[p], false);     // (a direct member write has no hook)
+    }
     return 0;
 }
 
@@ -124,8 +127,8 @@ void msh_snapshot_copy(void* h, int which, int32_t* feat_ptr, int32_t* feat_mp, 
     memcpy(mp_obs_ptr, s.mp_obs_ptr.data(), s.mp_obs_ptr.size() * 4);
     memcpy(mp_obs_kf, s.mp_obs_kf.data(), s.mp_obs_kf.size() * 4);
     memcpy(okf_total, s.okf_total.data(), s.okf_total.size() * 4);
-    for (size_t p = 0; p < s.vpMapPoints.size(); ++p) { mp_ids[p] = (int64_t)s.vpMapPoints[p]->mnId; is_var[p] = s.is_var[p]; }
-    for (size_t j = 0; j < s.vpOutsideKFs.size(); ++j) okf_ids[j] = (int64_t)s.vpOutsideKFs[j]->mnId;
+    for (size_t p = 0; p < s.mp_ids.size(); ++p) { mp_ids[p] = (int64_t)s.mp_ids[p]; is_var[p] = s.is_var[p]; }
+    for (size_t j = 0; j < s.okf_ids.size(); ++j) okf_ids[j] = (int64_t)s.okf_ids[j];
 }
 
 // the packed transport blob of a snapshot (MSS_LAYOUT_PACKED16): sizes first (out4 = tokens, pairs, packed flag, blob bytes),
@@ -244,7 +247,22 @@ int msh_map_counts(void* h, int64_t* out3) {
     return 0;
 }
 
-// reports of the windows processed so far: 13 doubles each
+// reports of the windows processed so far: 13 doubles each (msh_reports) / 19 with the mirror fields (msh_reports2)
+int msh_reports2(void* h, double* out, int cap_windows) {
+    World* w = static_cast<World*>(h);
+    const auto reps = w->ms->GetReports();
+    const int n = std::min(cap_windows, (int)reps.size());
+    for (int i = 0; i < n; ++i) {
+        const auto& r = reps[i];
+        double* o = out + 19 * i;
+        o[0] = r.status; o[1] = r.K; o[2] = r.H; o[3] = r.M; o[4] = r.n_vars; o[5] = r.n_kept; o[6] = r.n_deleted; o[7] = r.rounds;
+        o[8] = r.objective; o[9] = r.flatten_ms; o[10] = r.solve_ms; o[11] = r.apply_ms; o[12] = r.components;
+        o[13] = r.mirror; o[14] = (double)r.delta_ops; o[15] = r.build_ms; o[16] = (double)r.h2d_bytes; o[17] = (double)r.d2h_bytes; o[18] = 0;
+    }
+    return (int)reps.size();
+}
+int msh_mirror_active(void* h) { return static_cast<World*>(h)->ms->MirrorActive() ? 1 : 0; }
+
 int msh_reports(void* h, double* out, int cap_windows) {
     World* w = static_cast<World*>(h);
     const auto reps = w->ms->GetReports();

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "host", "libmss_host.so")
 SYMBOLS = ["msh_create", "msh_destroy", "msh_engine_ready", "msh_build_world", "msh_flatten_only", "msh_snapshot_sizes",
            "msh_snapshot_copy", "msh_start", "msh_feed", "msh_nonlocal_after", "msh_forwarded_count", "msh_wait_forwarded",
            "msh_stop_handshake", "msh_consume", "msh_finish", "msh_bad_flags", "msh_forwarded_ids", "msh_keyframe_state",
-           "msh_map_counts", "msh_reports", "msh_set_min_points", "msh_flatten_us"]
+           "msh_map_counts", "msh_reports", "msh_set_min_points", "msh_flatten_us", "msh_reports2", "msh_mirror_active"]
 _lib = None
 
 
@@ -57,13 +57,29 @@ def _p(a):
 class World:
     """One Atlas + LoopClosing + MapSparsification, populated from a WindowView."""
 
-    def __init__(self, view: WindowView, N=100, lam=500.0, grid_lam=10.0, window_length=None, inertial=False, non_local=30):
+    def __init__(self, view: WindowView, N=100, lam=500.0, grid_lam=10.0, window_length=None, inertial=False, non_local=30,
+                 mirror=None, batched_handback=None):
+        """mirror: None = the class default (device mirror on when a GPU is present), False = flatten every window from the
+        pointer graph (MSS_MIRROR=0), True = default.  batched_handback=False: per-point SetBadFlag like the reference."""
         self.lib = load_library()
         self.view = view
         self.tmp = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
         self.tmp.close()
         write_settings(self.tmp.name, N, lam, grid_lam, window_length if window_length is not None else max(view.K, 1), non_local)
-        self.h = C.c_void_p(self.lib.msh_create(self.tmp.name.encode(), 1 if inertial else 0))
+        env = {"MSS_MIRROR": None if mirror is None else ("1" if mirror else "0"),
+               "MSS_BATCHED_HANDBACK": None if batched_handback is None else ("1" if batched_handback else "0")}
+        saved = {k: os.environ.get(k) for k in env}
+        for k, v in env.items():
+            if v is not None:
+                os.environ[k] = v
+        try:
+            self.h = C.c_void_p(self.lib.msh_create(self.tmp.name.encode(), 1 if inertial else 0))
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
         self.lib.msh_build_world(self.h, view.K, view.H, view.M, _p(view.feat_ptr), _p(view.feat_mp), _p(view.feat_cell),
                                  _p(view.mp_nobs), _p(view.mp_obs_ptr), _p(view.mp_obs_kf), _p(view.okf_total))
 
@@ -148,8 +164,11 @@ class World:
         return dict(map_points=int(out[0]), sparsified_map_points=int(out[1]), sparsified_keyframes=int(out[2]))
 
     def reports(self):
-        out = np.zeros(13 * 64, np.float64)
-        n = min(self.lib.msh_reports(self.h, _p(out), 64), 64)
+        out = np.zeros(19 * 64, np.float64)
+        n = min(self.lib.msh_reports2(self.h, _p(out), 64), 64)
         keys = ["status", "K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "objective", "flatten_ms", "solve_ms", "apply_ms",
-                "components"]
-        return [dict(zip(keys, out[13 * i:13 * i + 13].tolist())) for i in range(n)]
+                "components", "mirror", "delta_ops", "build_ms", "h2d_bytes", "d2h_bytes", "_"]
+        return [dict(zip(keys, out[19 * i:19 * i + 19].tolist())) for i in range(n)]
+
+    def mirror_active(self):
+        return bool(self.lib.msh_mirror_active(self.h))

@@ -179,10 +179,10 @@ def test_thread_flow_matches_engine(hm, name, seed, over):
     from ms_slam_b200.engine import Engine
     from oracle import ilp_model as om
     view, N = msgen.make_config(name, seed, **over)
-    w = hm.World(view, N=N)
+    w = hm.World(view, N=N, mirror=False)
     eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
     try:
-        assert w.engine_ready()
+        assert w.engine_ready() and not w.mirror_active()
         w.start()
         w.feed(0, 10)                                   # trigger is "more than 10 queued" (MapSparsification.cc:197)
         assert w.wait_forwarded(1, timeout_ms=200) == -1 and w.forwarded_ids() == []
@@ -216,8 +216,32 @@ def test_thread_flow_matches_engine(hm, name, seed, over):
         assert w.map_counts()["sparsified_keyframes"] == view.K
         assert w.finish() == 0
         assert len(w.reports()) == 2 and w.reports()[1]["K"] == 0        # nothing left for the final flush
+        flat_outcome = (bad.copy(), rep["objective"], rep["n_deleted"], rep["n_kept"], rep["rounds"], w.keyframe_state().copy(),
+                        w.map_counts(), w.forwarded_ids())
     finally:
         eng.close()
+        w.close()
+    # ---- the same flow from the persistent device mirror: K keyframe handles up, a bitmask over map-point handles down; the
+    #      map must end up in exactly the same state (bit-identical to the flatten path)
+    w = hm.World(view, N=N, mirror=True)
+    try:
+        assert w.mirror_active()
+        w.start()
+        w.feed(0, 10)
+        assert w.wait_forwarded(1, timeout_ms=200) == -1
+        w.feed(10, view.K - 10)
+        assert w.wait_forwarded(view.K) == 0
+        rep = w.reports()[0]
+        assert rep["mirror"] == 1 and rep["status"] == 0
+        assert np.array_equal(w.bad_flags(), flat_outcome[0])
+        assert (rep["objective"], rep["n_deleted"], rep["n_kept"], rep["rounds"]) == flat_outcome[1:5]
+        assert rep["h2d_bytes"] < 64 * 1024 + 8 * view.K                 # handles and descriptors, not a flattened view
+        assert w.stop_handshake() == 1
+        w.consume()
+        assert w.finish() == 0
+        assert np.array_equal(w.keyframe_state(), flat_outcome[5]) and w.map_counts() == flat_outcome[6]
+        assert w.forwarded_ids() == flat_outcome[7]
+    finally:
         w.close()
 
 
@@ -227,7 +251,7 @@ def test_final_flush_takes_all_unsparsified_keyframes(hm):
     (MapSparsification.cc:38-52); the outside keyframes of the fixture are already sparsified and stay outside."""
     from ms_slam_b200.engine import Engine
     view, N = msgen.make_config("live", 2)
-    w = hm.World(view, N=N, window_length=8)
+    w = hm.World(view, N=N, window_length=8, mirror=False)
     eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
     try:
         w.start()
@@ -245,8 +269,21 @@ def test_final_flush_takes_all_unsparsified_keyframes(hm):
         assert w.forwarded_ids() == list(range(view.K))
         w.consume()                                     # quirk A.5.5: the same keyframes reach LoopClosing too -> second call
         assert (w.keyframe_state()[:view.K, 2] == 2).all()
+        st_flat = w.keyframe_state().copy()
     finally:
         eng.close()
+        w.close()
+    w = hm.World(view, N=N, window_length=8, mirror=True)     # the same shutdown from the device mirror
+    try:
+        w.start()
+        w.feed(0, 5)
+        assert w.finish() == 0
+        reps = w.reports()
+        assert len(reps) == 1 and reps[0]["mirror"] == 1 and reps[0]["K"] == view.K and reps[0]["objective"] == ref.objective
+        assert np.array_equal(w.bad_flags(), exp_bad)
+        w.consume()
+        assert np.array_equal(w.keyframe_state(), st_flat)
+    finally:
         w.close()
 
 
@@ -262,7 +299,7 @@ def test_final_flush_splits_into_components(hm):
     N = 100
     parts = [msgen.make_config("live", 41)[0], msgen.make_config("c1", 6)[0], msgen.make_config("live", 42, M=1500, H=20)[0]]
     whole = merge_views(parts, interleave=True)
-    w = hm.World(whole, N=N, window_length=8)
+    w = hm.World(whole, N=N, window_length=8, mirror=False)
     eng = Engine(N=N, lam=LAM, grid_lam=GLAM)
     try:
         w.start()
@@ -287,4 +324,15 @@ def test_final_flush_splits_into_components(hm):
         assert w.forwarded_ids() == list(range(whole.K))
     finally:
         eng.close()
+        w.close()
+    # from the device mirror: components found on the device view (mss_mirror_components), each solved from its keyframe handles
+    w = hm.World(whole, N=N, window_length=8, mirror=True)
+    try:
+        w.start()
+        w.feed(0, 5)
+        assert w.finish() == 0
+        r2 = w.reports()
+        assert len(r2) == 1 and r2[0]["mirror"] == 1 and r2[0]["status"] == 0 and r2[0]["components"] == reps[0]["components"]
+        assert np.array_equal(w.bad_flags(), exp_bad) and r2[0]["objective"] == reps[0]["objective"]
+    finally:
         w.close()
