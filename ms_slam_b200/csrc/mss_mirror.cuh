@@ -296,6 +296,7 @@ __global__ void mk_okf_collect(MirrorDev D, const MWin* W) {
     const MWin w = W[blockIdx.y];
     if (w.cnt[C_ERR]) return;
     const int klo = w.cnt[C_KFLO], khi = w.cnt[C_KFHI];
+    if (khi < klo) return;
     for (int kf = klo + blockIdx.x * blockDim.x + threadIdx.x; kf <= khi; kf += gridDim.x * blockDim.x) {
         if (!D.okf_mark[kf]) continue;
         const int p = atomicAdd(&w.cnt[C_H], 1);
@@ -456,8 +457,9 @@ __global__ void mk_reset(MirrorDev D, const MWin* W, int have_tables) {
         const int kf = w.kf[k];
         if (kf >= 0 && kf < D.n_kf && D.kf_win[kf] == w.w + 1) D.kf_win[kf] = 0;
     }
-    const int klo = w.cnt[C_KFLO], khi = w.cnt[C_KFHI];
-    for (int kf = klo + gt; kf <= khi; kf += gs) D.okf_mark[kf] = 0;
+    const int klo = w.cnt[C_KFLO], khi = w.cnt[C_KFHI];          // (INT_MAX, -1) when no variable was seen: nothing to clear
+    if (khi >= klo)
+        for (int kf = klo + gt; kf <= khi; kf += gs) D.okf_mark[kf] = 0;
 }
 
 }  // namespace mssm
