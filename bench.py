@@ -354,6 +354,63 @@ class Batch:
         self.dviews, self.pins = {}, []
 
 
+class MirrorBatch:
+    """The same B windows per GPU held in ONE persistent device mirror (include/mss.h mss_mirror_*): the maps are
+    loaded once, untimed (in a SLAM run they arrive as deltas while the map is built); a step then sends K keyframe handles per
+    window and gets a bitmask over map-point handles back."""
+
+    def __init__(self, eng, E, workload, windows, S):
+        from concurrent.futures import ThreadPoolExecutor
+        from ms_slam_b200 import msgen
+        from ms_slam_b200 import mirror as MR
+        self.eng, self.MR = eng, MR
+        self.mir = MR.Mirror(eng, S)
+        self.n = len(windows)
+        cfg = msgen.CONFIGS[workload]
+        span_kf = cfg["K"] + cfg["H"]
+
+        def make(i):
+            v = msgen.make_config(workload, seed=windows[i])[0]
+            return MR.arrays_from_view(v, S=S, seed=windows[i], kf0=i * span_kf, mp0=0, shuffle=False)
+        t0 = time.perf_counter()
+        self.kfs, mp0 = [], 0
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            for i, L in enumerate(pool.map(make, range(self.n))):
+                # map-point handles of window i start where window i-1 ended (disjoint maps = independent windows)
+                for key in ("slot_mp", "obs_mp"):
+                    L[key] = np.where(L[key] >= 0, L[key] + mp0, -1).astype(np.int32)
+                L["mp0"] = mp0
+                self.mir.load(L)
+                self.kfs.append(np.ascontiguousarray(L["window"], np.int32))
+                mp0 += L["n_mp"]
+        self.load_s = time.perf_counter() - t0
+        st = self.mir.stats()
+        words = (st["n_map_points"] + 31) // 32
+        self.cw = (MR.mss_mirror_window * self.n)()
+        self.cr = (E.mss_result * self.n)()
+        self.pins = []
+        for i in range(self.n):
+            p = eng.pinned((words + 1,), np.uint32)
+            p.array[...] = 0
+            self.pins.append(p)
+            self.cw[i].K, self.cw[i].kf = self.kfs[i].size, self.kfs[i].ctypes.data
+            self.cw[i].del_bits, self.cw[i].del_words, self.cw[i].apply = p.array.ctypes.data, words + 1, 0
+
+    def step(self):
+        return self.mir.lib.mss_mirror_solve(self.mir.handle, self.n, self.cw, self.cr)
+
+    def deleted_count(self, i):
+        w = self.cw[i]
+        lo, hi = w.h_lo >> 5, (w.h_hi + 31) >> 5
+        return int(np.unpackbits(self.pins[i].array[lo:hi].view(np.uint8)).sum())
+
+    def free(self):
+        self.mir.close()
+        for p in self.pins:
+            p.free()
+        self.pins = []
+
+
 def roofline_of(batch, kern_ms, st, peak):
     """roofline numbers of one launch of the persistent kernel over `batch` (this rank's windows)"""
     views, cr, mine = batch.views, batch.cr, batch.mine
@@ -390,23 +447,35 @@ def host_api_leg(N, lam, glam):
     from ms_slam_b200 import msgen
     from ms_slam_b200.host_mirror import World
     out = {}
-    for label, name, seed, kw in (("c2_flush", "c2", 0, {}), ("live_window", "live", 0, dict(window_length=30))):
-        try:
-            view, Nw = msgen.make_config(name, seed)
-            w = World(view, N=Nw, lam=lam, grid_lam=glam, **kw)
-            w.start()
-            if label == "live_window":
-                w.feed(0, view.K)                   # LocalMapping's hook: > 10 queued keyframes trigger a window
-                w.wait_forwarded(view.K, 60000)
-            w.finish(120000)
-            reps = w.reports()
-            r = max(reps, key=lambda x: x["M"]) if reps else {}
-            out[label] = {k: r.get(k) for k in ("K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "components", "flatten_ms",
-                                                "solve_ms", "apply_ms", "status")}
-            out[label]["mirror"] = w.mirror_report() if hasattr(w, "mirror_report") else None
-            w.close()
-        except Exception as e:      # noqa: BLE001
-            out[label] = {"error": repr(e)}
+    keys = ("K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "components", "flatten_ms", "solve_ms", "apply_ms", "status",
+            "mirror", "delta_ops", "build_ms", "h2d_bytes", "d2h_bytes")
+    for label, name, seed, kw, over in (("c2_flush", "c2", 0, {}, {}),
+                                        ("live_windows", "live", 0, dict(window_length=30), dict(K=60, M=12000))):
+        view, Nw = msgen.make_config(name, seed, **over)
+        for mode, mkw in (("device_mirror", dict(mirror=True)), ("flatten_batched_handback", dict(mirror=False)),
+                          ("flatten_per_point_setbadflag", dict(mirror=False, batched_handback=False))):
+            try:
+                w = World(view, N=Nw, lam=lam, grid_lam=glam, **kw, **mkw)
+                w.start()
+                if label == "live_windows":         # two successive 30-keyframe windows: the second one shows the steady state
+                    w.feed(0, 30)                   # LocalMapping's hook: > 10 queued keyframes trigger a window
+                    w.wait_forwarded(30, 60000)
+                    w.feed(30, 30)
+                    w.wait_forwarded(60, 60000)
+                w.finish(120000)
+                reps = [r for r in w.reports() if r["K"] > 0]
+                if label == "live_windows":
+                    out.setdefault(label, {})[mode] = {f"window_{i + 1}": {k: r.get(k) for k in keys} for i, r in enumerate(reps[:2])}
+                else:
+                    r = max(reps, key=lambda x: x["K"]) if reps else {}
+                    out.setdefault(label, {})[mode] = {k: r.get(k) for k in keys}
+                w.close()
+            except Exception as e:      # noqa: BLE001
+                out.setdefault(label, {})[mode] = {"error": repr(e)}
+    out["what"] = ("ORB_SLAM3::MapSparsification (libmss_host.so) driven like System / LocalMapping drive it; ms per window on the "
+                   "host: flatten_ms = pointer graph -> view (flatten modes) or drain of the recorded deltas into the device mirror "
+                   "(device_mirror; the first window also uploads the whole map), solve_ms = the C-ABI call incl. copies, apply_ms = "
+                   "hand-back into the map + forwarding; flatten_per_point_setbadflag is the reference's own hand-back loop")
     return out
 
 
@@ -420,6 +489,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mirror", action="store_true", help="skip the persistent-device-mirror arm")
     ap.add_argument("--no-extras", action="store_true", help="skip latency / host-API / c3 / c5 sub-entries (N=1, rank 0)")
     ap.add_argument("--order", default="discovery", choices=["generated", "discovery"],
                     help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
@@ -504,6 +574,45 @@ def main():
                "what": "mss_solve_batch with one pinned host blob per window in, pinned host keep bits + row coverage of the "
                        "owned windows out; copies inside the timed call"}
 
+    # ---- the same windows from the persistent device mirror: K keyframe handles up, deleted-handle bitmask down -------------
+    e2e_mirror = None
+    if not args.no_e2e and not args.no_mirror:
+        try:
+            mb = MirrorBatch(eng, E, args.workload, list(mine), cfg["n_feat"])
+            for _ in range(args.warmup):
+                rc = mb.step()
+                assert rc == 0, eng.lib.mss_last_error(eng.handle)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            bms, sms = [], []
+            e0.record(stream)
+            for _ in range(args.steps):
+                rc = mb.step()
+                st_m = mb.mir.stats()
+                bms.append(st_m["last_build_ms"]); sms.append(st_m["last_solve_ms"])
+            e1.record(stream)
+            barrier()
+            assert rc == 0, eng.lib.mss_last_error(eng.handle)
+            ms_m = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms_m], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_m = float(t.item())
+            same = all(mb.cr[i].objective == batch.cr[w].objective and mb.cr[i].n_kept == batch.cr[w].n_kept and
+                       mb.deleted_count(i) == batch.cr[w].n_vars - batch.cr[w].n_kept for i, w in enumerate(mine))
+            assert same, "mirror arm and view arm disagree"
+            e2e_mirror = {"value": nwin * args.steps / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m / args.steps,
+                          "h2d_bytes_per_step": int(st_m["last_h2d_bytes"]), "d2h_bytes_per_step": int(st_m["last_d2h_bytes"]),
+                          "assembly_ms_per_step": float(np.mean(bms)), "solve_kernel_ms_per_step": float(np.mean(sms)),
+                          "mirror_device_bytes": int(st_m["device_bytes"]), "map_load_s_untimed": mb.load_s,
+                          "same_result_as_view_arm": True,
+                          "what": "mss_mirror_solve: the maps of all windows live in one persistent device mirror (loaded once, "
+                                  "untimed: in a SLAM run they arrive as deltas); per step K keyframe handles per window go up, the view "
+                                  "is assembled on the device, the deleted-map-point bitmask comes back"}
+            mb.free()
+        except Exception as e:      # noqa: BLE001
+            e2e_mirror = {"error": repr(e)}
+
     # ---- what was timed is right: every owned window solved; both arms returned the same bitmask -----------------------
     cr = batch.cr
     for w in mine:
@@ -568,6 +677,7 @@ def main():
                              else f"per-step inputs {batch.in_bytes/1e6:.0f} MB per GPU (< L2)",
                        "kernel_ms_per_step": kern_ms, "grid_ctas": st_dev["grid_ctas"], "quality": quality, "numa": numa},
             "e2e": e2e,
+            "e2e_mirror": e2e_mirror,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -10,7 +10,6 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
-#include <unordered_map>
 
 using mssi::DevBuf;
 using mssi::align_up;
@@ -419,16 +418,33 @@ int mss_mirror_apply(mss_mirror* m, const mss_mirror_op* ops, int32_t n) {
     int* d_err = reinterpret_cast<int*>(m->upload.p + align_up((size_t)n * sizeof(DevOp), 16));
     MSS_CUDA(h, cudaMemsetAsync(d_err, 0, 4, h->stream));
     std::vector<DevOp> seg;
-    std::unordered_map<uint64_t, int> last;
     size_t up_off = 0;
+    // last op per address: open addressing over (key -> index of the last op seen), sized for the segment
+    std::vector<uint64_t> tkey;
+    std::vector<int> tval;
+    auto key_of = [](const DevOp& o) {
+        return ((uint64_t)o.kind << 60) | ((uint64_t)(uint32_t)o.a << 24) | (uint64_t)(uint32_t)(o.kind == MSS_MOP_MP ? 0 : o.b);
+    };
     auto flush = [&]() -> int {
         if (seg.empty()) return MSS_OK;
-        std::vector<DevOp> uniq;
-        uniq.reserve(last.size());
+        size_t cap = 16;
+        while (cap < seg.size() * 2) cap <<= 1;
+        tkey.assign(cap, ~0ull);
+        tval.assign(cap, -1);
         for (size_t i = 0; i < seg.size(); ++i) {
-            const DevOp& o = seg[i];
-            const uint64_t key = ((uint64_t)o.kind << 60) | ((uint64_t)(uint32_t)o.a << 24) | (uint64_t)(uint32_t)(o.kind == 3 ? 0 : o.b);
-            if (last[key] == (int)i) uniq.push_back(o);
+            const uint64_t key = key_of(seg[i]);
+            size_t s = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1);
+            while (tkey[s] != ~0ull && tkey[s] != key) s = (s + 1) & (cap - 1);
+            tkey[s] = key;
+            tval[s] = (int)i;
+        }
+        std::vector<DevOp> uniq;
+        uniq.reserve(seg.size());
+        for (size_t i = 0; i < seg.size(); ++i) {
+            const uint64_t key = key_of(seg[i]);
+            size_t s = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1);
+            while (tkey[s] != key) s = (s + 1) & (cap - 1);
+            if (tval[s] == (int)i) uniq.push_back(seg[i]);
         }
         MSS_CUDA(h, cudaMemcpyAsync(m->upload.p + up_off, uniq.data(), uniq.size() * sizeof(DevOp), cudaMemcpyHostToDevice, h->stream));
         MSS_CUDA(h, cudaStreamSynchronize(h->stream));           // `uniq` is pageable and dies with this scope
@@ -439,7 +455,6 @@ int mss_mirror_apply(mss_mirror* m, const mss_mirror_op* ops, int32_t n) {
         m->stats.last_h2d_bytes += (int64_t)(uniq.size() * sizeof(DevOp));
         up_off += align_up(uniq.size() * sizeof(DevOp), 16);
         seg.clear();
-        last.clear();
         return MSS_OK;
     };
     m->stats.last_h2d_bytes = 0;
@@ -452,8 +467,6 @@ int mss_mirror_apply(mss_mirror* m, const mss_mirror_op* ops, int32_t n) {
             h->stats.kernel_launches += 1;
             continue;
         }
-        const uint64_t key = ((uint64_t)o.kind << 60) | ((uint64_t)(uint32_t)o.a << 24) | (uint64_t)(uint32_t)(o.kind == MSS_MOP_MP ? 0 : o.b);
-        last[key] = (int)seg.size();
         seg.push_back(DevOp{o.kind, o.a, o.b, o.c});
     }
     if ((rc = flush())) return rc;

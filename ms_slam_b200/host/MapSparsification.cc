@@ -421,6 +421,7 @@ MapSparsification::MapSparsification(const std::string& strSettingsFile, Atlas* 
 }
 
 MapSparsification::~MapSparsification() {
+    if (mGraveThread.joinable()) mGraveThread.join();
     if (mpAtlas && mpRecorder) mpAtlas->GetCurrentMap()->SetMirror(nullptr);
     if (mpMirror) mss_mirror_destroy(mpMirror);
     delete mpRecorder;
@@ -462,25 +463,34 @@ void MapSparsification::Run() {
 }
 
 int MapSparsification::EraseBatched(vector<shared_ptr<MapPoint>>& vpDrop) {
+    // Everything that only frees memory (the dropped points themselves, the tree nodes of their observation maps) is
+    // collected and destroyed by a helper thread: the window is done when the map no longer shows the points.
+    struct Grave {
+        vector<shared_ptr<MapPoint>> points;
+        vector<MapPoint::ObsMap> maps;
+    };
+    std::unique_ptr<Grave> grave(new Grave());
     // first half of SetBadFlag for every point (bad, observations dropped), collecting the slots they sat in ...
     vector<std::pair<KeyFrame*, int>> vSlots;
     vSlots.reserve(vpDrop.size() * 4);
     vector<shared_ptr<MapPoint>> vDone;
     vDone.reserve(vpDrop.size());
+    grave->maps.reserve(vpDrop.size());
     for (shared_ptr<MapPoint>& pMP : vpDrop)
-        if (pMP && pMP->SetBadFlagBatched(vSlots)) vDone.emplace_back(std::move(pMP));
+        if (pMP && pMP->SetBadFlagBatched(vSlots, &grave->maps)) vDone.emplace_back(std::move(pMP));
     // ... then one lock per keyframe for all of its slots, and one lock of the map for its sets
-    std::sort(vSlots.begin(), vSlots.end());
-    vector<int> idx;
-    for (size_t i = 0; i < vSlots.size();) {
-        size_t j = i;
-        idx.clear();
-        while (j < vSlots.size() && vSlots[j].first == vSlots[i].first) idx.push_back(vSlots[j++].second);
-        vSlots[i].first->EraseMapPointMatches(idx);
-        i = j;
-    }
+    std::unordered_map<KeyFrame*, vector<int>> byKF;
+    byKF.reserve(1024);
+    for (const std::pair<KeyFrame*, int>& s : vSlots) byKF[s.first].push_back(s.second);
+    grave->points.reserve(vSlots.size() + vDone.size());
+    for (auto& kv : byKF) kv.first->EraseMapPointMatches(kv.second, &grave->points);
     if (!vDone.empty() && vDone[0]->GetMap()) vDone[0]->GetMap()->EraseMapPoints(vDone);
-    return (int)vDone.size();
+    const int n = (int)vDone.size();
+    for (shared_ptr<MapPoint>& p : vDone) grave->points.emplace_back(std::move(p));
+    if (mGraveThread.joinable()) mGraveThread.join();
+    Grave* raw = grave.release();
+    mGraveThread = std::thread([raw]() { delete raw; });
+    return n;
 }
 
 bool MapSparsification::SparsifyingFromMirror(vector<shared_ptr<KeyFrame>>& vpKFs, WindowReport& rep) {

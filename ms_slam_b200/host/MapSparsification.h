@@ -10,6 +10,7 @@
 
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mss.h"
@@ -134,6 +135,7 @@ private:
     mss_handle* mpEngine;               // replaces GRBEnv mGRBEnv (include/MapSparsification.h:59)
     mss_mirror* mpMirror = nullptr;     // persistent device mirror of the incidence (include/mss.h), fed by mpRecorder
     MirrorRecorder* mpRecorder = nullptr;
+    std::thread mGraveThread;           // frees what a batched hand-back released (see EraseBatched)
     bool mbBatchedHandback = true;      // MSS_BATCHED_HANDBACK=0: per-point SetBadFlag like the reference (flatten path only)
     float mfLambda;
     float mfGridLambda;

@@ -30,7 +30,11 @@ int MirrorRecorder::HandleOf(MapPoint* pMP) {
     h = pMP->mnMirrorHandle.load(std::memory_order_relaxed);
     if (h >= 0) return h;
     h = mnNextMP.fetch_add(1);
-    if ((size_t)h >= mvPoints.size()) mvPoints.resize((size_t)h + 1 + mvPoints.size() / 2);
+    if ((size_t)h >= mvPoints.size()) {
+        const size_t n = (size_t)h + 1 + mvPoints.size() / 2;
+        mvPoints.resize(n);
+        mvMpNobs.resize(n, 0); mvMpBad.resize(n, 0); mvMpDirty.resize(n, 0);
+    }
     mvPoints[h] = pMP->weak_from_this();
     pMP->mnMirrorHandle.store(h, std::memory_order_release);
     return h;
@@ -72,7 +76,6 @@ void MirrorRecorder::OnKeyFrameAdded(const std::shared_ptr<KeyFrame>& pKF) {
             for (size_t i : grid[col][row])
                 if (i < (size_t)n) add.cells[i] = (uint16_t)(col * MSS_GRID_ROWS + row);
     const std::vector<std::shared_ptr<MapPoint>> now = pKF->GetMapPointMatches();
-    std::vector<Rec> attrs;
     for (int i = 0; i < n && i < (int)now.size(); ++i) {
         const std::shared_ptr<MapPoint>& pMP = now[i];
         if (!pMP) continue;
@@ -80,11 +83,17 @@ void MirrorRecorder::OnKeyFrameAdded(const std::shared_ptr<KeyFrame>& pKF) {
         add.slot[i] = h;
         const std::tuple<int, int> idx = pMP->GetIndexInKeyFrame(pKF);
         if (std::get<0>(idx) == i || (std::get<0>(idx) == -1 && std::get<1>(idx) == i)) add.obs[i] = h;
-        attrs.push_back(Rec{MSS_MOP_MP, h, pMP->Observations(), pMP->isBad() ? 1 : 0});
+        {
+            // a point possibly first met through this keyframe: attributes as of now (read before mMutexPoints is taken: the
+            // hooks take it while they hold the point's own mutex)
+            const int nObs = pMP->Observations();
+            const bool bad = pMP->isBad();
+            std::unique_lock<std::mutex> lock(mMutexPoints);
+            if (!mvMpDirty[h]) { mvMpNobs[h] = nObs; mvMpBad[h] = bad ? 1 : 0; mvMpDirty[h] = 1; mvDirty.push_back(h); }
+        }
     }
     std::unique_lock<std::mutex> lock(mMutexQueue);
     mvAdds[at] = std::move(add);
-    mvQueue.insert(mvQueue.end(), attrs.begin(), attrs.end());
 }
 
 void MirrorRecorder::OnSlot(KeyFrame* pKF, int idx, MapPoint* pMP) {
@@ -101,7 +110,11 @@ void MirrorRecorder::OnObservation(KeyFrame* pKF, int idx, MapPoint* pMP) {
 
 void MirrorRecorder::OnMapPoint(MapPoint* pMP, int nObs, bool bBad) {
     if (Suppress::Depth() || !pMP) return;
-    Push(MSS_MOP_MP, HandleOf(pMP), nObs, bBad ? 1 : 0);
+    const int h = HandleOf(pMP);
+    std::unique_lock<std::mutex> lock(mMutexPoints);
+    mvMpNobs[h] = nObs;
+    mvMpBad[h] = bBad ? 1 : 0;
+    if (!mvMpDirty[h]) { mvMpDirty[h] = 1; mvDirty.push_back(h); }
 }
 
 void MirrorRecorder::OnCompact(KeyFrame* pKF) {
@@ -121,6 +134,16 @@ int MirrorRecorder::Flush(mss_mirror* m) {
     }
     int rc = MSS_OK;
     std::vector<mss_mirror_op> ops;
+    {
+        std::unique_lock<std::mutex> lock(mMutexPoints);
+        ops.reserve(mvDirty.size() + q.size());
+        for (int32_t h : mvDirty) {
+            ops.push_back(mss_mirror_op{MSS_MOP_MP, h, mvMpNobs[h], (int32_t)mvMpBad[h]});
+            mvMpDirty[h] = 0;
+        }
+        mvDirty.clear();
+    }
+    const long nAttr = (long)ops.size();
     auto send = [&]() {
         if (ops.empty() || rc != MSS_OK) { ops.clear(); return; }
         rc = mss_mirror_apply(m, ops.data(), (int32_t)ops.size());
@@ -150,7 +173,7 @@ int MirrorRecorder::Flush(mss_mirror* m) {
         i = j;
     }
     send();
-    mLastFlushOps = (long)q.size();
+    mLastFlushOps = (long)q.size() + nAttr;
     mLastFlushMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }

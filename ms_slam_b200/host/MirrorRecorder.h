@@ -75,6 +75,10 @@ private:
     std::vector<KfAdd> mvAdds;
     std::mutex mMutexPoints;
     std::vector<std::weak_ptr<MapPoint>> mvPoints;                 // handle -> object
+    // nObs / mbBad change with almost every map operation: only the latest values per point travel (one op per dirty point)
+    std::vector<int32_t> mvMpNobs;
+    std::vector<uint8_t> mvMpBad, mvMpDirty;
+    std::vector<int32_t> mvDirty;
     double mLastFlushMs = 0.0;
     long mLastFlushOps = 0;
 };

@@ -66,8 +66,8 @@ std::tuple<int, int> MapPoint::GetIndexInKeyFrame(shared_ptr<KeyFrame> pKF) {
     return it == mObservations.end() ? std::make_tuple(-1, -1) : it->second;
 }
 
-bool MapPoint::SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots) {
-    std::map<shared_ptr<KeyFrame>, std::tuple<int, int>> obs;
+bool MapPoint::SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots, std::vector<ObsMap>* pGrave) {
+    ObsMap obs;
     {
         std::unique_lock<std::mutex> lock(mMutexFeatures);
         if (mbBad) return false;
@@ -79,6 +79,7 @@ bool MapPoint::SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots)
         if (std::get<0>(kv.second) != -1) vSlots.emplace_back(kv.first.get(), std::get<0>(kv.second));
         if (std::get<1>(kv.second) != -1) vSlots.emplace_back(kv.first.get(), std::get<1>(kv.second));
     }
+    if (pGrave) pGrave->emplace_back(std::move(obs));       // the tree nodes are freed off the critical path
     return true;
 }
 
@@ -153,9 +154,10 @@ void KeyFrame::EraseMapPointMatch(const int& idx) {
     }
 }
 
-void KeyFrame::EraseMapPointMatches(const std::vector<int>& vIdx) {
-    std::vector<shared_ptr<MapPoint>> released;            // the last references die outside the lock
-    released.reserve(vIdx.size());
+void KeyFrame::EraseMapPointMatches(const std::vector<int>& vIdx, std::vector<shared_ptr<MapPoint>>* pGrave) {
+    std::vector<shared_ptr<MapPoint>> local;               // the last references die outside the lock
+    std::vector<shared_ptr<MapPoint>>& released = pGrave ? *pGrave : local;
+    released.reserve(released.size() + vIdx.size());
     {
         std::unique_lock<std::mutex> lock(mMutexFeatures);
         for (int idx : vIdx)
@@ -246,10 +248,25 @@ void Map::EraseMapPoint(shared_ptr<MapPoint> pMP) {
 
 void Map::EraseMapPoints(const std::vector<shared_ptr<MapPoint>>& vpMPs) {
     std::unique_lock<std::mutex> l(mMutexMap);
-    for (const shared_ptr<MapPoint>& p : vpMPs) {
-        mspMapPoints.erase(p);
-        mspSparsifiedMapPoints.erase(p);
+    if (vpMPs.size() * 8 < mspMapPoints.size()) {          // few: one lookup each
+        for (const shared_ptr<MapPoint>& p : vpMPs) {
+            mspMapPoints.erase(p);
+            mspSparsifiedMapPoints.erase(p);
+        }
+        return;
     }
+    // many (a sparsified window loses ~90 % of its points): one sweep over the sets instead of a tree search per point
+    std::vector<const MapPoint*> victims;
+    victims.reserve(vpMPs.size());
+    for (const shared_ptr<MapPoint>& p : vpMPs) victims.push_back(p.get());
+    std::sort(victims.begin(), victims.end());
+    auto sweep = [&](std::set<shared_ptr<MapPoint>, ById>& st) {
+        for (auto it = st.begin(); it != st.end();)
+            if (std::binary_search(victims.begin(), victims.end(), (const MapPoint*)it->get())) it = st.erase(it);
+            else ++it;
+    };
+    sweep(mspMapPoints);
+    if (!mspSparsifiedMapPoints.empty()) sweep(mspSparsifiedMapPoints);
 }
 
 void Map::AddSparsifiedMapPoint(shared_ptr<MapPoint> pMP) {

@@ -55,7 +55,8 @@ public:
     // Batched hand-back (not upstream): the first half of SetBadFlag (src/MapPoint.cc:227-243) -- mark bad, drop
     // the observations -- returning the (keyframe, slot) pairs instead of erasing them one by one; the caller clears the
     // slots with one lock per keyframe (KeyFrame::EraseMapPointMatches) and the map sets with one lock (Map::EraseMapPoints).
-    bool SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots);
+    typedef std::map<shared_ptr<KeyFrame>, std::tuple<int, int>> ObsMap;
+    bool SetBadFlagBatched(std::vector<std::pair<KeyFrame*, int>>& vSlots, std::vector<ObsMap>* pGrave = nullptr);
 
     long unsigned int mnId;
     int nObs;
@@ -78,7 +79,8 @@ public:
     int GetNumberMPs();
     void AddMapPoint(shared_ptr<MapPoint> pMP, const size_t& idx);
     void EraseMapPointMatch(const int& idx);
-    void EraseMapPointMatches(const std::vector<int>& vIdx);      // batched hand-back: one lock for all of them (not upstream)
+    // batched hand-back: one lock for all of them (not upstream); the emptied slots' references go to pGrave when given
+    void EraseMapPointMatches(const std::vector<int>& vIdx, std::vector<shared_ptr<MapPoint>>* pGrave = nullptr);
     void EraseBadDescriptor();
     std::vector<shared_ptr<MapPoint>> GetMapPointMatches();
     shared_ptr<MapPoint> GetMapPoint(const size_t& idx);

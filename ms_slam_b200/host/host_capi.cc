@@ -85,7 +85,9 @@ int msh_build_world(void* h, int K, int H, int M, const int32_t* feat_ptr, const
             std::shared_ptr<MapPoint> mp;
             if (i < (int)outside[j].size()) mp = w->mps[outside[j][i]];
             else { mp = std::make_shared<MapPoint>(next_mp++, map); map->AddMapPoint(mp); w->mps.push_back(mp); mp->nObs = 3; }
-            kf->AddMapPoint(mp, (size_t)i);
+            // GetNumberMPs() must come out as okf_total[j]: observers beyond that number observe the keyframe without
+            // sitting in one of its slots (mObservations and mvpMapPoints are separate structures upstream too)
+            if (i < okf_total[j]) kf->AddMapPoint(mp, (size_t)i);
             mp->AddObservation(kf, i);
         }
         kf->mbSparsified = true;            // processed by an earlier window: the final flush must not pick it up again

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from .engine import Engine, MssError, Result, mss_result, unpack_bits, MSS_OK, MSS_E_BADARG, MSS_E_NOCONVERGE
-from .window import PackedView
+from .window import PackedView, CELL_NONE
 
 MOP_SLOT, MOP_OBS, MOP_MP, MOP_KF_COMPACT = 1, 2, 3, 4
 OP_DTYPE = np.dtype([("kind", np.int32), ("a", np.int32), ("b", np.int32), ("c", np.int32)])
@@ -198,3 +198,51 @@ class Mirror:
         view = PackedView(K=K, H=H, M=M, feat_ptr=feat_ptr, slots=slots[:F].copy(), mp_nobs16=nobs16[:M].copy(),
                           obs_pairs=pairs[:O].copy(), okf_total=okf_total[:H].copy(), meta=dict(packed=True), n_max_floor=n_max_floor)
         return view, mp_handle[:M].copy(), okf_handle[:H].copy()
+
+
+def arrays_from_view(view, S=None, seed=0, kf0=0, mp0=0, shuffle=True):
+    """A map that flattens to `view`: window keyframes get handles kf0..kf0+K-1, outside keyframes kf0+K.., map points
+    mp0 + a random permutation of their table index (so the discovery numbering is not the identity), filler points behind
+    them bring every outside keyframe to its GetNumberMPs().  Returns dict(S, n_slots, cells, slot_mp, obs_mp, nobs, bad,
+    mp_of_table, window) ready for Mirror.load (tests, bench; oracle/mirror_model.py uses the same arrays)."""
+    K, H, M = view.K, view.H, view.M
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(M) if shuffle else np.arange(M)
+    mp_of = (mp0 + perm).astype(np.int64)                        # table index -> handle
+    obs_mp_tab = np.repeat(np.arange(M, dtype=np.int64), np.diff(view.mp_obs_ptr))
+    out = view.mp_obs_kf >= K
+    cnt_out = np.bincount(view.mp_obs_kf[out] - K, minlength=H) if H else np.zeros(0, np.int64)
+    n_win = np.diff(view.feat_ptr).astype(np.int64)
+    n_out = np.maximum(cnt_out, view.okf_total.astype(np.int64)) if H else np.zeros(0, np.int64)
+    if S is None:
+        S = int(max(n_win.max(initial=1), n_out.max(initial=1)))
+    n_slots = np.concatenate([n_win, n_out]).astype(np.int32)
+    slot_mp = np.full((K + H, S), -1, np.int32)
+    obs = np.full((K + H, S), -1, np.int32)
+    cells = np.full((K + H, S), CELL_NONE, np.uint16)
+    kf_of_slot = np.repeat(np.arange(K), n_win)
+    idx_in_kf = np.arange(view.F) - np.repeat(view.feat_ptr[:-1].astype(np.int64), n_win)
+    has = view.feat_mp >= 0
+    slot_mp[kf_of_slot[has], idx_in_kf[has]] = mp_of[view.feat_mp[has]]
+    obs[kf_of_slot[has], idx_in_kf[has]] = mp_of[view.feat_mp[has]]
+    cells[kf_of_slot, idx_in_kf] = view.feat_cell
+    next_mp = mp0 + M
+    fill_nobs = []
+    for j in range(H):
+        mps = obs_mp_tab[out][view.mp_obs_kf[out] - K == j]
+        tot = int(view.okf_total[j])
+        # GetNumberMPs() must come out as okf_total[j]: the first `tot` observers sit in a slot, further observers (a view may
+        # list more observers than valid slots) only observe; filler points bring the slots up to `tot`
+        obs[K + j, :mps.size] = mp_of[mps]
+        slot_mp[K + j, :min(mps.size, tot)] = mp_of[mps[:tot]]
+        extra = tot - mps.size
+        if extra > 0:
+            slot_mp[K + j, mps.size:tot] = np.arange(next_mp, next_mp + extra)
+            obs[K + j, mps.size:tot] = np.arange(next_mp, next_mp + extra)
+            next_mp += extra
+            fill_nobs += [3] * extra
+    nobs = np.zeros(next_mp - mp0, np.int32)
+    nobs[perm] = view.mp_nobs
+    nobs[M:] = fill_nobs
+    return dict(S=S, n_slots=n_slots, cells=cells, slot_mp=slot_mp, obs_mp=obs, nobs=nobs, mp_of_table=mp_of.astype(np.int32),
+                window=np.arange(kf0, kf0 + K, dtype=np.int32), kf0=kf0, mp0=mp0, n_mp=int(next_mp - mp0))

@@ -155,46 +155,4 @@ class MirrorModel:
         return view, mp_handle.astype(np.int32), okf.astype(np.int32)
 
 
-def load_view(view: WindowView, S=None, seed=0, kf0=0, mp0=0, shuffle=True):
-    """A map that flattens to `view`: window keyframes get handles kf0..kf0+K-1, outside keyframes kf0+K.., map points
-    mp0 + a random permutation of their table index (so the discovery numbering is not the identity), filler points behind
-    them bring every outside keyframe to its GetNumberMPs().  Returns dict(S, n_slots, cells, slot_mp, obs_mp, nobs, bad,
-    mp_of_table, window) ready for MirrorModel.add_keyframes / the device mirror."""
-    K, H, M = view.K, view.H, view.M
-    rng = np.random.default_rng(seed)
-    perm = rng.permutation(M) if shuffle else np.arange(M)
-    mp_of = (mp0 + perm).astype(np.int64)                        # table index -> handle
-    obs_mp_tab = np.repeat(np.arange(M, dtype=np.int64), np.diff(view.mp_obs_ptr))
-    out = view.mp_obs_kf >= K
-    cnt_out = np.bincount(view.mp_obs_kf[out] - K, minlength=H) if H else np.zeros(0, np.int64)
-    n_win = np.diff(view.feat_ptr).astype(np.int64)
-    n_out = np.maximum(cnt_out, view.okf_total.astype(np.int64)) if H else np.zeros(0, np.int64)
-    if S is None:
-        S = int(max(n_win.max(initial=1), n_out.max(initial=1)))
-    n_slots = np.concatenate([n_win, n_out]).astype(np.int32)
-    slot_mp = np.full((K + H, S), -1, np.int32)
-    obs = np.full((K + H, S), -1, np.int32)
-    cells = np.full((K + H, S), CELL_NONE, np.uint16)
-    kf_of_slot = np.repeat(np.arange(K), n_win)
-    idx_in_kf = np.arange(view.F) - np.repeat(view.feat_ptr[:-1].astype(np.int64), n_win)
-    has = view.feat_mp >= 0
-    slot_mp[kf_of_slot[has], idx_in_kf[has]] = mp_of[view.feat_mp[has]]
-    obs[kf_of_slot[has], idx_in_kf[has]] = mp_of[view.feat_mp[has]]
-    cells[kf_of_slot, idx_in_kf] = view.feat_cell
-    next_mp = mp0 + M
-    fill_nobs = []
-    for j in range(H):
-        mps = obs_mp_tab[out][view.mp_obs_kf[out] - K == j]
-        slot_mp[K + j, :mps.size] = mp_of[mps]
-        obs[K + j, :mps.size] = mp_of[mps]
-        extra = int(n_out[j] - mps.size)
-        if extra > 0:
-            slot_mp[K + j, mps.size:mps.size + extra] = np.arange(next_mp, next_mp + extra)
-            obs[K + j, mps.size:mps.size + extra] = np.arange(next_mp, next_mp + extra)
-            next_mp += extra
-            fill_nobs += [3] * extra
-    nobs = np.zeros(next_mp - mp0, np.int32)
-    nobs[perm] = view.mp_nobs
-    nobs[M:] = fill_nobs
-    return dict(S=S, n_slots=n_slots, cells=cells, slot_mp=slot_mp, obs_mp=obs, nobs=nobs, mp_of_table=mp_of.astype(np.int32),
-                window=np.arange(kf0, kf0 + K, dtype=np.int32), kf0=kf0, mp0=mp0, n_mp=int(next_mp - mp0))
+from ms_slam_b200.mirror import arrays_from_view as load_view      # noqa: E402,F401  (test helper: a map that flattens to a view)
