@@ -370,7 +370,9 @@ class MirrorBatch:
         span_kf = cfg["K"] + cfg["H"]
 
         def make(i):
-            v = msgen.make_config(workload, seed=windows[i])[0]
+            # map-point handles in discovery order: the recorder hands them out at first sight, keyframe after keyframe, i.e.
+            # in the order the map was built (the view arm numbers its transport form the same way)
+            v = msgen.make_config(workload, seed=windows[i])[0].compact().discovery_order()
             return MR.arrays_from_view(v, S=S, seed=windows[i], kf0=i * span_kf, mp0=0, shuffle=False)
         t0 = time.perf_counter()
         self.kfs, mp0 = [], 0

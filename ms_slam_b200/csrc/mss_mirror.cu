@@ -23,10 +23,11 @@ struct mss_mirror {
     int S = 0;
     int n_kf = 0, n_mp = 0;                   // handles in use: [0, n)
     size_t kf_cap = 0, mp_cap = 0;
-    DevBuf<int> slot_mp, obs_mp, kf_n, kf_win, okf_idx, mp_nobs, obs_lo, obs_hi, first, loc, owner;
+    DevBuf<int> slot_mp, obs_mp, kf_n, kf_win, okf_idx;
     DevBuf<uint16_t> slot_cell;
     DevBuf<unsigned> kf_key;
-    DevBuf<uint8_t> okf_mark, mp_bad, isvar;
+    DevBuf<uint8_t> okf_mark;
+    DevBuf<MpRec> mp;
     DevBuf<uint8_t> win;                      // per-call window buffers (descriptors, handle lists, counts, view arrays)
     DevBuf<uint8_t> upload;                   // staging of ops / bulk loads
     uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;    // pinned: descriptors up, counters and bitmask words down
@@ -39,8 +40,7 @@ namespace {
 MirrorDev dev_of(const mss_mirror* m) {
     MirrorDev D;
     D.slot_mp = m->slot_mp.p; D.obs_mp = m->obs_mp.p; D.slot_cell = m->slot_cell.p; D.kf_n = m->kf_n.p; D.kf_key = m->kf_key.p;
-    D.kf_win = m->kf_win.p; D.okf_mark = m->okf_mark.p; D.okf_idx = m->okf_idx.p; D.mp_nobs = m->mp_nobs.p; D.mp_bad = m->mp_bad.p;
-    D.obs_lo = m->obs_lo.p; D.obs_hi = m->obs_hi.p; D.first = m->first.p; D.loc = m->loc.p; D.owner = m->owner.p; D.isvar = m->isvar.p;
+    D.kf_win = m->kf_win.p; D.okf_mark = m->okf_mark.p; D.okf_idx = m->okf_idx.p; D.mp = m->mp.p;
     D.S = m->S; D.n_kf = m->n_kf; D.n_mp = m->n_mp;
     return D;
 }
@@ -87,25 +87,13 @@ int ensure_mps(mss_mirror* m, int n_mp) {
     if ((size_t)n_mp > m->mp_cap) {
         size_t cap = m->mp_cap ? m->mp_cap : 4096;
         while (cap < (size_t)n_mp) cap = cap + cap / 2 + 4096;
-        const size_t old = (size_t)m->n_mp, old_cap = m->mp_cap;
+        const size_t old_cap = m->mp.cap;
         int rc;
-        if ((rc = grow_fill(m, m->mp_nobs, old, cap, 0))) return rc;
-        if ((rc = grow_fill(m, m->mp_bad, old, cap, 0))) return rc;
-        if ((rc = grow_fill(m, m->obs_hi, old, cap, 0xFF))) return rc;                   // -1
-        if ((rc = grow_fill(m, m->loc, old, cap, 0xFF))) return rc;
-        if ((rc = grow_fill(m, m->owner, old, cap, 0))) return rc;
-        if ((rc = grow_fill(m, m->isvar, old, cap, 0))) return rc;
-        // INT_MAX is not a byte pattern: obs_lo and first get their idle value from a kernel
-        const size_t lo_old = m->obs_lo.cap, fi_old = m->first.cap;
-        if ((rc = ensure(h, m->obs_lo, cap, true))) return rc;
-        if ((rc = ensure(h, m->first, cap, true))) return rc;
-        const size_t keep = std::min(old, old_cap);
-        (void)lo_old; (void)fi_old;
-        mk_fill_i32<<<blocks_for(m->obs_lo.cap - keep, h->sm_count), kT, 0, h->stream>>>(m->obs_lo.p + keep, 0x7FFFFFFF, m->obs_lo.cap - keep);
-        mk_fill_i32<<<blocks_for(m->first.cap - keep, h->sm_count), kT, 0, h->stream>>>(m->first.p + keep, 0x7FFFFFFF, m->first.cap - keep);
+        if ((rc = ensure(h, m->mp, cap, true))) return rc;
+        const size_t keep = std::min((size_t)m->n_mp, old_cap);          // records in use keep their contents
+        mk_init_mp<<<blocks_for(m->mp.cap - keep, h->sm_count), kT, 0, h->stream>>>(m->mp.p + keep, m->mp.cap - keep);
         MSS_CUDA(h, cudaGetLastError());
-        m->mp_cap = std::min({m->mp_nobs.cap, m->mp_bad.cap, m->obs_lo.cap, m->obs_hi.cap, m->first.cap, m->loc.cap, m->owner.cap,
-                              m->isvar.cap});
+        m->mp_cap = m->mp.cap;
     }
     m->n_mp = std::max(m->n_mp, n_mp);
     return MSS_OK;
@@ -242,15 +230,12 @@ int assemble(mss_mirror* m, int nwin, const mss_mirror_window* win, Assembly& A)
     }
     memcpy(hp, A.hw.data(), (size_t)nwin * sizeof(MWin));
     MSS_CUDA(h, cudaMemcpyAsync(m->win.p, hp, (size_t)nwin * sizeof(MWin), cudaMemcpyHostToDevice, h->stream));
-    if (A.Kmax > 0) {
-        mk_number<<<g_kf, kT, 0, h->stream>>>(D, A.dW);
-        mk_slots<<<g_kf, kT, 0, h->stream>>>(D, A.dW);
-    }
+    if (A.Kmax > 0) mk_slots<<<g_kf, kT, 0, h->stream>>>(D, A.dW);
     mk_okf_total<<<dim3(std::max(1, std::min(sm * 2, kMaxOutside)), nwin), kT, 0, h->stream>>>(D, A.dW);
     mk_obs_scan<1><<<g_flat, kT, 0, h->stream>>>(D, A.dW);
     MSS_CUDA(h, cudaGetLastError());
     MSS_CUDA(h, cudaEventRecord(m->e1, h->stream));
-    h->stats.kernel_launches += 2 + (A.Kmax > 0 ? 2 : 0);
+    h->stats.kernel_launches += 2 + (A.Kmax > 0 ? 1 : 0);
     A.tables = true;
     m->stats.last_h2d_bytes = h2d;
     m->stats.windows_built += nwin;
@@ -308,9 +293,8 @@ void mss_mirror_destroy(mss_mirror* m) {
     if (!m) return;
     cudaSetDevice(m->h->device);
     cudaStreamSynchronize(m->h->stream);
-    release(m->slot_mp); release(m->obs_mp); release(m->kf_n); release(m->kf_win); release(m->okf_idx); release(m->mp_nobs);
-    release(m->obs_lo); release(m->obs_hi); release(m->first); release(m->loc); release(m->owner); release(m->slot_cell);
-    release(m->kf_key); release(m->okf_mark); release(m->mp_bad); release(m->isvar); release(m->win);
+    release(m->slot_mp); release(m->obs_mp); release(m->kf_n); release(m->kf_win); release(m->okf_idx); release(m->mp);
+    release(m->slot_cell); release(m->kf_key); release(m->okf_mark); release(m->win);
     release(m->upload);
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->e0) cudaEventDestroy(m->e0);
@@ -385,9 +369,14 @@ int mss_mirror_set_map_points(mss_mirror* m, int32_t mp0, int32_t n, const int32
     MSS_CUDA(h, cudaSetDevice(h->device));
     int rc;
     if ((rc = ensure_mps(m, mp0 + n))) return rc;
-    MSS_CUDA(h, cudaMemcpyAsync(m->mp_nobs.p + mp0, nobs, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    if (bad) MSS_CUDA(h, cudaMemcpyAsync(m->mp_bad.p + mp0, bad, (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    else MSS_CUDA(h, cudaMemsetAsync(m->mp_bad.p + mp0, 0, (size_t)n, h->stream));
+    const size_t off_bad = align_up((size_t)n * 4, 16);
+    if ((rc = ensure(h, m->upload, off_bad + (size_t)n + 16))) return rc;
+    MSS_CUDA(h, cudaMemcpyAsync(m->upload.p, nobs, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (bad) MSS_CUDA(h, cudaMemcpyAsync(m->upload.p + off_bad, bad, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    mk_set_mp<<<(n + kT - 1) / kT, kT, 0, h->stream>>>(m->mp.p + mp0, reinterpret_cast<const int*>(m->upload.p),
+                                                     bad ? m->upload.p + off_bad : nullptr, n);
+    MSS_CUDA(h, cudaGetLastError());
+    h->stats.kernel_launches += 1;
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     m->stats.n_map_points = m->n_mp;
     return MSS_OK;

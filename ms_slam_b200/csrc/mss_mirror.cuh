@@ -35,6 +35,23 @@ enum : int { C_M = 0, C_F, C_H, C_O, C_HLO, C_HHI, C_KFLO, C_KFHI, C_ERR, C_PAIR
 enum : int { ME_KF_RANGE = 1, ME_KF_TWICE = 2, ME_MP_RANGE = 4, ME_MP_SHARED = 8, ME_DEPENDENT = 16, ME_OUTSIDE_OVERFLOW = 32,
              ME_NOBS_RANGE = 64 };
 
+// Everything the kernels read or write per map point sits in ONE 32-byte record (one sector): the window assembly touches
+// a map point through a handle found in a slot, i.e. at a spread address, several times per pass.
+struct __align__(32) MpRec {
+    int nobs;                // MapPoint::nObs
+    int obs_lo, obs_hi;      // lowest / highest keyframe handle that ever observed the point (never shrinks: a superset filter
+                             // for the observation scan; the scan itself is exact); INT_MAX / -1 when none
+    int loc;                 // scratch: rank among the points its first keyframe discovers (table index = that keyframe's
+                             // first index + rank); -1 when idle
+    unsigned long long fo;   // scratch: (window id + 1) << 32 | position k*S + i of the first occurrence, one atomicMin per
+                             // valid slot; ~0 when idle.  Two windows meeting at one point: the loser sees a foreign id
+    uint8_t bad;             // MapPoint::mbBad
+    uint8_t isvar;           // scratch
+    uint8_t pad_[6];
+};
+constexpr unsigned long long kFoIdle = ~0ull;
+__device__ __forceinline__ unsigned long long fo_key(int w, int pos) { return ((unsigned long long)(unsigned)(w + 1) << 32) | (unsigned)pos; }
+
 struct MirrorDev {
     int* slot_mp;            // [kf_cap * S]
     int* obs_mp;             // [kf_cap * S]
@@ -44,14 +61,7 @@ struct MirrorDev {
     int* kf_win;             // [kf_cap] scratch: window id + 1 while a call is in flight, else 0
     uint8_t* okf_mark;       // [kf_cap] scratch
     int* okf_idx;            // [kf_cap] scratch: index of an outside keyframe in its window's table
-    int* mp_nobs;            // [mp_cap]
-    uint8_t* mp_bad;         // [mp_cap]
-    int* obs_lo;             // [mp_cap] lowest / highest keyframe handle that ever observed the point (never shrinks: a
-    int* obs_hi;             //          superset filter for the observation scan; the scan itself is exact)
-    int* first;              // [mp_cap] scratch: INT_MAX when idle
-    int* loc;                // [mp_cap] scratch: table index in the window, -1 when idle
-    int* owner;              // [mp_cap] scratch: window id + 1, 0 when idle
-    uint8_t* isvar;          // [mp_cap] scratch
+    MpRec* mp;               // [mp_cap]
     int S, n_kf, n_mp;
 };
 
@@ -98,8 +108,17 @@ __device__ __forceinline__ int block_excl(int v, int& total, int* s_w) {
 __global__ void mk_fill_i32(int* p, int v, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void mk_fill_u16(uint16_t* p, uint16_t v, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+__global__ void mk_init_mp(MpRec* p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        MpRec r;
+        r.nobs = 0; r.obs_lo = 0x7FFFFFFF; r.obs_hi = -1; r.loc = -1; r.fo = kFoIdle; r.bad = 0; r.isvar = 0;
+        for (int k = 0; k < 6; ++k) r.pad_[k] = 0;
+        p[i] = r;
+    }
+}
+__global__ void mk_set_mp(MpRec* p, const int* nobs, const uint8_t* bad, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { p[i].nobs = nobs[i]; p[i].bad = bad ? bad[i] : (uint8_t)0; }
 }
 
 // observer ranges of the map points named by the obs_mp entries of keyframes [kf0, kf0 + n)
@@ -108,7 +127,7 @@ __global__ void mk_obs_ranges(MirrorDev D, int kf0, int n) {
     for (size_t it = blockIdx.x * (size_t)blockDim.x + threadIdx.x; it < total; it += (size_t)gridDim.x * blockDim.x) {
         const int kf = kf0 + (int)(it / D.S);
         const int h = D.obs_mp[(size_t)kf0 * D.S + it];
-        if (h >= 0 && h < D.n_mp) { atomicMin(&D.obs_lo[h], kf); atomicMax(&D.obs_hi[h], kf); }
+        if (h >= 0 && h < D.n_mp) { atomicMin(&D.mp[h].obs_lo, kf); atomicMax(&D.mp[h].obs_hi, kf); }
     }
 }
 
@@ -126,12 +145,12 @@ __global__ void mk_apply_ops(MirrorDev D, const DevOp* ops, int n, int* err) {
             if (o.b >= D.kf_n[o.a]) atomicMax(&D.kf_n[o.a], o.b + 1);
         } else {
             D.obs_mp[pos] = o.c;
-            if (o.c >= 0) { atomicMin(&D.obs_lo[o.c], o.a); atomicMax(&D.obs_hi[o.c], o.a); }
+            if (o.c >= 0) { atomicMin(&D.mp[o.c].obs_lo, o.a); atomicMax(&D.mp[o.c].obs_hi, o.a); }
         }
     } else if (o.kind == 3) {
         if (o.a < 0 || o.a >= D.n_mp) { atomicOr(err, 1); return; }
-        D.mp_nobs[o.a] = o.b;
-        D.mp_bad[o.a] = o.c ? 1 : 0;
+        D.mp[o.a].nobs = o.b;
+        D.mp[o.a].bad = o.c ? 1 : 0;
     }
 }
 
@@ -156,7 +175,7 @@ __global__ void mk_kf_compact(MirrorDev D, int kf) {
             if (h >= 0) {                               // out + p <= c0 + i: never overtakes the part still to be read
                 D.slot_mp[base + out + p] = h;
                 D.obs_mp[base + out + p] = h;
-                if (h < D.n_mp) { atomicMin(&D.obs_lo[h], kf); atomicMax(&D.obs_hi[h], kf); }
+                if (h < D.n_mp) { atomicMin(&D.mp[h].obs_lo, kf); atomicMax(&D.mp[h].obs_hi, kf); }
             }
             out += tot;
         }
@@ -192,12 +211,14 @@ __global__ void mk_first(MirrorDev D, const MWin* W) {
             const int h = D.slot_mp[base + i];
             if (h < 0) continue;
             if (h >= D.n_mp) { err |= ME_MP_RANGE; continue; }
-            if (D.mp_bad[h]) continue;                                      // MapSparsification.cc:70,90
+            const MpRec r = D.mp[h];                                        // one sector: bad, current first occurrence, isvar
+            if (r.bad) continue;                                            // MapSparsification.cc:70,90
             ++nvalid;
-            atomicMin(&D.first[h], k * D.S + i);
-            const int old = atomicCAS(&D.owner[h], 0, w.w + 1);
-            if (old != 0 && old != w.w + 1) err |= ME_MP_SHARED;
-            if (D.slot_cell[base + i] != (uint16_t)kCellNone16) D.isvar[h] = 1;
+            // keyframes are scheduled roughly in window order, so most later occurrences find a smaller key in place and
+            // need no atomic (a stale read only costs a redundant atomicMin)
+            const unsigned long long key = fo_key(w.w, k * D.S + i);
+            if (key < r.fo) atomicMin(&D.mp[h].fo, key);
+            if (!r.isvar && D.slot_cell[base + i] != (uint16_t)kCellNone16) D.mp[h].isvar = 1;
         }
         int tot;
         block_excl(nvalid, tot, s_w);
@@ -206,7 +227,8 @@ __global__ void mk_first(MirrorDev D, const MWin* W) {
     }
 }
 
-// one CTA per window keyframe: map points it discovers; handle range; observer range of the variables
+// one CTA per window keyframe: the map points it discovers and their rank among them (slot order); handle range; observer
+// range of the variables; a point first met by another window of the call = the windows are not independent
 __global__ void mk_count(MirrorDev D, const MWin* W) {
     __shared__ int s_w[kT / 32];
     const MWin w = W[blockIdx.y];
@@ -215,18 +237,31 @@ __global__ void mk_count(MirrorDev D, const MWin* W) {
         const int kf = w.kf[k];
         const size_t base = (size_t)kf * D.S;
         const int n = D.kf_n[kf];
-        int nfirst = 0, hlo = 0x7FFFFFFF, hhi = -1, klo = 0x7FFFFFFF, khi = -1, nmax_obs = 0;
-        for (int i = threadIdx.x; i < n; i += kT) {
-            const int h = D.slot_mp[base + i];
-            if (h < 0 || h >= D.n_mp || D.mp_bad[h] || D.first[h] != k * D.S + i) continue;
-            ++nfirst;
-            hlo = min(hlo, h); hhi = max(hhi, h);
-            const int no = D.mp_nobs[h];
-            nmax_obs = max(nmax_obs, no);
-            if (D.isvar[h]) { klo = min(klo, D.obs_lo[h]); khi = max(khi, D.obs_hi[h]); }
+        int run = 0, hlo = 0x7FFFFFFF, hhi = -1, klo = 0x7FFFFFFF, khi = -1, nmax_obs = 0;
+        unsigned err = 0;
+        for (int b0 = 0; b0 < n; b0 += kT) {
+            const int i = b0 + (int)threadIdx.x;
+            int h = -1;
+            MpRec r;
+            if (i < n) {
+                h = D.slot_mp[base + i];
+                if (h >= 0 && h < D.n_mp) {
+                    r = D.mp[h];
+                    if (r.bad) h = -1;
+                    else if ((int)(r.fo >> 32) != w.w + 1) { err |= ME_MP_SHARED; h = -1; }
+                    else if ((unsigned)r.fo != (unsigned)(k * D.S + i)) h = -1;
+                } else h = -1;
+            }
+            int tot;
+            const int p = block_excl(h >= 0 ? 1 : 0, tot, s_w);
+            if (h >= 0) {
+                D.mp[h].loc = run + p;
+                hlo = min(hlo, h); hhi = max(hhi, h);
+                nmax_obs = max(nmax_obs, r.nobs);
+                if (r.isvar) { klo = min(klo, r.obs_lo); khi = max(khi, r.obs_hi); }
+            }
+            run += tot;
         }
-        int tot;
-        block_excl(nfirst, tot, s_w);
         hlo = __reduce_min_sync(0xFFFFFFFFu, hlo); hhi = __reduce_max_sync(0xFFFFFFFFu, hhi);
         klo = __reduce_min_sync(0xFFFFFFFFu, klo); khi = __reduce_max_sync(0xFFFFFFFFu, khi);
         nmax_obs = __reduce_max_sync(0xFFFFFFFFu, nmax_obs);
@@ -235,7 +270,8 @@ __global__ void mk_count(MirrorDev D, const MWin* W) {
             if (khi >= 0) { atomicMin(&w.cnt[C_KFLO], klo); atomicMax(&w.cnt[C_KFHI], khi); }
             if (nmax_obs > 65535) atomicOr(&w.cnt[C_ERR], ME_NOBS_RANGE);
         }
-        if (threadIdx.x == 0) w.kf_first[k] = tot;
+        if (err) atomicOr(&w.cnt[C_ERR], (int)err);
+        if (threadIdx.x == 0) w.kf_first[k] = run;
     }
 }
 
@@ -257,38 +293,48 @@ __global__ void mk_scan(const MWin* W) {
     if (threadIdx.x == 0) { w.cnt[C_M] = cm; w.cnt[C_F] = cf; }
 }
 
-// Observation scan over the keyframes of the observer range.  PASS 0 counts the pairs and marks the outside keyframes,
-// PASS 1 emits the pairs, PASS 2 applies the deletion (SetBadFlag, src/MapPoint.cc:227-255: every (kf, idx) of the point's
-// observations is erased from the keyframe and the observation itself is dropped).
+// Observation scan over the keyframes of the observer range, one warp per keyframe at a time.  PASS 0 counts the pairs and
+// marks the outside keyframes, PASS 1 emits the pairs; both skip the window's own keyframes before touching their
+// observations (mnMapSaprsificationId == mnId, MapSparsification.cc:132).  PASS 2 applies the deletion (SetBadFlag,
+// src/MapPoint.cc:227-255: every (kf, idx) of the point's observations is erased from the keyframe and the observation
+// itself is dropped) and therefore visits every keyframe of the range.
 template <int PASS>
 __global__ void mk_obs_scan(MirrorDev D, const MWin* W) {
     const MWin w = W[blockIdx.y];
     if (w.cnt[C_ERR] || (PASS == 2 && !w.apply)) return;
     const int klo = w.cnt[C_KFLO], khi = w.cnt[C_KFHI];
     if (khi < klo) return;
-    const size_t total = (size_t)(khi - klo + 1) * D.S;
     const int me = w.w + 1;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int hbase = w.cnt[C_HLO] & ~31;
     int npairs = 0;
-    for (size_t it = blockIdx.x * (size_t)blockDim.x + threadIdx.x; it < total; it += (size_t)gridDim.x * blockDim.x) {
-        const int kf = klo + (int)(it / D.S), i = (int)(it % D.S);
-        const size_t pos = (size_t)kf * D.S + i;
-        const int h = D.obs_mp[pos];
-        if (h < 0 || h >= D.n_mp || D.owner[h] != me) continue;
-        if (PASS == 2) {
-            const int b = h - (w.cnt[C_HLO] & ~31);
-            if ((w.del[b >> 5] >> (b & 31)) & 1u) { D.obs_mp[pos] = -1; D.slot_mp[pos] = -1; }
-            continue;
-        }
-        if (!D.isvar[h]) continue;                          // MapSparsification.cc:127-142 walks the variables only
+    for (int kf = klo + gw; kf <= khi; kf += nw) {
         const int kw = D.kf_win[kf];
-        if (kw == me) continue;                             // a window keyframe (mnMapSaprsificationId == mnId, :132)
-        if (kw != 0) { atomicOr(&w.cnt[C_ERR], ME_DEPENDENT); continue; }
-        if (PASS == 0) { D.okf_mark[kf] = 1; ++npairs; }
-        else w.pairs[atomicAdd(&w.cnt[C_PAIRCUR], 1)] = ((uint32_t)D.loc[h] << 12) | (uint32_t)D.okf_idx[kf];
+        if (PASS != 2 && kw == me) continue;
+        const size_t base = (size_t)kf * D.S;
+        const int n = D.kf_n[kf];
+        bool any = false;
+        for (int i = lane; i < n; i += 32) {
+            const int h = D.obs_mp[base + i];
+            if (h < 0 || h >= D.n_mp) continue;
+            const MpRec r = D.mp[h];
+            if ((int)(r.fo >> 32) != me) continue;
+            if (PASS == 2) {
+                const int b = h - hbase;
+                if ((w.del[b >> 5] >> (b & 31)) & 1u) { D.obs_mp[base + i] = -1; D.slot_mp[base + i] = -1; }
+                continue;
+            }
+            if (!r.isvar) continue;                         // MapSparsification.cc:127-142 walks the variables only
+            if (kw != 0) { atomicOr(&w.cnt[C_ERR], ME_DEPENDENT); continue; }
+            if (PASS == 0) { any = true; ++npairs; }
+            else w.pairs[atomicAdd(&w.cnt[C_PAIRCUR], 1)] = ((uint32_t)(w.kf_first[(unsigned)r.fo / (unsigned)D.S] + r.loc) << 12) | (uint32_t)D.okf_idx[kf];
+        }
+        if (PASS == 0 && any) D.okf_mark[kf] = 1;
     }
     if (PASS == 0) {
         npairs = __reduce_add_sync(0xFFFFFFFFu, npairs);
-        if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&w.cnt[C_O], npairs);
+        if (lane == 0 && npairs) atomicAdd(&w.cnt[C_O], npairs);
     }
 }
 
@@ -339,7 +385,7 @@ __global__ void mk_okf_total(MirrorDev D, const MWin* W) {
         int c = 0;
         for (int i = threadIdx.x; i < n; i += kT) {
             const int h = D.slot_mp[base + i];
-            c += (h >= 0 && h < D.n_mp && !D.mp_bad[h]) ? 1 : 0;
+            c += (h >= 0 && h < D.n_mp && !D.mp[h].bad) ? 1 : 0;
         }
         int tot;
         block_excl(c, tot, s_w);
@@ -347,37 +393,9 @@ __global__ void mk_okf_total(MirrorDev D, const MWin* W) {
     }
 }
 
-// one CTA per window keyframe: table index of the map points it discovers (discovery order), handle and nObs tables
-__global__ void mk_number(MirrorDev D, const MWin* W) {
-    __shared__ int s_w[kT / 32];
-    const MWin w = W[blockIdx.y];
-    if (w.cnt[C_ERR]) return;
-    for (int k = blockIdx.x; k < w.K; k += gridDim.x) {
-        const int kf = w.kf[k];
-        const size_t base = (size_t)kf * D.S;
-        const int n = D.kf_n[kf];
-        int run = w.kf_first[k];
-        for (int b0 = 0; b0 < n; b0 += kT) {
-            const int i = b0 + (int)threadIdx.x;
-            int h = -1;
-            if (i < n) {
-                h = D.slot_mp[base + i];
-                if (h >= 0 && (h >= D.n_mp || D.mp_bad[h] || D.first[h] != k * D.S + i)) h = -1;
-            }
-            int tot;
-            const int p = block_excl(h >= 0 ? 1 : 0, tot, s_w);
-            if (h >= 0) {
-                const int idx = run + p;
-                D.loc[h] = idx;
-                w.mp_handle[idx] = h;
-                w.nobs16[idx] = (uint16_t)min(max(D.mp_nobs[h], 0), 65535);
-            }
-            run += tot;
-        }
-    }
-}
-
-// one CTA per window keyframe: its valid slots, in slot order, as (table index << 12) | cell
+// one CTA per window keyframe: its valid slots, in slot order, as (table index << 12) | cell; the table index of a point =
+// first index of the keyframe that discovers it + its rank there (mk_count); that keyframe also writes the point's row of
+// the handle and nObs tables (discovery order)
 __global__ void mk_slots(MirrorDev D, const MWin* W) {
     __shared__ int s_w[kT / 32];
     const MWin w = W[blockIdx.y];
@@ -389,16 +407,26 @@ __global__ void mk_slots(MirrorDev D, const MWin* W) {
         int run = w.feat_ptr[k];
         for (int b0 = 0; b0 < n; b0 += kT) {
             const int i = b0 + (int)threadIdx.x;
-            int h = -1;
+            int h = -1, idx = 0;
             if (i < n) {
                 h = D.slot_mp[base + i];
-                if (h >= 0 && (h >= D.n_mp || D.mp_bad[h])) h = -1;
+                if (h >= 0 && h < D.n_mp) {
+                    const MpRec r = D.mp[h];
+                    if (r.bad) h = -1;
+                    else {
+                        idx = w.kf_first[(unsigned)r.fo / (unsigned)D.S] + r.loc;
+                        if ((unsigned)r.fo == (unsigned)(k * D.S + i)) {
+                            w.mp_handle[idx] = h;
+                            w.nobs16[idx] = (uint16_t)min(max(r.nobs, 0), 65535);
+                        }
+                    }
+                } else h = -1;
             }
             int tot;
             const int p = block_excl(h >= 0 ? 1 : 0, tot, s_w);
             if (h >= 0) {
                 const unsigned c = D.slot_cell[base + i];
-                w.slots[run + p] = ((uint32_t)D.loc[h] << 12) | (c == kCellNone16 ? 0xFFFu : c);
+                w.slots[run + p] = ((uint32_t)idx << 12) | (c == kCellNone16 ? 0xFFFu : c);
             }
             run += tot;
         }
@@ -422,7 +450,7 @@ __global__ void mk_deleted(MirrorDev D, const MWin* W) {
         const int h = w.mp_handle[idx];
         const int b = h - (w.cnt[C_HLO] & ~31);
         atomicOr(&w.del[b >> 5], 1u << (b & 31));
-        if (w.apply) D.mp_bad[h] = 1;
+        if (w.apply) D.mp[h].bad = 1;
         ++nd;
     }
     nd = __reduce_add_sync(0xFFFFFFFFu, nd);
@@ -438,7 +466,7 @@ __global__ void mk_reset(MirrorDev D, const MWin* W, int have_tables) {
         const int M = w.cnt[C_M];
         for (int idx = gt; idx < M; idx += gs) {
             const int h = w.mp_handle[idx];
-            D.first[h] = 0x7FFFFFFF; D.loc[h] = -1; D.owner[h] = 0; D.isvar[h] = 0;
+            D.mp[h].fo = kFoIdle; D.mp[h].loc = -1; D.mp[h].isvar = 0;
         }
     } else {
         // no tables (error before the numbering pass): walk the window's slots again
@@ -449,7 +477,7 @@ __global__ void mk_reset(MirrorDev D, const MWin* W, int have_tables) {
             const int n = D.kf_n[kf];
             for (int i = gt; i < n; i += gs) {
                 const int h = D.slot_mp[base + i];
-                if (h >= 0 && h < D.n_mp && D.owner[h] == w.w + 1) { D.first[h] = 0x7FFFFFFF; D.loc[h] = -1; D.owner[h] = 0; D.isvar[h] = 0; }
+                if (h >= 0 && h < D.n_mp && (int)(D.mp[h].fo >> 32) == w.w + 1) { D.mp[h].fo = kFoIdle; D.mp[h].loc = -1; D.mp[h].isvar = 0; }
             }
         }
     }

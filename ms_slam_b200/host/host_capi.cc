@@ -87,12 +87,14 @@ int msh_build_world(void* h, int K, int H, int M, const int32_t* feat_ptr, const
             else { mp = std::make_shared<MapPoint>(next_mp++, map); map->AddMapPoint(mp); w->mps.push_back(mp); mp->nObs = 3; }
             // GetNumberMPs() must come out as okf_total[j]: observers beyond that number observe the keyframe without
             // sitting in one of its slots (mObservations and mvpMapPoints are separate structures upstream too)
-            if (i < okf_total[j]) kf->AddMapPoint(mp, (size_t)i);
-            mp->AddObservation(kf, i);
+            if (i < okf_total[j]) { kf->AddMapPoint(mp, (size_t)i); mp->AddObservation(kf, i); }
         }
         kf->mbSparsified = true;            // processed by an earlier window: the final flush must not pick it up again
         w->kfs.push_back(kf);
         map->AddKeyFrame(kf);
+        // (slot-less observations are added once the keyframe is in the map, like any later map operation: a keyframe
+        // enters the map with observations only where it holds the point, LocalMapping::ProcessNewKeyFrame)
+        for (int i = okf_total[j]; i < (int)outside[j].size(); ++i) w->mps[outside[j][i]]->AddObservation(kf, i);
     }
     for (int p = 0; p < M; ++p) {
         w->mps[p]->nObs = mp_nobs[p];      // the view's Observations(), whatever the stereo mix was

@@ -336,3 +336,25 @@ def test_final_flush_splits_into_components(hm):
         assert np.array_equal(w.bad_flags(), exp_bad) and r2[0]["objective"] == reps[0]["objective"]
     finally:
         w.close()
+
+
+@pytest.mark.gpu
+def test_c2_sized_flush_from_the_mirror_equals_the_flatten_path(hm):
+    """The north-star window (500 KF x 200k MP) through the C++ class as a final flush, once flattened from the pointer graph
+    and once from the persistent device mirror: the same map points are deleted; the mirror path ships a few KB."""
+    view, N = msgen.make_config("c2", 3)
+    out = {}
+    for mirror in (False, True):
+        w = hm.World(view, N=N, mirror=mirror)
+        try:
+            w.start()
+            assert w.finish(timeout_ms=120000) == 0
+            rep = [r for r in w.reports() if r["K"] > 0][0]
+            out[mirror] = (w.bad_flags(), rep)
+        finally:
+            w.close()
+    assert out[True][1]["mirror"] == 1 and out[False][1]["mirror"] == 0
+    assert np.array_equal(out[True][0], out[False][0])
+    for k in ("objective", "n_deleted", "n_kept", "n_vars", "rounds"):
+        assert out[True][1][k] == out[False][1][k], k
+    assert out[True][1]["h2d_bytes"] < 16384 and out[True][1]["d2h_bytes"] < 65536
