@@ -190,6 +190,19 @@ int mss_comm_unique_id(void* out_id128);
 int mss_comm_init(mss_handle* h, const void* id128, int32_t rank, int32_t nranks);
 int mss_comm_destroy(mss_handle* h);
 
+/* Multi-GPU from ONE process (the reference is a single process, src/System.cc:159-160: its sparsifier can drive all the
+ * GPUs of the box, it cannot be one rank of many).  A multi handle owns one engine per device and one worker thread per
+ * device; window w of a batch is solved by device w % n (host views, host result buffers), all devices at the same time.
+ * No collective: the host is the only consumer of the bitmasks. */
+typedef struct mss_multi mss_multi;
+int  mss_multi_create(const mss_config* cfg, const int32_t* devices /* NULL = 0..n-1; cfg->device is ignored */, int32_t n, mss_multi** out);
+void mss_multi_destroy(mss_multi* m);
+int  mss_multi_device_count(const mss_multi* m);
+const char* mss_multi_last_error(const mss_multi* m);
+int  mss_multi_set_params(mss_multi* m, int32_t min_points, float lambda, float grid_lambda);
+int  mss_multi_solve_batch(mss_multi* m, int32_t nwin, const mss_window_view* views, mss_result* results);
+int  mss_multi_get_stats(const mss_multi* m, int32_t device_index, mss_stats* out);
+
 /* Pinned host memory for views/results that travel every call (optional; any host memory works). */
 void* mss_host_alloc(size_t bytes);
 void  mss_host_free(void* p);

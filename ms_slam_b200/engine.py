@@ -76,7 +76,10 @@ SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_se
            "mss_get_stats", "mss_stream", "mss_debug_trace", "mss_debug_get_trace", "mss_components",
            # persistent device mirror (bound in ms_slam_b200/mirror.py)
            "mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
-           "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components"]
+           "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components",
+           # several GPUs from one process
+           "mss_multi_create", "mss_multi_destroy", "mss_multi_device_count", "mss_multi_last_error", "mss_multi_set_params",
+           "mss_multi_solve_batch", "mss_multi_get_stats"]
 
 _lib = None
 
@@ -355,3 +358,59 @@ class Engine:
     def solve_batch_raw(self, cviews, cresults, n):
         """Timed-loop entry: prebuilt ctypes arrays, no numpy work. Returns the status code."""
         return self.lib.mss_solve_batch(self.handle, n, cviews, cresults)
+
+
+class MultiEngine:
+    """Several GPUs driven from one process (include/mss.h mss_multi_*): window w of a batch -> device w % n."""
+
+    def __init__(self, devices, N=100, lam=500.0, grid_lam=10.0):
+        self.lib = load_library()
+        self.lib.mss_multi_create.argtypes = [C.POINTER(mss_config), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        self.lib.mss_multi_destroy.argtypes = [C.c_void_p]
+        self.lib.mss_multi_destroy.restype = None
+        self.lib.mss_multi_last_error.argtypes = [C.c_void_p]
+        self.lib.mss_multi_last_error.restype = C.c_char_p
+        self.lib.mss_multi_solve_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(mss_window_view), C.POINTER(mss_result)]
+        self.lib.mss_multi_get_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(mss_stats)]
+        self.lib.mss_multi_set_params.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float]
+        self.lib.mss_multi_device_count.argtypes = [C.c_void_p]
+        dev = np.ascontiguousarray(devices, np.int32)
+        cfg = mss_config(0, N, lam, grid_lam, 0, 0, 0, 0)
+        self.handle = C.c_void_p()
+        rc = self.lib.mss_multi_create(C.byref(cfg), dev.ctypes.data, dev.size, C.byref(self.handle))
+        if rc != MSS_OK:
+            self.handle = None
+            raise MssError(rc, "mss_multi_create failed")
+        self.n = dev.size
+
+    def close(self):
+        if self.handle:
+            self.lib.mss_multi_destroy(self.handle)
+            self.handle = None
+
+    def stats(self, i):
+        s = mss_stats()
+        self.lib.mss_multi_get_stats(self.handle, i, C.byref(s))
+        return {f: getattr(s, f) for f, _ in mss_stats._fields_}
+
+    def solve_batch(self, views):
+        n = len(views)
+        cv = (mss_window_view * n)()
+        cr = (mss_result * n)()
+        bufs = []
+        for i, v in enumerate(views):
+            cv[i] = Engine._host_view(v)
+            kb, cov, sl = np.zeros((v.M + 31) // 32, np.uint32), np.zeros(v.K + v.H, np.int32), np.zeros(v.K + v.H, np.int32)
+            cr[i].keep_bits, cr[i].kf_cov, cr[i].kf_slack = kb.ctypes.data, cov.ctypes.data, sl.ctypes.data
+            bufs.append((kb, cov, sl))
+        rc = self.lib.mss_multi_solve_batch(self.handle, n, cv, cr)
+        if rc != MSS_OK:
+            raise MssError(rc, self.lib.mss_multi_last_error(self.handle).decode())
+        out = []
+        for (kb, cov, sl), v, r in zip(bufs, views, cr):
+            out.append(Result(keep=unpack_bits(kb, v.M), keep_bits=kb, kf_cov=cov, kf_slack=sl, objective=r.objective,
+                              dual_bound=r.dual_bound, sum_cost=r.sum_cost, uncovered_cells=r.uncovered_cells,
+                              total_slack=r.total_slack, n_max=r.n_max, n_vars=r.n_vars, n_cells=r.n_cells, nnz=r.nnz,
+                              n_kept=r.n_kept, rounds=r.rounds, status=r.status, time_build_us=r.time_build_us,
+                              time_solve_us=r.time_solve_us))
+        return out

@@ -405,6 +405,20 @@ MapSparsification::MapSparsification(const std::string& strSettingsFile, Atlas* 
     // recorder is attached to the map before any other thread runs (System constructs the sparsifier before it starts the
     // threads, src/System.cc:159-160); keyframes already in the map are registered here.
     if (const char* bh = std::getenv("MSS_BATCHED_HANDBACK")) mbBatchedHandback = std::atoi(bh) != 0;
+    // MSS_DEVICES=n (or a list "0,2,3"): the independent components of the final flush are dealt out over n GPUs of the box,
+    // driven from this one process (mss_multi_*); live windows stay on the first device
+    if (const char* dv = std::getenv("MSS_DEVICES")) {
+        vector<int32_t> devs;
+        const std::string str(dv);
+        if (str.find(',') == std::string::npos) { for (int i = 0; i < std::atoi(dv); ++i) devs.push_back(i); }
+        else { size_t p = 0; while (p < str.size()) { devs.push_back(std::atoi(str.c_str() + p)); p = str.find(',', p); if (p == std::string::npos) break; ++p; } }
+        if (mpEngine && devs.size() > 1) {
+            if (mss_multi_create(&cfg, devs.data(), (int32_t)devs.size(), &mpMulti) != MSS_OK) {
+                mpMulti = nullptr;
+                std::cerr << "MapSparsification: MSS_DEVICES=" << dv << ": not all of these devices are usable; the flush stays on one GPU" << std::endl;
+            }
+        }
+    }
     const char* mir = std::getenv("MSS_MIRROR");
     if (mpEngine && mpAtlas && !(mir && std::atoi(mir) == 0)) {
         const char* sl = std::getenv("MSS_MIRROR_SLOTS");
@@ -424,6 +438,7 @@ MapSparsification::~MapSparsification() {
     if (mGraveThread.joinable()) mGraveThread.join();
     if (mpAtlas && mpRecorder) mpAtlas->GetCurrentMap()->SetMirror(nullptr);
     if (mpMirror) mss_mirror_destroy(mpMirror);
+    if (mpMulti) mss_multi_destroy(mpMulti);
     delete mpRecorder;
     if (mpEngine) mss_destroy(mpEngine);
 }
@@ -587,7 +602,8 @@ bool MapSparsification::SparsifyingFromMirror(vector<shared_ptr<KeyFrame>>& vpKF
 void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
     mnId++;
     WindowReport rep;
-    if (mpMirror && mpRecorder && !vpKFs.empty() && SparsifyingFromMirror(vpKFs, rep)) {
+    // (a flush that is to be dealt out over several GPUs is flattened on the host: a mirror lives on one device)
+    if (mpMirror && mpRecorder && !vpKFs.empty() && !(mbFlushing && mpMulti) && SparsifyingFromMirror(vpKFs, rep)) {
         std::unique_lock<std::mutex> lock(mMutexReports);
         if (mReports.size() >= kMaxReports) mReports.erase(mReports.begin());
         mReports.push_back(rep);
@@ -624,7 +640,13 @@ void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
                     results[i] = mss_result{};
                     results[i].keep_bits = bits[i].data();
                 }
-                rc = mss_solve_batch(mpEngine, (int32_t)n, views.data(), results.data());
+                if (mpMulti) {
+                    mss_multi_set_params(mpMulti, mnMinNum, mfLambda, mfGridLambda);
+                    rc = mss_multi_solve_batch(mpMulti, (int32_t)n, views.data(), results.data());
+                    rep.devices = mss_multi_device_count(mpMulti);
+                } else {
+                    rc = mss_solve_batch(mpEngine, (int32_t)n, views.data(), results.data());
+                }
                 if (rc == MSS_OK || rc == MSS_E_NOCONVERGE) {
                     for (size_t i = 0; i < n; ++i) {
                         for (size_t q = 0; q < parts[i].part_mp.size(); ++q)
@@ -637,7 +659,8 @@ void MapSparsification::Sparsifying(vector<shared_ptr<KeyFrame>>& vpKFs) {
                     }
                     rep.components = (int)n;
                 } else {
-                    std::cerr << "MapSparsification: window " << mnId << " not sparsified: " << mss_last_error(mpEngine) << std::endl;
+                    std::cerr << "MapSparsification: window " << mnId << " not sparsified: "
+                              << (mpMulti ? mss_multi_last_error(mpMulti) : mss_last_error(mpEngine)) << std::endl;
                 }
                 solved = true;
             }

@@ -106,6 +106,7 @@ public:
         long delta_ops = 0;             // records drained into the mirror before this window
         double build_ms = 0.0;          // device time of the view assembly (mirror) inside solve_ms
         long h2d_bytes = 0, d2h_bytes = 0;
+        int devices = 1;                // GPUs the window's components were dealt out to
     };
     std::vector<WindowReport> GetReports();           // the last kMaxReports windows
     static constexpr size_t kMaxReports = 256;
@@ -133,6 +134,7 @@ private:
     bool mbFlushing = false;            // Sparsifying() is running the final flush
 
     mss_handle* mpEngine;               // replaces GRBEnv mGRBEnv (include/MapSparsification.h:59)
+    mss_multi* mpMulti = nullptr;       // MSS_DEVICES > 1: the components of the final flush are dealt out over several GPUs
     mss_mirror* mpMirror = nullptr;     // persistent device mirror of the incidence (include/mss.h), fed by mpRecorder
     MirrorRecorder* mpRecorder = nullptr;
     std::thread mGraveThread;           // frees what a batched hand-back released (see EraseBatched)

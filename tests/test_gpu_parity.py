@@ -420,3 +420,48 @@ def test_gated_batch_of_tiny_ragged_windows(build_native):
             if rep == 0:
                 check_against_cpu(plain[i], N, a)
     e1.close(); e2.close()
+
+
+def test_one_process_drives_two_gpus(eng, emulation_golden):
+    """mss_multi_*: the single-process way to use several GPUs (the reference is one process): the 64 windows of config 4 dealt
+    out over two devices by worker threads of this process, bit-identical to one GPU, both devices busy."""
+    import hashlib, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    from ms_slam_b200.engine import MultiEngine
+    N = msgen.CONFIGS["c4"]["N"]
+    views = [msgen.make_config("c4", 1000 + w)[0] for w in range(64)]
+    me = MultiEngine([0, 1], N=N, lam=LAM, grid_lam=GLAM)
+    try:
+        res = me.solve_batch(views)
+        for w, r in enumerate(res):
+            gold = emulation_golden[fixture_key("c4", 1000 + w)]
+            assert r.status == 0 and hashlib.sha256(r.keep_bits.tobytes()).hexdigest() == gold["keep_sha256"]
+            assert (r.objective, r.n_kept, r.rounds) == (gold["objective"], gold["n_kept"], gold["rounds"])
+        assert me.stats(0)["solves"] == 32 and me.stats(1)["solves"] == 32
+    finally:
+        me.close()
+
+
+def test_flush_of_the_cpp_class_over_two_gpus(build_native):
+    """The C++ class with MSS_DEVICES=2: the final flush over an atlas of >= 8 disjoint components is dealt out over two
+    devices and deletes exactly what one GPU deletes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    from ms_slam_b200 import merge_views, host_mirror as hm
+    parts = [msgen.make_config("live", 60 + i, M=2500 + 300 * i, H=6 if i % 2 else 0)[0] for i in range(9)]
+    whole = merge_views(parts, interleave=True)
+    out = {}
+    for devices in (None, 2):
+        w = hm.World(whole, N=100, window_length=8, mirror=False, devices=devices)
+        try:
+            w.start()
+            w.feed(0, 5)
+            assert w.finish() == 0
+            rep = w.reports()[0]
+            out[devices] = (w.bad_flags(), rep)
+        finally:
+            w.close()
+    assert out[2][1]["devices"] == 2 and out[None][1]["devices"] == 1 and out[2][1]["components"] >= 8
+    assert np.array_equal(out[2][0], out[None][0]) and out[2][1]["objective"] == out[None][1]["objective"]
