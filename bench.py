@@ -580,21 +580,25 @@ def main():
     e2e_mirror = None
     if not args.no_e2e and not args.no_mirror:
         try:
-            mb = MirrorBatch(eng, E, args.workload, list(mine), cfg["n_feat"])
+            # (a mirror belongs to one device: with several ranks every rank keeps the maps of its own windows in its own
+            # mirror, on a handle without a communicator -- the deleted-handle bitmasks are consumed by the host that owns them)
+            eng_m = eng if world == 1 else E.Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+            mb = MirrorBatch(eng_m, E, args.workload, list(mine), cfg["n_feat"])
             for _ in range(args.warmup):
                 rc = mb.step()
-                assert rc == 0, eng.lib.mss_last_error(eng.handle)
+                assert rc == 0, eng_m.lib.mss_last_error(eng_m.handle)
             barrier()
+            stream_m = torch.cuda.ExternalStream(eng_m.lib.mss_stream(eng_m.handle), device=torch.device("cuda", local_rank))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             bms, sms = [], []
-            e0.record(stream)
+            e0.record(stream_m)
             for _ in range(args.steps):
                 rc = mb.step()
                 st_m = mb.mir.stats()
                 bms.append(st_m["last_build_ms"]); sms.append(st_m["last_solve_ms"])
-            e1.record(stream)
+            e1.record(stream_m)
             barrier()
-            assert rc == 0, eng.lib.mss_last_error(eng.handle)
+            assert rc == 0, eng_m.lib.mss_last_error(eng_m.handle)
             ms_m = e0.elapsed_time(e1)
             if world > 1:
                 t = torch.tensor([ms_m], device="cuda")
@@ -612,6 +616,8 @@ def main():
                                   "untimed: in a SLAM run they arrive as deltas); per step K keyframe handles per window go up, the view "
                                   "is assembled on the device, the deleted-map-point bitmask comes back"}
             mb.free()
+            if eng_m is not eng:
+                eng_m.close()
         except Exception as e:      # noqa: BLE001
             e2e_mirror = {"error": repr(e)}
 

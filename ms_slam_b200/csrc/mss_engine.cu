@@ -470,6 +470,10 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
     // caller did not ask arrays for -- their bitmasks stay in the all-gathered device buffer).
     int64_t d2h = 0;
     {
+        auto wants_full = [&](int w) {
+            const mss_result& r = results[w];
+            return !res_on_device(views[w]) && (r.keep_bits || r.kf_cov || r.kf_slack);
+        };
         int n_full = 0;
         bool uniform = true;
         for (int w = 0; w < nwin; ++w) {
@@ -480,13 +484,19 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         if (nranks > 1) uniform = true;                        // rank-major slots with one stride
         const size_t stride = nranks > 1 ? (size_t)slot_stride : (nwin > 1 ? (size_t)(out_off[1] - out_off[0]) : (size_t)slot_of(views[0]).total);
         const size_t nslots = nranks > 1 ? (size_t)nranks * spr : (size_t)nwin;
-        auto wants_full = [&](int w) {
-            const mss_result& r = results[w];
-            return !res_on_device(views[w]) && (r.keep_bits || r.kf_cov || r.kf_slack);
-        };
+        // several ranks, and the caller asks arrays exactly for the windows this rank solved (the usual case: the others'
+        // bitmasks stay in the all-gathered device buffer): the rank's slots are contiguous, one copy brings them all
+        bool own_only = nranks > 1 && nl > 0 && n_full == nl;
+        for (int w = 0; w < nwin && own_only; ++w) own_only = wants_full(w) == ((w % nranks) == rank);
         if (n_full == nwin) {
             MSS_CUDA_LAUNCHED(h, cudaMemcpyAsync(h->h_out, h->out.p, out_words * 4, cudaMemcpyDeviceToHost, h->stream));
             d2h += (int64_t)(out_words * 4);
+        } else if (own_only) {
+            const size_t region = (size_t)spr * slot_stride, off = (size_t)rank * region;
+            MSS_CUDA_LAUNCHED(h, cudaMemcpy2DAsync(h->h_out, stride * 4, h->out.p, stride * 4, (size_t)mss::kHdrWords * 4, nslots,
+                                                   cudaMemcpyDeviceToHost, h->stream));
+            MSS_CUDA_LAUNCHED(h, cudaMemcpyAsync(h->h_out + off, h->out.p + off, region * 4, cudaMemcpyDeviceToHost, h->stream));
+            d2h += (int64_t)(nslots * mss::kHdrWords * 4 + region * 4);
         } else {
             if (uniform) {      // headers of all slots in one strided copy
                 MSS_CUDA_LAUNCHED(h, cudaMemcpy2DAsync(h->h_out, stride * 4, h->out.p, stride * 4, (size_t)mss::kHdrWords * 4, nslots,

@@ -292,7 +292,10 @@ std::vector<shared_ptr<MapPoint>> Map::GetAllMapPoints() {
 
 long unsigned int Map::MapPointsInMap() { std::unique_lock<std::mutex> l(mMutexMap); return mspMapPoints.size(); }
 long unsigned int Map::SparsifiedMapPointsInMap() { std::unique_lock<std::mutex> l(mMutexMap); return mspSparsifiedMapPoints.size(); }
-long unsigned int Map::SparsifiedKeyFramesInMap() { std::unique_lock<std::mutex> l(mMutexMap); return mspSparsifiedKeyFrames.size(); }
+std::vector<shared_ptr<KeyFrame>> Map::GetAllSparsifiedKeyFrames() {
+    std::unique_lock<std::mutex> l(mMutexMap);
+    return std::vector<shared_ptr<KeyFrame>>(mspSparsifiedKeyFrames.begin(), mspSparsifiedKeyFrames.end());
+}
 
 std::vector<shared_ptr<KeyFrame>> Atlas::GetAllKeyFrames() {
     std::unique_lock<std::mutex> l(mMutexAtlas);

@@ -127,7 +127,7 @@ public:
     std::vector<shared_ptr<MapPoint>> GetAllMapPoints();
     long unsigned int MapPointsInMap();
     long unsigned int SparsifiedMapPointsInMap();
-    long unsigned int SparsifiedKeyFramesInMap();
+    std::vector<shared_ptr<KeyFrame>> GetAllSparsifiedKeyFrames();     // include/Map.h:60
     void SetIniertialBA2() { std::unique_lock<std::mutex> l(mMutexMap); mbIMU_BA2 = true; }
     bool GetIniertialBA2() { std::unique_lock<std::mutex> l(mMutexMap); return mbIMU_BA2; }
 

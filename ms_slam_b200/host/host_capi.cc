@@ -247,7 +247,7 @@ void msh_keyframe_state(void* h, int32_t* out3) {
 
 int msh_map_counts(void* h, int64_t* out3) {
     Map* m = static_cast<World*>(h)->atlas.GetCurrentMap();
-    out3[0] = (int64_t)m->MapPointsInMap(); out3[1] = (int64_t)m->SparsifiedMapPointsInMap(); out3[2] = (int64_t)m->SparsifiedKeyFramesInMap();
+    out3[0] = (int64_t)m->MapPointsInMap(); out3[1] = (int64_t)m->SparsifiedMapPointsInMap(); out3[2] = (int64_t)m->GetAllSparsifiedKeyFrames().size();
     return 0;
 }
 
