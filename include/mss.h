@@ -304,6 +304,24 @@ int  mss_mirror_build_view(mss_mirror* m, const mss_mirror_window* window, int32
 int  mss_mirror_components(mss_mirror* m, const mss_mirror_window* window, int32_t* kf_label, int32_t* ncomp, int32_t* n_max);
 int  mss_mirror_get_stats(const mss_mirror* m, mss_mirror_stats* out);
 
+/* ---- Compaction of sparsified keyframes on the device ----------------------------------------------------------
+ * KeyFrame::EraseBadDescriptor (src/KeyFrame.cc:311-361) keeps, in order, the rows of mDescriptors (32 bytes), mvKeysUn
+ * (cv::KeyPoint, 28 bytes), mvuRight and mvDepth whose slot still holds a map point.  mss_compact_keyframes does that in place
+ * on device-resident arrays, one CTA per keyframe; any of the four arrays may be NULL.  n_out[nkf] (host) receives the rows
+ * left.  With mss_mirror_compact_keyframes the flags come from the mirror (slot_mp[kf][i] >= 0, i.e. after a window's
+ * deletion was applied on the device) and the mirror's own rows of these keyframes are compacted as well (MSS_MOP_KF_COMPACT). */
+typedef struct mss_kf_payload {
+    int32_t n;                 /* rows (keypoints) before the compaction */
+    int32_t kf;                /* keyframe handle in the mirror (mss_mirror_compact_keyframes), else -1 */
+    const uint8_t* keep;       /* [n] device: 1 = the row survives (mss_compact_keyframes) */
+    void*   descriptors;       /* [n][32] device */
+    void*   keypoints;         /* [n][28] device */
+    float*  uright;            /* [n] device */
+    float*  depth;             /* [n] device */
+} mss_kf_payload;
+int mss_compact_keyframes(mss_handle* h, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
+int mss_mirror_compact_keyframes(mss_mirror* m, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
+
 int   mss_get_stats(const mss_handle* h, mss_stats* out);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
 void* mss_stream(mss_handle* h);

@@ -6,6 +6,7 @@
 #define MSS_KERNELS_TYPES_ONLY
 #include "mss_internal.h"
 #include "mss_mirror.cuh"
+#include "mss_compact.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -635,6 +636,52 @@ int mss_mirror_components(mss_mirror* m, const mss_mirror_window* window, int32_
     h->err = keep_err;
     if (err) { h->err = "mirror window rejected:" + mirror_error_text(err); return MSS_E_BADARG; }
     return rc;
+}
+
+static int compact_impl(mss_handle* h, mss_mirror* m, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out) {
+    h->err.clear();
+    if (nkf < 0 || (nkf > 0 && (!kfs || !n_out))) { h->err = "compact_keyframes: bad arguments"; return MSS_E_BADARG; }
+    if (nkf == 0) return MSS_OK;
+    MSS_CUDA(h, cudaSetDevice(h->device));
+    std::vector<mssc::KfPayload> hp(nkf);
+    for (int i = 0; i < nkf; ++i) {
+        const mss_kf_payload& k = kfs[i];
+        if (k.n < 0 || (!m && k.n > 0 && !k.keep) || (m && (k.kf < 0 || k.kf >= m->n_kf || k.n > m->S))) {
+            h->err = "compact_keyframes: keyframe " + std::to_string(i) + ": bad row count, flags or handle";
+            return MSS_E_BADARG;
+        }
+        hp[i] = mssc::KfPayload{k.n, m ? k.kf : -1, m ? nullptr : k.keep, static_cast<uint4*>(k.descriptors),
+                                static_cast<uint32_t*>(k.keypoints), k.uright, k.depth};
+    }
+    DevBuf<uint8_t>& up = m ? m->upload : h->stage;
+    const size_t off_out = align_up((size_t)nkf * sizeof(mssc::KfPayload), 16);
+    int rc = ensure(h, up, off_out + (size_t)nkf * 4 + 16);
+    if (rc) return rc;
+    MSS_CUDA(h, cudaMemcpyAsync(up.p, hp.data(), (size_t)nkf * sizeof(mssc::KfPayload), cudaMemcpyHostToDevice, h->stream));
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));                  // hp is pageable
+    mssc::compact_keyframes_kernel<<<std::min(nkf, h->sm_count * 8), mssc::kT, 0, h->stream>>>(
+        reinterpret_cast<const mssc::KfPayload*>(up.p), nkf, m ? m->slot_mp.p : nullptr, m ? m->S : 0, reinterpret_cast<int*>(up.p + off_out));
+    MSS_CUDA(h, cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    if (m) {                                                        // the mirror's own rows follow (EraseBadDescriptor semantics)
+        const MirrorDev D = dev_of(m);
+        for (int i = 0; i < nkf; ++i) mk_kf_compact<<<1, kT, 0, h->stream>>>(D, kfs[i].kf);
+        MSS_CUDA(h, cudaGetLastError());
+        h->stats.kernel_launches += nkf;
+    }
+    MSS_CUDA(h, cudaMemcpyAsync(n_out, up.p + off_out, (size_t)nkf * 4, cudaMemcpyDeviceToHost, h->stream));
+    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MSS_OK;
+}
+
+int mss_compact_keyframes(mss_handle* h, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out) {
+    if (!h) return MSS_E_BADARG;
+    return compact_impl(h, nullptr, nkf, kfs, n_out);
+}
+
+int mss_mirror_compact_keyframes(mss_mirror* m, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out) {
+    if (!m) return MSS_E_BADARG;
+    return compact_impl(m->h, m, nkf, kfs, n_out);
 }
 
 int mss_mirror_get_stats(const mss_mirror* m, mss_mirror_stats* out) {

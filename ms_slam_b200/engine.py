@@ -77,6 +77,7 @@ SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_se
            # persistent device mirror (bound in ms_slam_b200/mirror.py)
            "mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
            "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components",
+           "mss_compact_keyframes", "mss_mirror_compact_keyframes",
            # several GPUs from one process
            "mss_multi_create", "mss_multi_destroy", "mss_multi_device_count", "mss_multi_last_error", "mss_multi_set_params",
            "mss_multi_solve_batch", "mss_multi_get_stats"]

@@ -23,6 +23,11 @@ class mss_mirror_stats(C.Structure):
                 ("last_h2d_bytes", C.c_int64), ("last_d2h_bytes", C.c_int64)]
 
 
+class mss_kf_payload(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kf", C.c_int32), ("keep", C.c_void_p), ("descriptors", C.c_void_p), ("keypoints", C.c_void_p),
+                ("uright", C.c_void_p), ("depth", C.c_void_p)]
+
+
 class mss_mirror_window(C.Structure):
     _fields_ = [("K", C.c_int32), ("n_max_floor", C.c_int32), ("kf", C.c_void_p), ("del_bits", C.c_void_p),
                 ("del_words", C.c_int32), ("h_lo", C.c_int32), ("h_hi", C.c_int32),
@@ -32,7 +37,7 @@ class mss_mirror_window(C.Structure):
 
 SYMBOLS = ["mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
            "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats",
-           "mss_mirror_components"]
+           "mss_mirror_components", "mss_compact_keyframes", "mss_mirror_compact_keyframes"]
 
 
 def _declare(lib):
@@ -50,11 +55,75 @@ def _declare(lib):
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mss_mirror_get_stats.argtypes = [C.c_void_p, C.POINTER(mss_mirror_stats)]
     lib.mss_mirror_components.argtypes = [C.c_void_p, C.POINTER(mss_mirror_window), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.mss_compact_keyframes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(mss_kf_payload), C.c_void_p]
+    lib.mss_mirror_compact_keyframes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(mss_kf_payload), C.c_void_p]
     lib._mirror_declared = True
 
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+class KeyframePayload:
+    """The per-keypoint arrays of one keyframe in device memory (what KeyFrame::EraseBadDescriptor compacts,
+    /root/reference/src/KeyFrame.cc:311-361): descriptors u8 [n,32], keypoints 7 x 32-bit words, uRight, depth."""
+    _ARR = ("keep", "descriptors", "keypoints", "uright", "depth")
+
+    def __init__(self, engine: Engine, n, keep=None, descriptors=None, keypoints=None, uright=None, depth=None, kf=-1):
+        self.engine, self.n, self.kf = engine, int(n), int(kf)
+        self.ptr, self.meta = {}, {}
+        lib, h = engine.lib, engine.handle
+        given = dict(keep=None if keep is None else np.ascontiguousarray(keep, np.uint8),
+                     descriptors=None if descriptors is None else np.ascontiguousarray(descriptors, np.uint8).reshape(self.n, 32),
+                     keypoints=None if keypoints is None else np.ascontiguousarray(keypoints).view(np.uint32).reshape(self.n, 7),
+                     uright=None if uright is None else np.ascontiguousarray(uright, np.float32),
+                     depth=None if depth is None else np.ascontiguousarray(depth, np.float32))
+        for name, a in given.items():
+            if a is None:
+                self.ptr[name] = None
+                continue
+            p = lib.mss_device_alloc(h, max(a.nbytes, 16))
+            if not p:
+                raise MssError(-4, "device allocation failed")
+            if a.nbytes:
+                engine._check(lib.mss_memcpy_h2d(h, p, a.ctypes.data, a.nbytes))
+            self.ptr[name], self.meta[name] = p, (a.dtype, a.shape)
+
+    def c_struct(self) -> "mss_kf_payload":
+        return mss_kf_payload(self.n, self.kf, *[self.ptr[k] for k in self._ARR])
+
+    def fetch(self, n_rows):
+        """the first n_rows rows of every array (after a compaction: the survivors)"""
+        out = {}
+        for name in self._ARR[1:]:
+            if self.ptr[name] is None:
+                out[name] = None
+                continue
+            dt, shape = self.meta[name]
+            a = np.zeros((n_rows,) + tuple(shape[1:]), dt)
+            if a.nbytes:
+                self.engine._check(self.engine.lib.mss_memcpy_d2h(self.engine.handle, a.ctypes.data, self.ptr[name], a.nbytes))
+            out[name] = a
+        return out
+
+    def free(self):
+        for p in self.ptr.values():
+            if p:
+                self.engine.lib.mss_device_free(self.engine.handle, p)
+        self.ptr = {}
+
+
+def compact_keyframes(engine: Engine, payloads, mirror: "Mirror" = None):
+    """mss_compact_keyframes / mss_mirror_compact_keyframes over a list of KeyframePayload -> rows left per keyframe"""
+    _declare(engine.lib)
+    n = len(payloads)
+    arr = (mss_kf_payload * max(n, 1))(*[p.c_struct() for p in payloads])
+    out = np.zeros(max(n, 1), np.int32)
+    if mirror is None:
+        engine._check(engine.lib.mss_compact_keyframes(engine.handle, n, arr, out.ctypes.data))
+    else:
+        engine._check(engine.lib.mss_mirror_compact_keyframes(mirror.handle, n, arr, out.ctypes.data))
+    return out[:n]
 
 
 class MirrorResult:

@@ -156,3 +156,12 @@ class MirrorModel:
 
 
 from ms_slam_b200.mirror import arrays_from_view as load_view      # noqa: E402,F401  (test helper: a map that flattens to a view)
+
+
+def erase_bad_descriptor_rows(keep, descriptors=None, keypoints=None, uright=None, depth=None):
+    """KeyFrame::EraseBadDescriptor (/root/reference/src/KeyFrame.cc:311-361) restated for the per-keypoint arrays: the rows
+    whose slot still holds a map point survive, in order (DescriptorsNew.push_back(mDescriptors.row(i)), vKeysUnNew,
+    vuRightNew, vDepthNew at :331-342).  keep: bool [n]; descriptors u8 [n,32]; keypoints [n,7] 32-bit words
+    (cv::KeyPoint = pt.x, pt.y, size, angle, response, octave, class_id); uright / depth f32 [n].  Returns the new arrays."""
+    keep = np.asarray(keep, bool)
+    return tuple(None if a is None else np.asarray(a)[keep].copy() for a in (descriptors, keypoints, uright, depth))
