@@ -322,6 +322,12 @@ typedef struct mss_kf_payload {
 int mss_compact_keyframes(mss_handle* h, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
 int mss_mirror_compact_keyframes(mss_mirror* m, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
 
+/* Lower bound of the reference ILP, proven on the device per window (mss_result.dual_bound; NaN while off -- the default --
+ * or when the round cap was hit).  The reference gets its certificate from GUROBI's branch and bound (MIPGap 0.002,
+ * src/MapSparsification.cc:153-157); here it comes from the state reached by exact dominance rules + one round of dual
+ * ascent (csrc/mss_bound.cuh): objective / dual_bound - 1 is a certified optimality gap.  Costs six short extra phases per
+ * window and a copy of the residual lists in device memory.  Also switched on by the environment variable MSS_DUAL_BOUND=1. */
+int   mss_set_dual_bound(mss_handle* h, int32_t enable);
 int   mss_get_stats(const mss_handle* h, mss_stats* out);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
 void* mss_stream(mss_handle* h);

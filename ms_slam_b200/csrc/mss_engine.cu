@@ -263,6 +263,11 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
     if ((rc = ensure(h, h->ent, (size_t)(Ftot + Otot) + 16))) return rc;
     if ((rc = ensure(h, h->live, (size_t)(Ftot + Otot) + 16))) return rc;
     if ((rc = ensure(h, h->rows, (size_t)7 * ((size_t)Rtot + 16)))) return rc;
+    if (h->want_bound) {
+        if ((rc = ensure(h, h->b_snap, (size_t)(Ftot + Otot) + 16))) return rc;
+        if ((rc = ensure(h, h->b_rows, (size_t)2 * ((size_t)Rtot + 16)))) return rc;
+        if ((rc = ensure(h, h->b_vars, (size_t)2 * ((size_t)Mpad + 16)))) return rc;
+    }
     if ((rc = ensure(h, h->out, out_words + 16))) return rc;
     if ((rc = ensure(h, h->stage, stage_bytes + 16))) return rc;
     if ((rc = ensure(h, h->sync, sync_words))) return rc;
@@ -400,6 +405,11 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         const size_t rs = (size_t)Rtot + 16;
         P.row_off = h->rows.p; P.ent_n = h->rows.p + rs; P.live_n = h->rows.p + 2 * rs; P.row_need = h->rows.p + 3 * rs;
         P.row_cov = h->rows.p + 4 * rs; P.row_ncell = h->rows.p + 5 * rs; P.ocursor = h->rows.p + 6 * rs;
+    }
+    if (h->want_bound) {
+        P.b_snap = h->b_snap.p;
+        P.b_snap_n = h->b_rows.p; P.b_snap_d = h->b_rows.p + ((size_t)Rtot + 16);
+        P.b_share = h->b_vars.p; P.b_red = h->b_vars.p + ((size_t)Mpad + 16);
     }
     P.out = h->out.p;
     P.Ftot = (int)Ftot;
@@ -572,7 +582,17 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         r.sum_cost = (int64_t)(((uint64_t)slot[10] << 32) | slot[9]);
         r.objective = (double)r.sum_cost + (double)h->cfg.grid_lambda * (double)r.uncovered_cells +
                       (double)h->cfg.lambda * (double)r.total_slack;
+        // lower bound proven on the device (mss_bound.cuh): flag 1 = counters of the snapshot, 2 = dominance alone decided
+        // every point (the selection is optimal)
         r.dual_bound = NAN;
+        if (slot[16] == 2u) r.dual_bound = r.objective;
+        else if (slot[16] == 1u) {
+            const int64_t cost_in = (int64_t)(((uint64_t)slot[21] << 32) | slot[20]);
+            const uint64_t zsum = ((uint64_t)slot[23] << 32) | slot[22], drows = ((uint64_t)slot[25] << 32) | slot[24];
+            const int64_t u0 = (int64_t)r.uncovered_cells - (int64_t)slot[18];
+            r.dual_bound = (double)cost_in + (double)h->cfg.grid_lambda * (double)u0 + (double)h->cfg.lambda * (double)slot[17] +
+                           (double)(zsum + drows) / (double)(1 << mss::kBndScBits);
+        }
         r.time_build_us = (float)t_build_us;
         r.time_solve_us = (float)t_solve_us;
         if (r.status != MSS_OK && ret == MSS_OK) { ret = r.status; h->err = "window " + std::to_string(w) + ": round cap reached (selection is feasible but may be loose)"; }
@@ -648,6 +668,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if ((e = cudaHostAlloc((void**)&h->h_one, 64, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     *h->h_one = 1u;
     if (const char* oc = getenv("MSS_OVERLAP_COPY")) h->overlap_copy = atoi(oc);
+    if (const char* db = getenv("MSS_DUAL_BOUND")) h->want_bound = atoi(db) != 0;
     h->stats.sm_count = h->sm_count;
     *out = h;
     return MSS_OK;
@@ -659,6 +680,7 @@ void mss_destroy(mss_handle* h) {
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     release(h->meta); release(h->ws); release(h->st); release(h->acc); release(h->gain); release(h->deg);
     release(h->seen); release(h->vlist); release(h->trace); release(h->ent); release(h->live); release(h->rows); release(h->out); release(h->stage); release(h->sync); release(h->cc);
+    release(h->b_snap); release(h->b_rows); release(h->b_vars);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -677,6 +699,12 @@ int mss_set_params(mss_handle* h, int32_t min_points, float lambda, float grid_l
     if (!h) return MSS_E_BADARG;
     if (min_points < 0 || !(lambda >= 0.f) || !(grid_lambda >= 0.f)) { h->err = "bad parameters"; return MSS_E_BADARG; }
     h->cfg.min_points = min_points; h->cfg.lambda = lambda; h->cfg.grid_lambda = grid_lambda;
+    return MSS_OK;
+}
+
+int mss_set_dual_bound(mss_handle* h, int32_t enable) {
+    if (!h) return MSS_E_BADARG;
+    h->want_bound = enable != 0;
     return MSS_OK;
 }
 

@@ -52,6 +52,11 @@ struct mss_handle {
     int h_trace_nwin = 0;
     mssi::DevBuf<uint32_t> ent, live;      // CSR entries / live lists (keyframe-row segments, then outside-row segments)
     mssi::DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
+    // dual bound (mss_set_dual_bound): copy of the live lists at the snapshot, per-row and per-point scratch
+    bool want_bound = false;
+    mssi::DevBuf<uint32_t> b_snap;
+    mssi::DevBuf<int> b_rows;              // snap_n | snap_d
+    mssi::DevBuf<unsigned> b_vars;         // share | red
     mssi::DevBuf<uint32_t> out;
     mssi::DevBuf<uint8_t> stage;           // host views staged here
     mssi::DevBuf<unsigned> sync;           // Ctrl (first 128 B) | one barrier counter per group, 128 B apart | ready flags

@@ -43,7 +43,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kCells = 64 * 48;
 constexpr int kCellsPerThread = kCells / kThreads;     // 12
 constexpr int kVarTile = 256;          // var_base alignment; one var-pass tile belongs to exactly one window
-constexpr int kHdrWords = 16;          // result-slot header
+constexpr int kHdrWords = 32;          // result-slot header (16 words of counters + 16 of the dual bound)
 constexpr unsigned kCellNone = 0xFFFFu;     // view: slot whose keypoint is not in the grid
 constexpr unsigned kCellCov = 0xFFFu;       // packed entry: "no cell / cell already covered"
 constexpr int kCellBits = 12;
@@ -105,6 +105,10 @@ struct WinState {
     unsigned error;
     int t_rounds, t_greedy, t_status;      // written by the tail CTA for the rest of the group
     RoundCnt rc[3];
+    // dual bound (mss_bound.cuh): cost of the points taken in the snapshot, cell duals, row multipliers (fixed point 2^-10),
+    // deficit beyond the undecided points, residual cells left uncovered by the final selection
+    unsigned long long b_cost_in, b_zsum, b_drows;
+    unsigned b_s0, b_res_unc;
 };
 
 struct GroupDesc {
@@ -153,6 +157,12 @@ struct Params {
     double lam, glam;
     unsigned long long watchdog_ns;
     int tail_vars, tail_ents;    // residual size handed to the shared-memory tail (<= kTailVars / kTailEnts; 0 = never)
+    // dual bound (optional, all nullptr = off; mss_bound.cuh)
+    uint32_t* b_snap;            // [Ftot + Otot]
+    int* b_snap_n;               // [Rtot]
+    int* b_snap_d;               // [Rtot]
+    unsigned* b_share;           // [Mpad]
+    unsigned* b_red;             // [Mpad]
     const unsigned* ready;       // optional [nwin] (queue order): set to 1 by a stream-ordered host->device copy once the views
                                  // of that window have landed in the staging buffer; nullptr = everything is resident
 };
@@ -328,9 +338,9 @@ __device__ __forceinline__ int warp_excl_scan(BlockScratch& S, int warp_val, int
 // (rank+1)-th largest key (rank elements are larger, counting multiplicity) among the keys produced by `emit`.
 // The caller guarantees that more than `rank` keys exist.  8 radix passes of 8 bits, most significant first.
 template <class Emit>
-__device__ unsigned long long block_kth_largest(BlockScratch& S, int rank, Emit emit) {
+__device__ unsigned long long block_kth_largest(BlockScratch& S, int rank, Emit emit, int low_shift = 0) {
     unsigned long long prefix = 0, mask = 0;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int shift = 56; shift >= low_shift; shift -= 8) {          // (keys whose bits below low_shift are all zero)
         __syncthreads();
         S.hist[threadIdx.x] = 0;            // kThreads == 256 bins
         __syncthreads();
@@ -2252,6 +2262,8 @@ __device__ __forceinline__ void trace_mark(const Params& P, const GroupCtx& G, i
     }
 }
 
+#include "mss_bound.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------
 // one window, solved by the CTAs of one group
 // ---------------------------------------------------------------------------------------------------------------
@@ -2353,8 +2365,26 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         if (rounds >= P.max_rounds) { status = -5; return (int)MODE_FORCE; }
         return (int)MODE_GREEDY;
     };
+    // dual bound: the snapshot is taken right before the first greedy step (mss_bound.cuh); 0 = not taken
+    const BoundBufs BB{P.b_snap, P.b_snap_n, P.b_snap_d, P.b_share, P.b_red};
+    const bool want_bound = P.b_snap != nullptr;
+    int snap_flag = 0;
+    auto bound_snapshot = [&](const int* vprev, int nv, bool csr) -> bool {
+        bound_b0(P, BB, D, ws, G.cta, G.ncta, csr ? P.ent : P.live, csr ? P.ent_n : P.live_n, vprev, nv);
+        if (!group_sync(P, G)) return false;
+        bound_b2(P, BB, D, ws, G.cta, G.ncta, tab);
+        if (!group_sync(P, G)) return false;
+        bound_b3(P, BB, D, ws, G.cta, G.ncta, vprev, nv);
+        if (!group_sync(P, G)) return false;
+        bound_b4(P, BB, D, ws, G.cta, G.ncta, S);        // reads only the snapshot copies: no barrier needed behind it
+        __syncthreads();
+        snap_flag = 1;
+        trace_mark(P, G, w, tn, 9, (unsigned)nv, t_win);
+        return true;
+    };
     mode = after_prop(ws.rc[0].changed, ws.rc[0].nfree);
     trace_mark(P, G, w, tn, 14, ws.rc[0].nfree, t_win);
+    if (want_bound && mode == MODE_GREEDY && !bound_snapshot(P.vlist + D.var_base, vcnt, true)) return false;
     while (mode != MODE_DONE) {
         ++seq;
         RoundCnt& rc = ws.rc[seq % 3];
@@ -2400,7 +2430,12 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
             vcnt = (int)rc.nfree;
             prev_sumdeg = rc.sumdeg;
             mode = after_prop(rc.changed, rc.nfree);
-            if ((mode == MODE_PROP || mode == MODE_GREEDY) && src_cnt <= P.tail_vars && src_deg <= (unsigned)P.tail_ents &&
+            if (want_bound && snap_flag == 0 && greedy_steps == 0 && mode == MODE_GREEDY &&
+                !bound_snapshot(P.vlist + (size_t)src_buf * P.Mpad + D.var_base, src_cnt, false)) return false;
+            // (with the dual bound on, the shared-memory tail -- which may take greedy steps of its own -- starts only after
+            // the snapshot; it is result-neutral, so the selection is the same either way)
+            if ((mode == MODE_PROP || mode == MODE_GREEDY) && (!want_bound || snap_flag != 0 || greedy_steps > 0) &&
+                src_cnt <= P.tail_vars && src_deg <= (unsigned)P.tail_ents &&
                 rc.rows_live <= (unsigned)kTailRows && rc.maxlive <= (unsigned)kTailRowMax) {
                 if (G.cta == 0)
                     tail_solve(P, D, ws, T, S, P.vlist + (size_t)src_buf * P.Mpad + D.var_base, src_cnt, mode, drop_mode, rounds,
@@ -2421,8 +2456,21 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
         case MODE_D2: ++drop_rounds; mode = (drop_rounds >= P.max_drop_rounds) ? MODE_EVAL : MODE_D1; break;
         case MODE_EVAL: unc_final = rc.uncovered; slack_final = rc.slack;      // fallthrough
         case MODE_EVALV: {
+            if (snap_flag == 1) {
+                bound_final(P, BB, D, ws, G.cta, G.ncta, tab);
+                if (!group_sync(P, G)) return false;
+            }
             if (G.cta == 0 && threadIdx.x == 0) {
                 uint32_t* hdr = P.out + D.out_off;
+                // dual bound: 1 = snapshot counters below, 2 = propagation alone decided everything (the selection is optimal),
+                // 0 = none (not asked for, or the round cap forced the rest in)
+                hdr[16] = !want_bound || status != 0 ? 0u : (snap_flag == 1 ? 1u : (greedy_steps == 0 ? 2u : 0u));
+                hdr[17] = ws.b_s0;
+                hdr[18] = ws.b_res_unc;
+                hdr[19] = 0u;
+                hdr[20] = (uint32_t)(ws.b_cost_in & 0xFFFFFFFFull); hdr[21] = (uint32_t)(ws.b_cost_in >> 32);
+                hdr[22] = (uint32_t)(ws.b_zsum & 0xFFFFFFFFull);    hdr[23] = (uint32_t)(ws.b_zsum >> 32);
+                hdr[24] = (uint32_t)(ws.b_drows & 0xFFFFFFFFull);   hdr[25] = (uint32_t)(ws.b_drows >> 32);
                 hdr[0] = (uint32_t)status;
                 hdr[1] = (uint32_t)rounds;
                 hdr[2] = (uint32_t)ws.n_max;

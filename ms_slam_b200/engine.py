@@ -77,7 +77,7 @@ SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_se
            # persistent device mirror (bound in ms_slam_b200/mirror.py)
            "mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
            "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components",
-           "mss_compact_keyframes", "mss_mirror_compact_keyframes",
+           "mss_compact_keyframes", "mss_mirror_compact_keyframes", "mss_set_dual_bound",
            # several GPUs from one process
            "mss_multi_create", "mss_multi_destroy", "mss_multi_device_count", "mss_multi_last_error", "mss_multi_set_params",
            "mss_multi_solve_batch", "mss_multi_get_stats"]
@@ -122,6 +122,7 @@ def load_library(path: str = LIB_PATH):
     lib.mss_get_stats.argtypes = [C.c_void_p, C.POINTER(mss_stats)]
     lib.mss_stream.argtypes = [C.c_void_p]
     lib.mss_stream.restype = C.c_void_p
+    lib.mss_set_dual_bound.argtypes = [C.c_void_p, C.c_int32]
     lib.mss_debug_trace.argtypes = [C.c_void_p, C.c_int32]
     lib.mss_debug_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
     _lib = lib
@@ -266,6 +267,10 @@ class Engine:
     def set_params(self, N, lam, grid_lam):
         self._check(self.lib.mss_set_params(self.handle, N, lam, grid_lam))
         self.N, self.lam, self.grid_lam = N, lam, grid_lam
+
+    def set_dual_bound(self, enable=True):
+        """per-window lower bound of the reference ILP proven on the device (Result.dual_bound; NaN while off)"""
+        self._check(self.lib.mss_set_dual_bound(self.handle, 1 if enable else 0))
 
     def stats(self) -> dict:
         s = mss_stats()

@@ -29,7 +29,7 @@ for i in range(batch):
     ends.append(t[-1][2] / 1e3 if t else -1)
 print("per-window end (us):", " ".join(f"{e:.0f}" for e in ends))
 tr = eng.get_trace(0)
-names = {10: "init", 11: "W1", 12: "W2", 13: "W3", 15: "W4pairs", 14: "W4R1", 1: "PROP", 2: "GREEDY", 3: "FORCE", 4: "D1", 5: "D2", 6: "EVAL", 7: "EVALV", 8: "TAIL", 20: "t-gather", 21: "t-PROP", 22: "t-GREEDY", 30: "t-rows", 31: "t-maxn"}
+names = {10: "init", 11: "W1", 12: "W2", 13: "W3", 15: "W4pairs", 14: "W4R1", 1: "PROP", 2: "GREEDY", 3: "FORCE", 4: "D1", 5: "D2", 6: "EVAL", 7: "EVALV", 8: "TAIL", 9: "BOUND", 20: "t-gather", 21: "t-PROP", 22: "t-GREEDY", 30: "t-rows", 31: "t-maxn"}
 prev = 0
 out = []
 for ph, free, ns in tr:
