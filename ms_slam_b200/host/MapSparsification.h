@@ -11,6 +11,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <limits>
 #include <vector>
 
 #include "../../include/mss.h"
@@ -107,6 +108,9 @@ public:
         double build_ms = 0.0;          // device time of the view assembly (mirror) inside solve_ms
         long h2d_bytes = 0, d2h_bytes = 0;
         int devices = 1;                // GPUs the window's components were dealt out to
+        double dual_bound = std::numeric_limits<double>::quiet_NaN();   // lower bound of the reference ILP proven on the device
+                                        // (sum over the components; NaN unless MSS_DUAL_BOUND=1): objective / dual_bound - 1 is
+                                        // a certified optimality gap, the counterpart of GUROBI's MIPGap (:155-156)
     };
     std::vector<WindowReport> GetReports();           // the last kMaxReports windows
     static constexpr size_t kMaxReports = 256;

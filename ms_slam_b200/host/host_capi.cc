@@ -258,10 +258,11 @@ int msh_reports2(void* h, double* out, int cap_windows) {
     const int n = std::min(cap_windows, (int)reps.size());
     for (int i = 0; i < n; ++i) {
         const auto& r = reps[i];
-        double* o = out + 19 * i;
+        double* o = out + 20 * i;
         o[0] = r.status; o[1] = r.K; o[2] = r.H; o[3] = r.M; o[4] = r.n_vars; o[5] = r.n_kept; o[6] = r.n_deleted; o[7] = r.rounds;
         o[8] = r.objective; o[9] = r.flatten_ms; o[10] = r.solve_ms; o[11] = r.apply_ms; o[12] = r.components;
         o[13] = r.mirror; o[14] = (double)r.delta_ops; o[15] = r.build_ms; o[16] = (double)r.h2d_bytes; o[17] = (double)r.d2h_bytes; o[18] = r.devices;
+        o[19] = r.dual_bound;
     }
     return (int)reps.size();
 }

@@ -58,7 +58,7 @@ class World:
     """One Atlas + LoopClosing + MapSparsification, populated from a WindowView."""
 
     def __init__(self, view: WindowView, N=100, lam=500.0, grid_lam=10.0, window_length=None, inertial=False, non_local=30,
-                 mirror=None, batched_handback=None, devices=None):
+                 mirror=None, batched_handback=None, devices=None, dual_bound=None):
         """mirror: None = the class default (device mirror on when a GPU is present), False = flatten every window from the
         pointer graph (MSS_MIRROR=0), True = default.  batched_handback=False: per-point SetBadFlag like the reference."""
         self.lib = load_library()
@@ -68,7 +68,8 @@ class World:
         write_settings(self.tmp.name, N, lam, grid_lam, window_length if window_length is not None else max(view.K, 1), non_local)
         env = {"MSS_MIRROR": None if mirror is None else ("1" if mirror else "0"),
                "MSS_BATCHED_HANDBACK": None if batched_handback is None else ("1" if batched_handback else "0"),
-               "MSS_DEVICES": None if devices is None else str(devices)}
+               "MSS_DEVICES": None if devices is None else str(devices),
+               "MSS_DUAL_BOUND": None if dual_bound is None else ("1" if dual_bound else "0")}
         saved = {k: os.environ.get(k) for k in env}
         for k, v in env.items():
             if v is not None:
@@ -165,11 +166,11 @@ class World:
         return dict(map_points=int(out[0]), sparsified_map_points=int(out[1]), sparsified_keyframes=int(out[2]))
 
     def reports(self):
-        out = np.zeros(19 * 64, np.float64)
+        out = np.zeros(20 * 64, np.float64)
         n = min(self.lib.msh_reports2(self.h, _p(out), 64), 64)
         keys = ["status", "K", "H", "M", "n_vars", "n_kept", "n_deleted", "rounds", "objective", "flatten_ms", "solve_ms", "apply_ms",
-                "components", "mirror", "delta_ops", "build_ms", "h2d_bytes", "d2h_bytes", "devices"]
-        return [dict(zip(keys, out[19 * i:19 * i + 19].tolist())) for i in range(n)]
+                "components", "mirror", "delta_ops", "build_ms", "h2d_bytes", "d2h_bytes", "devices", "dual_bound"]
+        return [dict(zip(keys, out[20 * i:20 * i + 20].tolist())) for i in range(n)]
 
     def mirror_active(self):
         return bool(self.lib.msh_mirror_active(self.h))

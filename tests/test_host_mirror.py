@@ -358,3 +358,34 @@ def test_c2_sized_flush_from_the_mirror_equals_the_flatten_path(hm):
     for k in ("objective", "n_deleted", "n_kept", "n_vars", "rounds"):
         assert out[True][1][k] == out[False][1][k], k
     assert out[True][1]["h2d_bytes"] < 16384 and out[True][1]["d2h_bytes"] < 65536
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mirror", [False, True])
+def test_windows_carry_a_certificate(hm, mirror):
+    """MSS_DUAL_BOUND=1: every window the class solves reports the lower bound the device proved for it (the counterpart of
+    GUROBI's MIPGap, MapSparsification.cc:155-156) -- never above the LP optimum of the reference model, within 1 % of F."""
+    from oracle import ilp_model as om
+    view, N = msgen.make_config("live", 2)
+    w = hm.World(view, N=N, mirror=mirror, dual_bound=True)
+    try:
+        w.start()
+        w.feed(0, view.K)
+        assert w.wait_forwarded(view.K) == 0
+        rep = w.reports()[0]
+        lp = om.solve_lp(view, N, LAM, GLAM).objective
+        assert rep["status"] == 0 and np.isfinite(rep["dual_bound"])
+        assert rep["dual_bound"] <= lp + 1e-6 and rep["objective"] <= 1.01 * rep["dual_bound"]
+        assert w.finish() == 0
+    finally:
+        w.close()
+    w = hm.World(view, N=N, mirror=mirror)                   # off by default: no bound, same selection
+    try:
+        w.start()
+        w.feed(0, view.K)
+        assert w.wait_forwarded(view.K) == 0
+        rep2 = w.reports()[0]
+        assert np.isnan(rep2["dual_bound"]) and rep2["objective"] == rep["objective"] and rep2["n_deleted"] == rep["n_deleted"]
+        assert w.finish() == 0
+    finally:
+        w.close()
