@@ -322,6 +322,42 @@ typedef struct mss_kf_payload {
 int mss_compact_keyframes(mss_handle* h, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
 int mss_mirror_compact_keyframes(mss_mirror* m, int32_t nkf, const mss_kf_payload* kfs, int32_t* n_out);
 
+/* ---- BoW re-transform of compacted keyframes + KeyFrameDatabase inverted file ---------------------------------------
+ * After the compaction the reference transforms the surviving descriptors of a sparsified keyframe again
+ * (mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4), src/KeyFrame.cc:352-354; DBoW2 TemplatedVocabulary.h:1126-1259)
+ * and LoopClosing::DeleteOutdatedInfo adds it to the KeyFrameDatabase (src/LoopClosing.cc:318-329).
+ *
+ * mss_voc_create: the vocabulary tree as DBoW2's text file lists it (TemplatedVocabulary.h:1338-1418): node 0 is the root,
+ * node i > 0 has parent[i] < i, is_leaf[i], a 32-byte ORB descriptor and a weight; children keep their order of appearance,
+ * word ids are handed out to the leaves in file order.  TF-IDF weighting with L1 scoring (ORBvoc: "10 6 0 0").
+ * mss_bow_transform: per keyframe n descriptors in DEVICE memory (e.g. the rows mss_compact_keyframes left) -> per feature the
+ * word and the node `levelsup` levels above the leaves (HOST arrays, may be NULL), the BowVector (distinct words ascending +
+ * L1-normalised values, bit-identical to DBoW2's doubles) and the FeatureVector as (node, feature) pairs in map order.
+ * add_to_database != 0: the keyframes are appended to the inverted file (KeyFrameDatabase::add).
+ * mss_kfdb_common_words: words a query BowVector shares with every database keyframe id < kf_cap (the counting loop of the
+ * detection queries, src/KeyFrameDatabase.cc:610-640). */
+typedef struct mss_vocabulary mss_vocabulary;
+typedef struct mss_bow_keyframe {
+    int32_t n;                 /* descriptors (<= 4096) */
+    int32_t kf_id;             /* id stored in the inverted file */
+    const void* descriptors;   /* [n][32] device */
+    int32_t* word;             /* [n] host out, may be NULL */
+    int32_t* node;             /* [n] host out, may be NULL */
+    int32_t* bow_word;         /* [n] host out: distinct words, ascending */
+    double*  bow_value;        /* [n] host out */
+    int32_t* n_bow;            /* host out: entries of the BowVector */
+    int32_t* fv_node;          /* [n] host out: FeatureVector, pairs sorted by (node, feature) */
+    int32_t* fv_feature;       /* [n] host out */
+    int32_t* n_fv;             /* host out */
+} mss_bow_keyframe;
+int  mss_voc_create(mss_handle* h, int32_t n_nodes, int32_t levels, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* descriptors,
+                    const double* weight, mss_vocabulary** out);
+void mss_voc_destroy(mss_vocabulary* v);
+int32_t mss_voc_words(const mss_vocabulary* v);
+int  mss_bow_transform(mss_vocabulary* v, int32_t nkf, const mss_bow_keyframe* kfs, int32_t levelsup, int32_t add_to_database);
+int  mss_kfdb_common_words(mss_vocabulary* v, int32_t n_query_words, const int32_t* query_words, int32_t kf_cap, int32_t* common);
+int32_t mss_kfdb_postings(const mss_vocabulary* v);
+
 /* Lower bound of the reference ILP, proven on the device per window (mss_result.dual_bound; NaN while off -- the default --
  * or when the round cap was hit).  The reference gets its certificate from GUROBI's branch and bound (MIPGap 0.002,
  * src/MapSparsification.cc:153-157); here it comes from the state reached by exact dominance rules + one round of dual

@@ -18,6 +18,7 @@
 //   db_add / db_common   postings (word, keyframe) appended to the inverted file; words in common per database keyframe
 // The vocabulary (ORBvoc: k = 10, L = 6, ~1.1 M nodes x 32 B = 35 MB) stays resident in L2; the work is popc + L2 traffic.
 #include "../../include/mss.h"
+#define MSS_KERNELS_TYPES_ONLY
 #include "mss_internal.h"
 
 #include <algorithm>
@@ -106,6 +107,7 @@ __global__ void bow_vectors(int nkf, const int* feat_off, const int* word, const
                             double* bow_val, int* n_bow, int* fv_node, int* fv_feat, int* n_fv, int* err) {
     extern __shared__ unsigned long long key[];
     __shared__ int s_cnt;
+    __shared__ double s_norm;
     for (int q = blockIdx.x; q < nkf; q += gridDim.x) {
         const int f0 = feat_off[q], n = feat_off[q + 1] - f0;
         if (n > kMaxFeat) { if (threadIdx.x == 0) { atomicOr(err, 1); n_bow[q] = 0; n_fv[q] = 0; } continue; }
@@ -134,14 +136,12 @@ __global__ void bow_vectors(int nkf, const int* feat_off, const int* word, const
             }
             s_cnt = m;
             n_bow[q] = m;
-            // (the division runs in parallel below)
-            bow_val[f0 + n - 1 + (m == n ? 0 : 0)] = bow_val[f0 + n - 1];    // no-op: keeps the compiler from reordering the loop
-            reinterpret_cast<double*>(key)[kMaxFeat - 1 < np2 ? np2 - 1 : np2 - 1] = norm;     // hand the norm to the other threads
+            s_norm = norm;                   // (the division runs in parallel below)
         }
         __syncthreads();
         {
             const int m = s_cnt;
-            const double norm = reinterpret_cast<double*>(key)[np2 - 1];
+            const double norm = s_norm;
             if (norm > 0.0)
                 for (int i = threadIdx.x; i < m; i += kT) bow_val[f0 + i] = bow_val[f0 + i] / norm;
         }

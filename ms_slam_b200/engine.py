@@ -78,6 +78,8 @@ SYMBOLS = ["mss_version", "mss_create", "mss_destroy", "mss_last_error", "mss_se
            "mss_mirror_create", "mss_mirror_destroy", "mss_mirror_add_keyframe", "mss_mirror_add_keyframes",
            "mss_mirror_set_map_points", "mss_mirror_apply", "mss_mirror_solve", "mss_mirror_build_view", "mss_mirror_get_stats", "mss_mirror_components",
            "mss_compact_keyframes", "mss_mirror_compact_keyframes", "mss_set_dual_bound",
+           # BoW re-transform + keyframe database (bound in ms_slam_b200/bow.py)
+           "mss_voc_create", "mss_voc_destroy", "mss_voc_words", "mss_bow_transform", "mss_kfdb_common_words", "mss_kfdb_postings",
            # several GPUs from one process
            "mss_multi_create", "mss_multi_destroy", "mss_multi_device_count", "mss_multi_last_error", "mss_multi_set_params",
            "mss_multi_solve_batch", "mss_multi_get_stats"]
