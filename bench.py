@@ -481,6 +481,86 @@ def host_api_leg(N, lam, glam):
     return out
 
 
+def after_path_leg(eng, E, torch, local_rank, peak):
+    """The two steps right behind the path, on the device: compaction of the per-keypoint arrays of the
+    keyframes of one c2-sized window (KeyFrame::EraseBadDescriptor, 68 B per row: pure data movement, HBM roofline) and the BoW
+    re-transform of the surviving descriptors against an ORBvoc-shaped vocabulary (k = 10, L = 6: 1.1 M nodes, 35 MB,
+    L2-resident).  Timed with CUDA events on the engine's stream around the C-ABI call (it includes the small descriptor
+    upload and the read-back of the row counts / vectors)."""
+    from ms_slam_b200 import bow as BW
+    from ms_slam_b200.mirror import KeyframePayload, compact_keyframes
+    out = {}
+    stream = torch.cuda.ExternalStream(eng.lib.mss_stream(eng.handle), device=torch.device("cuda", local_rank))
+    rng = np.random.default_rng(0)
+    nkf, rows, frac = 500, 2000, 0.15                                    # c2: 500 keyframes x 2000 keypoints, ~15 % of the points survive
+    def payloads():
+        ps = []
+        for _ in range(nkf):
+            ps.append(KeyframePayload(eng, rows, rng.random(rows) < frac, rng.integers(0, 256, size=(rows, 32), dtype=np.uint8),
+                                      rng.integers(0, 2**31, size=(rows, 7), dtype=np.int64).astype(np.uint32),
+                                      rng.random(rows, dtype=np.float32), rng.random(rows, dtype=np.float32)))
+        return ps
+    try:
+        times, left = [], None
+        for it in range(4):                                              # in place: fresh arrays every time (first one = warm-up)
+            ps = payloads()
+            from ms_slam_b200 import mirror as MR
+            MR._declare(eng.lib)
+            carr = (MR.mss_kf_payload * nkf)(*[p.c_struct() for p in ps])       # (marshalling outside the timed call)
+            left = np.zeros(nkf, np.int32)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = eng.lib.mss_compact_keyframes(eng.handle, nkf, carr, left.ctypes.data)
+            e1.record(stream)
+            e1.synchronize()
+            assert rc == 0
+            times.append(e0.elapsed_time(e1))
+            if it < 3:
+                for p in ps:
+                    p.free()
+        ms = float(np.median(times[1:]))
+        moved = nkf * rows * (68 + 1) + int(left.sum()) * 68             # every row and its flag read once, survivors written once
+        out["compaction"] = {"keyframes": nkf, "rows_per_keyframe": rows, "rows_left": int(left.sum()), "call_ms": ms,
+                             "algorithmic_bytes": moved, "achieved_gbs": moved / ms / 1e6, "frac_of_hbm_peak": moved / ms / 1e6 / peak,
+                             "what": "mss_compact_keyframes over the keyframes of one c2-sized window, one launch; the call also uploads 500 "
+                                     "descriptors of the arrays (28 KB) and reads the row counts back, so this is a lower bound of the kernel's rate"}
+        # ---- BoW re-transform of the survivors ---------------------------------------------------------------------------------
+        voc = BW.synthetic_vocabulary(k=10, L=6, seed=0, ragged=False)
+        V = BW.Vocabulary(eng, voc)
+        counts = [int(x) for x in left]
+        ptrs = [p.ptr["descriptors"] for p in ps]
+        times = []
+        barr = (BW.mss_bow_keyframe * nkf)()
+        keep_alive = []
+        for q in range(nkf):                                                 # host arrays for every output, marshalled once
+            n = max(counts[q], 1)
+            o = [np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64), np.zeros(1, np.int32),
+                 np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(1, np.int32)]
+            keep_alive.append(o)
+            barr[q] = BW.mss_bow_keyframe(counts[q], q, ptrs[q], *[a.ctypes.data for a in o])
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = eng.lib.mss_bow_transform(V.handle, nkf, barr, 4, 1 if it == 3 else 0)
+            e1.record(stream)
+            e1.synchronize()
+            assert rc == 0
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[1:]))
+        nd = int(sum(counts))
+        out["bow_transform"] = {"keyframes": nkf, "descriptors": nd, "vocabulary_nodes": int(voc["parent"].size), "call_ms": ms,
+                                "descriptors_per_s": nd / (ms * 1e-3), "node_descriptor_bytes_read": nd * 6 * 10 * 32,
+                                "achieved_gbs_from_l2": nd * 6 * 10 * 32 / ms / 1e6,
+                                "what": "mss_bow_transform: tree descent (6 levels x 10 children x 32 B per descriptor, from L2) + per-keyframe "
+                                        "BowVector / FeatureVector + read-back of the vectors to the host"}
+        V.close()
+        for p in ps:
+            p.free()
+    except Exception as e:      # noqa: BLE001
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -750,6 +830,10 @@ def main():
             line["other_configs"] = sub
             # ---- the reference-facing C++ API around the solve -----------------------------------------------------------------
             line["host_api"] = host_api_leg(N, msgen.LAMBDA, msgen.GRID_LAMBDA)
+            # ---- the steps right behind the path, on the device (f2 compaction, f4 BoW re-transform) --------------------------
+            e2 = E.Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+            line["after_path"] = after_path_leg(e2, E, torch, local_rank, peak)
+            e2.close()
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)

@@ -32,6 +32,14 @@ def synthetic_vocabulary(k=10, L=3, seed=0, stop_frac=0.05, ragged=True):
     that with `ragged` a few inner nodes have fewer children or are leaves early.  Random 256-bit descriptors, positive
     idf-like weights, a fraction of stopped words (weight 0).  -> dict(parent, is_leaf, desc, weight, k, L)"""
     rng = np.random.default_rng(seed)
+    if not ragged:                                           # complete tree in breadth-first order (fast path for large trees)
+        n = (k ** (L + 1) - 1) // (k - 1)
+        parent = np.maximum((np.arange(n, dtype=np.int64) - 1) // k, 0).astype(np.int32)
+        is_leaf = (np.arange(n) >= (k ** L - 1) // (k - 1)).astype(np.uint8)
+        desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        weight = np.where(is_leaf == 1, rng.random(n) * 8.0 + 0.01, 0.0)
+        weight[(is_leaf == 1) & (rng.random(n) < stop_frac)] = 0.0
+        return dict(parent=parent, is_leaf=is_leaf, desc=desc, weight=weight.astype(np.float64), k=k, L=L)
     parent, level = [0], [0]
     frontier = [0]
     for lev in range(1, L + 1):

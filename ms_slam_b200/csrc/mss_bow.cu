@@ -204,6 +204,7 @@ struct mss_vocabulary {
     DevBuf<int> word_count;      // [n_words] + cursor + err
     DevBuf<unsigned> bitmap;
     int n_postings = 0;
+    uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;      // pinned hand-back buffer
 };
 
 extern "C" {
@@ -265,6 +266,7 @@ void mss_voc_destroy(mss_vocabulary* v) {
     if (!v) return;
     cudaSetDevice(v->h->device);
     release(v->desc); release(v->ints); release(v->weight); release(v->scratch); release(v->postings); release(v->word_count); release(v->bitmap);
+    if (v->h_pin) cudaFreeHost(v->h_pin);
     delete v;
 }
 
@@ -330,27 +332,26 @@ int mss_bow_transform(mss_vocabulary* v, int32_t nkf, const mss_bow_keyframe* kf
         MSS_CUDA(h, cudaMemcpyAsync(&v->n_postings, d_cursor, 4, cudaMemcpyDeviceToHost, h->stream));
     }
     MSS_CUDA(h, cudaGetLastError());
-    // hand-back
-    std::vector<int> nb(nkf), nf(nkf);
-    int err = 0;
-    MSS_CUDA(h, cudaMemcpyAsync(nb.data(), d_nb, (size_t)nkf * 4, cudaMemcpyDeviceToHost, h->stream));
-    MSS_CUDA(h, cudaMemcpyAsync(nf.data(), d_nf, (size_t)nkf * 4, cudaMemcpyDeviceToHost, h->stream));
-    MSS_CUDA(h, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    // hand-back: everything the kernels produced comes back with ONE copy into pinned memory (per-keyframe copies into the
+    // caller's pageable arrays would cost ~10 us each), then plain memcpy on the host
+    if ((rc = ensure_pinned(h, (void**)&v->h_pin, &v->h_pin_cap, bytes - o_nb))) return rc;
+    MSS_CUDA(h, cudaMemcpyAsync(v->h_pin, S + o_nb, bytes - o_nb, cudaMemcpyDeviceToHost, h->stream));
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (err) { h->err = "bow_transform: device error " + std::to_string(err); return MSS_E_INTERNAL; }
+    const uint8_t* H = v->h_pin - o_nb;                              // same offsets as on the device
+    const int *nb = (const int*)(H + o_nb), *nf = (const int*)(H + o_nf);
+    if (*(const int*)(H + o_err)) { h->err = "bow_transform: device error " + std::to_string(*(const int*)(H + o_err)); return MSS_E_INTERNAL; }
     for (int q = 0; q < nkf; ++q) {
         const mss_bow_keyframe& k = kfs[q];
         const size_t f0 = (size_t)off[q];
         if (k.n_bow) *k.n_bow = nb[q];
         if (k.n_fv) *k.n_fv = nf[q];
-        if (k.word && k.n) MSS_CUDA(h, cudaMemcpyAsync(k.word, d_word + f0, (size_t)k.n * 4, cudaMemcpyDeviceToHost, h->stream));
-        if (k.node && k.n) MSS_CUDA(h, cudaMemcpyAsync(k.node, d_node + f0, (size_t)k.n * 4, cudaMemcpyDeviceToHost, h->stream));
-        if (k.bow_word && nb[q]) MSS_CUDA(h, cudaMemcpyAsync(k.bow_word, d_bw + f0, (size_t)nb[q] * 4, cudaMemcpyDeviceToHost, h->stream));
-        if (k.bow_value && nb[q]) MSS_CUDA(h, cudaMemcpyAsync(k.bow_value, d_bv + f0, (size_t)nb[q] * 8, cudaMemcpyDeviceToHost, h->stream));
-        if (k.fv_node && nf[q]) MSS_CUDA(h, cudaMemcpyAsync(k.fv_node, d_fn + f0, (size_t)nf[q] * 4, cudaMemcpyDeviceToHost, h->stream));
-        if (k.fv_feature && nf[q]) MSS_CUDA(h, cudaMemcpyAsync(k.fv_feature, d_ff + f0, (size_t)nf[q] * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (k.word && k.n) memcpy(k.word, (const int*)(H + o_word) + f0, (size_t)k.n * 4);
+        if (k.node && k.n) memcpy(k.node, (const int*)(H + o_node) + f0, (size_t)k.n * 4);
+        if (k.bow_word && nb[q]) memcpy(k.bow_word, (const int*)(H + o_bw) + f0, (size_t)nb[q] * 4);
+        if (k.bow_value && nb[q]) memcpy(k.bow_value, (const double*)(H + o_bv) + f0, (size_t)nb[q] * 8);
+        if (k.fv_node && nf[q]) memcpy(k.fv_node, (const int*)(H + o_fn) + f0, (size_t)nf[q] * 4);
+        if (k.fv_feature && nf[q]) memcpy(k.fv_feature, (const int*)(H + o_ff) + f0, (size_t)nf[q] * 4);
     }
-    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
     return MSS_OK;
 }
 
