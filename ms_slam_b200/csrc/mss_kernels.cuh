@@ -1087,9 +1087,15 @@ __device__ void row_prop(const Params& P, const WinDesc& D, int R, int n, int of
     unsigned long long* acc_w = P.acc + D.var_base;
     const int need = P.row_need[R];
     const int cov0 = P.row_cov[R];
+    // entries per thread = exactly the 32-entry blocks a warp's share of the list needs (a c2 keyframe row of 1 250 .. 1 600
+    // entries takes 5 .. 7, not 8: the unrolled row code has no idle iterations)
     if (n <= kThreads) row_prop_regs<1>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else if (n <= 2 * kThreads) row_prop_regs<2>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 3 * kThreads) row_prop_regs<3>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else if (n <= 4 * kThreads) row_prop_regs<4>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 5 * kThreads) row_prop_regs<5>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 6 * kThreads) row_prop_regs<6>(P, D, R, n, src, dst, need, cov0, par, tab, S);
+    else if (n <= 7 * kThreads) row_prop_regs<7>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else if (n <= kRegRow) row_prop_regs<8>(P, D, R, n, src, dst, need, cov0, par, tab, S);
     else {
         // long row: two passes over the list in global memory
@@ -1484,8 +1490,8 @@ __device__ __forceinline__ void row_d1_regs(const Params& P, const WinDesc& D, i
     RowRegs<EPT> X;
     load_row(X, src, n, st_w);
 #pragma unroll
-    for (int b = 0; b < EPT; ++b)
-        if (X.e[b] != kEntInvalid && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
+    for (int b = 0; b < EPT; ++b)           // (only the cells of IN entries are counted and read below: the others need no zeroing)
+        if (X.e[b] != kEntInvalid && X.s[b] == ST_IN && (X.e[b] & kCellCov) != kCellCov) tab[X.e[b] & kCellCov] = 0u;
     __syncthreads();
     unsigned m[EPT];
 #pragma unroll
@@ -1538,7 +1544,11 @@ __device__ void row_d1_eval(const Params& P, const WinDesc& D, RoundCnt& rc, int
     int cin = 0, ccells = 0, z = 0;
     if (n > 0 && n <= kThreads) row_d1_regs<1>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0 && n <= 2 * kThreads) row_d1_regs<2>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 3 * kThreads) row_d1_regs<3>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0 && n <= 4 * kThreads) row_d1_regs<4>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 5 * kThreads) row_d1_regs<5>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 6 * kThreads) row_d1_regs<6>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
+    else if (n > 0 && n <= 7 * kThreads) row_d1_regs<7>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0 && n <= kRegRow) row_d1_regs<8>(P, D, n, src, dst, need, par, accumulate, tab, S, cin, ccells);
     else if (n > 0) {
         zero_tab(tab);
