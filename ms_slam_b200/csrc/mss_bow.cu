@@ -313,6 +313,7 @@ int mss_bow_transform(mss_vocabulary* v, int32_t nkf, const mss_bow_keyframe* kf
     int *d_off = (int*)(S + o_off), *d_id = (int*)(S + o_id), *d_nb = (int*)(S + o_nb), *d_nf = (int*)(S + o_nf), *d_err = (int*)(S + o_err);
     int *d_word = (int*)(S + o_word), *d_node = (int*)(S + o_node), *d_bw = (int*)(S + o_bw), *d_fn = (int*)(S + o_fn), *d_ff = (int*)(S + o_ff);
     double *d_w = (double*)(S + o_w), *d_bv = (double*)(S + o_bv);
+    MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (total > 0) {
         const int groups_per_cta = mssb::kT / mssb::kGroup;
         const int grid = std::max(1, std::min((total + groups_per_cta - 1) / groups_per_cta, h->sm_count * 16));
@@ -331,12 +332,17 @@ int mss_bow_transform(mss_vocabulary* v, int32_t nkf, const mss_bow_keyframe* kf
         h->stats.kernel_launches += 1;
         MSS_CUDA(h, cudaMemcpyAsync(&v->n_postings, d_cursor, 4, cudaMemcpyDeviceToHost, h->stream));
     }
+    MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     MSS_CUDA(h, cudaGetLastError());
     // hand-back: everything the kernels produced comes back with ONE copy into pinned memory (per-keyframe copies into the
     // caller's pageable arrays would cost ~10 us each), then plain memcpy on the host
     if ((rc = ensure_pinned(h, (void**)&v->h_pin, &v->h_pin_cap, bytes - o_nb))) return rc;
     MSS_CUDA(h, cudaMemcpyAsync(v->h_pin, S + o_nb, bytes - o_nb, cudaMemcpyDeviceToHost, h->stream));
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;  // descent + vectors (+ inverted file)
+    }
     const uint8_t* H = v->h_pin - o_nb;                              // same offsets as on the device
     const int *nb = (const int*)(H + o_nb), *nf = (const int*)(H + o_nf);
     if (*(const int*)(H + o_err)) { h->err = "bow_transform: device error " + std::to_string(*(const int*)(H + o_err)); return MSS_E_INTERNAL; }

@@ -659,6 +659,7 @@ static int compact_impl(mss_handle* h, mss_mirror* m, int32_t nkf, const mss_kf_
     if (rc) return rc;
     MSS_CUDA(h, cudaMemcpyAsync(up.p, hp.data(), (size_t)nkf * sizeof(mssc::KfPayload), cudaMemcpyHostToDevice, h->stream));
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));                  // hp is pageable
+    MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     mssc::compact_keyframes_kernel<<<std::min(nkf, h->sm_count * 8), mssc::kT, 0, h->stream>>>(
         reinterpret_cast<const mssc::KfPayload*>(up.p), nkf, m ? m->slot_mp.p : nullptr, m ? m->S : 0, reinterpret_cast<int*>(up.p + off_out));
     MSS_CUDA(h, cudaGetLastError());
@@ -669,8 +670,11 @@ static int compact_impl(mss_handle* h, mss_mirror* m, int32_t nkf, const mss_kf_
         MSS_CUDA(h, cudaGetLastError());
         h->stats.kernel_launches += nkf;
     }
+    MSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     MSS_CUDA(h, cudaMemcpyAsync(n_out, up.p + off_out, (size_t)nkf * 4, cudaMemcpyDeviceToHost, h->stream));
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;      // the compaction kernel(s)
     return MSS_OK;
 }
 
