@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -344,12 +346,17 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
     }
     MSS_CUDA(h, cudaMemcpyAsync(h->meta.p, h->h_meta, meta_bytes, cudaMemcpyHostToDevice, h->stream));
     h2d += (int64_t)meta_bytes;
-    MSS_CUDA(h, cudaMemsetAsync(h->sync.p, 0, sync_words * 4, h->stream));
-    for (int w : rejected) MSS_CUDA(h, cudaMemsetAsync(h->out.p + out_off[w], 0, (size_t)mss::kHdrWords * 4, h->stream));
-    if (gated) {
-        MSS_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
-        MSS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+    // (cleared by a DMA copy of pinned zeros: a memset kernel would have to wait for a persistent kernel of another handle
+    // on this device to drain, and with it this call's staging copies)
+    if (sync_words * 4 > h->h_zero_cap) {
+        const size_t old = h->h_zero_cap;
+        if ((rc = ensure_pinned(h, (void**)&h->h_zero, &h->h_zero_cap, sync_words * 4))) return rc;
+        (void)old;
+        memset(h->h_zero, 0, h->h_zero_cap);
     }
+    MSS_CUDA(h, cudaMemcpyAsync(h->sync.p, h->h_zero, sync_words * 4, cudaMemcpyHostToDevice, h->stream));
+    for (int w : rejected) MSS_CUDA(h, cudaMemsetAsync(h->out.p + out_off[w], 0, (size_t)mss::kHdrWords * 4, h->stream));
+    if (gated) MSS_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));      // (the staging stream waits for it right before the copies)
     // ---- staging copies, in queue order ------------------------------------------------------------------------------------
     cudaError_t copy_err = cudaSuccess;
     auto copy_window = [&](int i) {
@@ -457,11 +464,15 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         launched = true;
         MSS_CUDA_LAUNCHED(h, cudaEventRecord(h->ev1, h->stream));
         if (gated) {
-            // the kernel is running (or queued); feed it: window after window in queue order, flag after data
+            // the kernel is running (or queued); feed it: window after window in queue order, flag after data.  The whole
+            // batch is enqueued under the device's staging mutex: batches of different handles travel one after the other
+            std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(h->copy_mutex));
+            copy_err = cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0);
             for (int q = 0; q < nl && copy_err == cudaSuccess; ++q) {
                 copy_window(plan.order[q]);
                 if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(d_ready + q, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream);
             }
+            if (copy_err == cudaSuccess) copy_err = cudaEventRecord(h->ev_copied, h->copy_stream);
             MSS_CUDA_LAUNCHED(h, copy_err);
             h2d += 4ll * nl;
         }
@@ -531,7 +542,8 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         h->stats.kernel_launches += 1;
     }
     MSS_CUDA_LAUNCHED(h, cudaStreamSynchronize(h->stream));
-    if (gated) MSS_CUDA_LAUNCHED(h, cudaStreamSynchronize(h->copy_stream));     // (only an aborted launch can finish before its copies)
+    if (gated) MSS_CUDA_LAUNCHED(h, cudaEventSynchronize(h->ev_copied));       // (only an aborted launch can finish before its copies;
+                                                                               //  the stream itself may already carry another handle's batch)
     if (nl > 0) MSS_CUDA(h, cudaEventElapsedTime(&dev_ms, h->ev0, h->ev1));
     unsigned long long row_entries = 0, var_visits = 0;
     if (nl > 0) {
@@ -618,6 +630,25 @@ extern "C" {
 
 int mss_version(void) { return MSS_VERSION; }
 
+// One staging (host -> device) stream per DEVICE, shared by every handle on it.  Handles are single-threaded, so an
+// application that wants the copies of one batch to travel while another batch is being solved runs two handles from two
+// threads (bench.py `e2e`); their staging copies must then queue FIFO, batch after batch -- copies of two batches that
+// interleave would feed both persistent kernels at half the PCIe rate.  The mutex orders the enqueueing of whole batches.
+namespace {
+struct DeviceCopyStream { cudaStream_t stream = nullptr; std::mutex enqueue; };
+std::mutex g_copy_table_mutex;
+std::map<int, DeviceCopyStream*> g_copy_table;
+DeviceCopyStream* device_copy_stream(int device) {
+    std::lock_guard<std::mutex> lock(g_copy_table_mutex);
+    auto it = g_copy_table.find(device);
+    if (it != g_copy_table.end()) return it->second;
+    DeviceCopyStream* d = new DeviceCopyStream();
+    if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { delete d; return nullptr; }
+    g_copy_table[device] = d;                 // lives as long as the process (handles come and go)
+    return d;
+}
+}  // namespace
+
 int mss_create(const mss_config* cfg, mss_handle** out) {
     if (!cfg || !out) return MSS_E_BADARG;
     *out = nullptr;
@@ -663,7 +694,13 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if (const char* te = getenv("MSS_TAIL_ENTS")) h->tail_ents = atoi(te);
     if (const char* wd = getenv("MSS_WATCHDOG_MS")) { const long long ms = atoll(wd); if (ms > 0) h->watchdog_ns = (unsigned long long)ms * 1000000ull; }
     if ((e = cudaHostAlloc((void**)&h->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
-    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    {
+        DeviceCopyStream* dcs = device_copy_stream(h->device);
+        if (!dcs) return fail("cudaStreamCreate (staging stream)", cudaErrorUnknown);
+        h->copy_stream = dcs->stream;
+        h->copy_mutex = &dcs->enqueue;
+    }
+    if ((e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void**)&h->h_one, 64, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
     *h->h_one = 1u;
@@ -688,7 +725,8 @@ void mss_destroy(mss_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     if (h->h_one) cudaFreeHost(h->h_one);
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+    if (h->h_zero) cudaFreeHost(h->h_zero);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

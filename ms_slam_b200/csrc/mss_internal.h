@@ -34,6 +34,9 @@ struct mss_handle {
     int max_ctas_per_sm = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;  // compute stream -> copy stream: the ready flags of this call have been zeroed
+    cudaEvent_t ev_copied = nullptr; // copy stream: the last staging copy of this call
+    void* copy_mutex = nullptr;      // std::mutex of the device's shared copy stream (see device_copy_stream in mss_engine.cu)
+    uint8_t* h_zero = nullptr; size_t h_zero_cap = 0;   // pinned zeros: the sync words are cleared by a DMA copy, not by a kernel
     int overlap_copy = 1;            // host views: copy on the copy stream while the kernel runs (per-window ready flags); 0 = copy first
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
