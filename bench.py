@@ -314,7 +314,7 @@ class Batch:
                 if layout in ("packed", "packed16"):
                     self.hv[w] = E.packed_c_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
                                                  *self.pin_blob([v.feat_ptr, v.slots, v.mp_nobs16, v.obs_pairs, v.okf_total]),
-                                                 tokens16=layout == "packed16")
+                                                 tokens16=layout == "packed16", nobs8=bool(v.meta.get("nobs8")))
                 else:
                     self.hv[w] = E.mss_window_view(v.K, v.H, v.M, v.F, v.O, E.MEM_HOST,
                                                    *self.pin_blob([v.feat_ptr, v.feat_mp, v.feat_cell, v.mp_nobs, v.mp_obs_ptr,
@@ -815,7 +815,7 @@ def main():
             "config": {"workload": f"{args.workload}: {K} KF x {M} MP KITTI-00-shaped windows (msgen-v1 seeds 0..{nwin-1}) in the transport "
                                    "form FlattenWindow emits: valid slots + outside observations only, map points numbered "
                                    + ("in discovery order (mnIndexForSparsification)" if args.order == "discovery" else "as generated (random)")
-                                   + f", {args.layout} layout",
+                                   + f", {args.layout} layout" + (", one-byte nObs table" if any(v.meta.get("nobs8") for v in batch.views.values()) else ""),
                        "windows_per_gpu_per_step": B, "global_windows_per_step": nwin,
                        "N": N, "lambda": msgen.LAMBDA, "grid_lambda": msgen.GRID_LAMBDA,
                        "parallelism": f"window w -> rank w % {world}; one NCCL all-gather of result slots" if world > 1 else "single GPU",

@@ -121,7 +121,8 @@ typedef struct mss_window_view {
     const uint32_t* obs_pairs; /* [O]   observations of the window's map points by OUTSIDE keyframes only, in any order:
                                         (map-point table index << 12) | j, j = 0..H-1 the outside keyframe (KF-table index K + j) */
     int32_t result_memory;     /* mss_result_memory of keep_bits / kf_cov / kf_slack of this window's mss_result */
-    int32_t reserved_;         /* 0 */
+    int32_t nobs8;             /* packed layouts: != 0 -> mp_nobs16 points to a uint8_t array [M] instead (valid when Observations() <= 255
+                                  for every map point of the window: one byte less per map point on the wire) */
 } mss_window_view;
 
 /* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view unless the view's

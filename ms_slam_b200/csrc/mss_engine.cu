@@ -199,7 +199,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             const bool pk = v.layout != MSS_LAYOUT_SOA;
             stage_bytes = align_up(stage_bytes, 128);     // a window's staging region starts on its own cache line (see `stage`)
             stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up(slots_bytes(v), 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
-                           align_up((size_t)v.M * (pk ? 2 : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
+                           align_up((size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
                            align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16);
         }
     }
@@ -299,12 +299,13 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         const bool pk = v.layout != MSS_LAYOUT_SOA;
         d.packed = packed_code(v);
         d.n_max_floor = v.n_max_floor;
+        d.nobs8 = (pk && v.nobs8) ? 1 : 0;
         if (v.memory == MSS_MEM_HOST) {
             soff = align_up(soff, 128);
             d.feat_ptr = (const int*)stage(v.feat_ptr, (size_t)(v.K + 1) * 4);
             d.feat_mp = (const int*)stage(slots_ptr(v), slots_bytes(v));
             d.feat_cell = pk ? nullptr : (const uint16_t*)stage(v.feat_cell, (size_t)v.F * 2);
-            d.mp_nobs = (const int*)stage(pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
+            d.mp_nobs = (const int*)stage(pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4));
             d.mp_obs_ptr = pk ? nullptr : (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
             d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
             d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
@@ -374,7 +375,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             const void* src[7] = {v.feat_ptr, slots_ptr(v), pk ? nullptr : (const void*)v.feat_cell,
                                   pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
                                   pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
-            const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+            const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4),
                                    pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
             const uint8_t* base = static_cast<const uint8_t*>(src[0]);
             size_t off = 0, end = 0;
@@ -389,7 +390,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
         put(d.feat_mp, slots_ptr(v), slots_bytes(v));
         if (!pk) put(d.feat_cell, v.feat_cell, (size_t)v.F * 2);
-        put(d.mp_nobs, pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? 2 : 4));
+        put(d.mp_nobs, pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, (size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4));
         if (!pk) put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
         put(d.mp_obs_kf, pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
         put(d.okf_total, v.okf_total, (size_t)v.H * 4);
@@ -768,11 +769,12 @@ int mss_components(mss_handle* h, const mss_window_view* view, int32_t* row_labe
     WinDesc d;
     memset(&d, 0, sizeof(d));
     d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O; d.packed = packed_code(v);
+    d.nobs8 = (pk && v.nobs8) ? 1 : 0;
     if (host) {
         const void* src[7] = {v.feat_ptr, slots_ptr(v), pk ? nullptr : (const void*)v.feat_cell,
                               pk ? (const void*)v.mp_nobs16 : (const void*)v.mp_nobs, pk ? nullptr : (const void*)v.mp_obs_ptr,
                               pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, v.okf_total};
-        const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? 2 : 4),
+        const size_t len[7] = {(size_t)(v.K + 1) * 4, slots_bytes(v), pk ? 0 : (size_t)v.F * 2, (size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4),
                                pk ? 0 : (size_t)(v.M + 1) * 4, (size_t)v.O * 4, (size_t)v.H * 4};
         size_t total = 0;
         for (int a = 0; a < 7; ++a) total += align_up(len[a], 16);

@@ -88,7 +88,7 @@ struct WinDesc {
                      // the outside observations as u32 pairs (map point << 12 | outside keyframe), mp_obs_ptr is unused
                      // 2 = MSS_LAYOUT_PACKED16: as 1, but feat_mp holds u16 tokens (delta of the map-point index << 12 | cell)
     int n_max_floor; // nMax is at least this (a component of a larger window keeps the window-wide nMax)
-    int pad_[1];
+    int nobs8;       // packed layouts: mp_nobs is a u8 array (mss_window_view::nobs8)
 };
 
 // per-phase counters; three copies rotate so that a copy is zeroed two phases before it is used again
@@ -378,7 +378,8 @@ __device__ __forceinline__ int outside_need(int cnt, int total, int N) {
 // View accessors: the SoA layout carries i32 / u16 arrays, the packed transport layout u32 slots and u16 tables
 // (include/mss.h, mss_layout); the branch is uniform per window.
 __device__ __forceinline__ int ld_nobs(const WinDesc& D, int mp) {
-    return D.packed ? (int)ldv(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp) : ldv(D.mp_nobs + mp);
+    if (!D.packed) return ldv(D.mp_nobs + mp);
+    return D.nobs8 ? (int)ldv(reinterpret_cast<const uint8_t*>(D.mp_nobs) + mp) : (int)ldv(reinterpret_cast<const uint16_t*>(D.mp_nobs) + mp);
 }
 __device__ __forceinline__ int ld_obs_kf(const WinDesc& D, int o) { return ldv(D.mp_obs_kf + o); }      // SoA layout only
 // MSS_LAYOUT_PACKED16: the slots of a keyframe, sorted by map-point index, as 16-bit tokens.  d = t >> 12, low = t & 0xFFF:

@@ -41,16 +41,17 @@ class mss_window_view(C.Structure):
                 ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
                 ("layout", C.c_int32), ("n_max_floor", C.c_int32),
                 ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("slots16", C.c_void_p), ("obs_pairs", C.c_void_p),
-                ("result_memory", C.c_int32), ("reserved_", C.c_int32)]
+                ("result_memory", C.c_int32), ("nobs8", C.c_int32)]
 
 
-def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total, n_max_floor=0, tokens16=False) -> "mss_window_view":
-    """MSS_LAYOUT_PACKED (u32 slots) or MSS_LAYOUT_PACKED16 (u16 tokens) view from raw addresses"""
+def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total, n_max_floor=0, tokens16=False,
+                  nobs8=False) -> "mss_window_view":
+    """MSS_LAYOUT_PACKED (u32 slots) or MSS_LAYOUT_PACKED16 (u16 tokens) view from raw addresses; nobs8: the nObs table holds bytes"""
     if tokens16:
         return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, None, None, okf_total,
-                               LAYOUT_PACKED16, n_max_floor, None, mp_nobs16, slots, obs_pairs)
+                               LAYOUT_PACKED16, n_max_floor, None, mp_nobs16, slots, obs_pairs, 0, 1 if nobs8 else 0)
     return mss_window_view(K, H, M, F, O, memory, feat_ptr, None, None, None, None, None, okf_total,
-                           LAYOUT_PACKED, n_max_floor, slots, mp_nobs16, None, obs_pairs)
+                           LAYOUT_PACKED, n_max_floor, slots, mp_nobs16, None, obs_pairs, 0, 1 if nobs8 else 0)
 
 
 class mss_result(C.Structure):
@@ -191,6 +192,7 @@ class DeviceView:
         self.K, self.H, self.M, self.F, self.O = view.K, view.H, view.M, view.F, view.O
         self.n_max_floor = int(getattr(view, "n_max_floor", 0))
         self.tokens16 = bool(self.packed and view.meta.get("tokens16"))
+        self.nobs8 = bool(self.packed and view.meta.get("nobs8"))
         self.ptrs = {}
         lib, h = engine.lib, engine.handle
         for name in self._ARR:
@@ -209,7 +211,7 @@ class DeviceView:
     def c_view(self) -> mss_window_view:
         if self.packed:
             return packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
-                                 n_max_floor=self.n_max_floor, tokens16=self.tokens16)
+                                 n_max_floor=self.n_max_floor, tokens16=self.tokens16, nobs8=self.nobs8)
         return mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
                                LAYOUT_SOA, self.n_max_floor)
 
@@ -311,7 +313,7 @@ class Engine:
         if isinstance(v, PackedView):
             return packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
                                  v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data,
-                                 n_max_floor=v.n_max_floor, tokens16=bool(v.meta.get("tokens16")))
+                                 n_max_floor=v.n_max_floor, tokens16=bool(v.meta.get("tokens16")), nobs8=bool(v.meta.get("nobs8")))
         return mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
                                v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
                                v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data, LAYOUT_SOA, v.n_max_floor)

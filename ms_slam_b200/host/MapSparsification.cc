@@ -106,7 +106,9 @@ void WindowSnapshot::Pack() {
     packed = false;
     const size_t M = mp_nobs.size(), F = feat_mp.size(), O = mp_obs_kf.size();
     if (M > (1u << 20) || H > 4095) return;
-    for (int32_t n : mp_nobs) if (n < 0 || n > 65535) return;
+    int32_t nobs_max = 0;
+    for (int32_t n : mp_nobs) { if (n < 0 || n > 65535) return; nobs_max = std::max(nobs_max, n); }
+    nobs8 = nobs_max <= 255;                   // one byte per map point on the wire whenever Observations() fits
     auto up = [](size_t x) { return (x + 15) / 16 * 16; };
     std::vector<uint32_t> slots(F);
     for (size_t i = 0; i < F; ++i) {
@@ -134,7 +136,7 @@ void WindowSnapshot::Pack() {
     off_nobs = off_slots + up(n_tokens * 2);
     n_pairs = 0;
     for (size_t o = 0; o < O; ++o) n_pairs += mp_obs_kf[o] >= K ? 1 : 0;       // FlattenWindow emits outside observations only
-    off_pairs = off_nobs + up(M * 2);
+    off_pairs = off_nobs + up(M * (nobs8 ? 1 : 2));
     off_okf = off_pairs + up(n_pairs * 4);
     const size_t total = off_okf + up((size_t)H * 4);
     if (!blob) blob = std::make_shared<Blob>();
@@ -158,8 +160,13 @@ void WindowSnapshot::Pack() {
             }
         }
     });
-    uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
-    for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
+    if (nobs8) {
+        uint8_t* nobs = blob->p + off_nobs;
+        for (size_t p = 0; p < M; ++p) nobs[p] = (uint8_t)mp_nobs[p];
+    } else {
+        uint16_t* nobs = reinterpret_cast<uint16_t*>(blob->p + off_nobs);
+        for (size_t p = 0; p < M; ++p) nobs[p] = (uint16_t)mp_nobs[p];
+    }
     uint32_t* pairs = reinterpret_cast<uint32_t*>(blob->p + off_pairs);
     size_t np = 0;
     for (size_t p = 0; p < M; ++p)
@@ -234,6 +241,7 @@ mss_window_view WindowSnapshot::View() const {
         v.feat_ptr = reinterpret_cast<const int32_t*>(blob->p);
         v.slots16 = reinterpret_cast<const uint16_t*>(blob->p + off_slots);
         v.mp_nobs16 = reinterpret_cast<const uint16_t*>(blob->p + off_nobs);
+        v.nobs8 = nobs8 ? 1 : 0;
         v.obs_pairs = reinterpret_cast<const uint32_t*>(blob->p + off_pairs);
         v.okf_total = reinterpret_cast<const int32_t*>(blob->p + off_okf);
         return v;

@@ -50,6 +50,7 @@ struct WindowSnapshot {
     std::shared_ptr<Blob> blob;
     size_t off_slots = 0, off_nobs = 0, off_pairs = 0, off_okf = 0, n_pairs = 0, n_tokens = 0;
     bool packed = false;
+    bool nobs8 = false;                 // the blob carries Observations() as one byte per map point (all <= 255)
     int n_max_floor = 0;       // window-wide nMax carried by a component of a larger window (mss.h)
     std::vector<int32_t> part_mp;   // component only: index of each of its map points in the parent snapshot
     void Pack();

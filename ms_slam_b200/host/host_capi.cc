@@ -149,9 +149,11 @@ void msh_snapshot_packed_copy(void* h, int which, int32_t* tok_ptr, uint16_t* to
     if (v.layout != MSS_LAYOUT_PACKED16) return;
     memcpy(tok_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
     memcpy(tokens, v.slots16, (size_t)v.F * 2);
-    memcpy(nobs16, v.mp_nobs16, (size_t)v.M * 2);
+    if (v.nobs8) { const uint8_t* b = reinterpret_cast<const uint8_t*>(v.mp_nobs16); for (int p = 0; p < v.M; ++p) nobs16[p] = b[p]; }   // widened
+    else memcpy(nobs16, v.mp_nobs16, (size_t)v.M * 2);
     memcpy(pairs, v.obs_pairs, (size_t)v.O * 4);
 }
+int msh_snapshot_nobs8(void* h, int which) { return snap(static_cast<World*>(h), which).View().nobs8; }
 
 // The calls System makes at start-up (src/System.cc:160): run the sparsifier on its own thread.
 int msh_start(void* h) {

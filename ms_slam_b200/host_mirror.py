@@ -133,6 +133,7 @@ class World:
         out = dict(tok_ptr=np.zeros(K + 1, np.int32), tokens=np.zeros(int(sz[0]), np.uint16), nobs16=np.zeros(M, np.uint16),
                    pairs=np.zeros(int(sz[1]), np.uint32), blob_bytes=int(sz[3]))
         self.lib.msh_snapshot_packed_copy(self.h, which, _p(out["tok_ptr"]), _p(out["tokens"]), _p(out["nobs16"]), _p(out["pairs"]))
+        out["nobs8"] = bool(self.lib.msh_snapshot_nobs8(self.h, which))       # the blob carries one byte per map point
         return out
 
     # the calls the rest of the SLAM system makes

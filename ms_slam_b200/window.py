@@ -248,7 +248,7 @@ class PackedView:
     M: int
     feat_ptr: np.ndarray      # int32 [K+1]
     slots: np.ndarray         # uint32 [F] (MSS_LAYOUT_PACKED) or uint16 tokens [F] (MSS_LAYOUT_PACKED16, see pack_view)
-    mp_nobs16: np.ndarray     # uint16 [M]
+    mp_nobs16: np.ndarray     # uint16 [M]; uint8 [M] when meta["nobs8"] (mss_window_view::nobs8: every Observations() <= 255)
     obs_pairs: np.ndarray     # uint32 [O] (map point << 12) | outside keyframe j (KF-table index K + j)
     okf_total: np.ndarray     # int32 [H]
     meta: dict = field(default_factory=dict)
@@ -292,11 +292,12 @@ def _tokens16(slots_sorted, feat_ptr):
     return tok, tptr
 
 
-def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False) -> PackedView:
+def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False, nobs8=None) -> PackedView:
     """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges.
     sort_slots: order the slots of every keyframe by map-point index (the order of the slots inside a keyframe carries no
     meaning for the model; sorted, the 32 entries a warp handles touch neighbouring map points, which turns the state
-    gathers of the row phases into nearly coalesced accesses).  FlattenWindow emits this order."""
+    gathers of the row phases into nearly coalesced accesses).  FlattenWindow emits this order.
+    nobs8: Observations() as one byte per map point; None = what FlattenWindow does: with tokens16 whenever every value fits."""
     if v.M > (1 << 20) or v.H > 4095:
         raise ValueError("window too large for the packed layout")
     if v.M and int(v.mp_nobs.max()) > 65535:
@@ -310,6 +311,11 @@ def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False) -
     owner = np.repeat(np.arange(v.M, dtype=np.int64), np.diff(v.mp_obs_ptr))
     outside = v.mp_obs_kf >= v.K                     # observations by window keyframes are not part of the pair list
     pairs = ((owner[outside] << 12) | (v.mp_obs_kf[outside].astype(np.int64) - v.K)).astype(np.uint32)
+    if nobs8 is None:
+        nobs8 = bool(tokens16 and (v.M == 0 or int(v.mp_nobs.max()) <= 255))
+    if nobs8 and v.M and int(v.mp_nobs.max()) > 255:
+        raise ValueError("Observations() above 255: nobs8 does not apply")
+    nobs = np.ascontiguousarray(v.mp_nobs.astype(np.uint8 if nobs8 else np.uint16))
     if tokens16:
         # MSS_LAYOUT_PACKED16: valid slots only, sorted by map point inside every keyframe, delta-coded as u16 tokens
         kf = np.repeat(np.arange(v.K, dtype=np.int64), np.diff(v.feat_ptr))
@@ -318,11 +324,11 @@ def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False) -
         ptr[1:] = np.cumsum(np.bincount(kf[ok], minlength=v.K))
         tok, tptr = _tokens16(slots[ok], ptr)
         return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=np.ascontiguousarray(tptr, dtype=np.int32), slots=np.ascontiguousarray(tok),
-                          mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
-                          okf_total=v.okf_total, meta=dict(v.meta, packed=True, tokens16=True), n_max_floor=v.n_max_floor)
+                          mp_nobs16=nobs, obs_pairs=np.ascontiguousarray(pairs),
+                          okf_total=v.okf_total, meta=dict(v.meta, packed=True, tokens16=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor)
     return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
-                      mp_nobs16=np.ascontiguousarray(v.mp_nobs.astype(np.uint16)), obs_pairs=np.ascontiguousarray(pairs),
-                      okf_total=v.okf_total, meta=dict(v.meta, packed=True), n_max_floor=v.n_max_floor)
+                      mp_nobs16=nobs, obs_pairs=np.ascontiguousarray(pairs),
+                      okf_total=v.okf_total, meta=dict(v.meta, packed=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor)
 
 
 def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:

@@ -173,7 +173,11 @@ def test_packed_layout_same_result(eng, name, seed):
     view, N = msgen.make_config(name, seed)
     eng.set_params(N, LAM, GLAM)
     soa = eng.solve(view)
-    for pv in (pack_view(view), pack_view(view.compact()), pack_view(view.compact(), sort_slots=True), pack_view(view, tokens16=True)):
+    # (tokens16 picks the one-byte nObs table whenever every Observations() fits: both widths of the table are covered)
+    forms = (pack_view(view), pack_view(view.compact()), pack_view(view.compact(), sort_slots=True), pack_view(view, tokens16=True),
+             pack_view(view, tokens16=True, nobs8=False), pack_view(view.compact(), nobs8=True))
+    assert forms[3].meta["nobs8"] and forms[3].mp_nobs16.dtype == np.uint8 and forms[4].mp_nobs16.dtype == np.uint16
+    for pv in forms:
         pk = eng.solve(pv)
         assert np.array_equal(soa.keep_bits, pk.keep_bits) and np.array_equal(soa.kf_cov, pk.kf_cov)
         assert (soa.objective, soa.rounds, soa.n_vars, soa.n_cells, soa.nnz, soa.n_max) == \

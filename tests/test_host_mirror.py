@@ -105,6 +105,8 @@ def test_flatten_packed_blob_matches_the_python_packer(hm, name, seed, over):
         assert blob is not None
         ref = pack_view(flat, tokens16=True)
         assert np.array_equal(blob["tok_ptr"], ref.feat_ptr) and np.array_equal(blob["tokens"], ref.slots)
+        assert blob["nobs8"] == bool(ref.meta["nobs8"]) == (int(flat.mp_nobs.max()) <= 255)      # one byte per map point when it fits
+        assert ref.mp_nobs16.dtype == (np.uint8 if blob["nobs8"] else np.uint16)
         assert np.array_equal(blob["nobs16"], ref.mp_nobs16) and np.array_equal(np.sort(blob["pairs"]), np.sort(ref.obs_pairs))
         kf = np.repeat(np.arange(flat.K), np.diff(flat.feat_ptr))
         want = sorted(zip(kf.tolist(), flat.feat_mp.tolist(), flat.feat_cell.tolist()))
