@@ -660,8 +660,21 @@ static int compact_impl(mss_handle* h, mss_mirror* m, int32_t nkf, const mss_kf_
     MSS_CUDA(h, cudaMemcpyAsync(up.p, hp.data(), (size_t)nkf * sizeof(mssc::KfPayload), cudaMemcpyHostToDevice, h->stream));
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));                  // hp is pageable
     MSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    mssc::compact_keyframes_kernel<<<std::min(nkf, h->sm_count * 8), mssc::kT, 0, h->stream>>>(
-        reinterpret_cast<const mssc::KfPayload*>(up.p), nkf, m ? m->slot_mp.p : nullptr, m ? m->S : 0, reinterpret_cast<int*>(up.p + off_out));
+    // TMA-staged variant when every array (and the mirror's slot rows) is 16-byte aligned; MSS_COMPACT_TMA=0 forces the register variant
+    bool tma = !(getenv("MSS_COMPACT_TMA") && atoi(getenv("MSS_COMPACT_TMA")) == 0) && (!m || m->S % 4 == 0);
+    for (int i = 0; i < nkf && tma; ++i) {
+        const mssc::KfPayload& k = hp[i];
+        tma = ((reinterpret_cast<uintptr_t>(k.desc) | reinterpret_cast<uintptr_t>(k.keys) | reinterpret_cast<uintptr_t>(k.uright) |
+                reinterpret_cast<uintptr_t>(k.depth) | reinterpret_cast<uintptr_t>(k.keep)) & 15u) == 0;
+    }
+    if (tma) {
+        static_assert(sizeof(mssc::TmaSmem) <= 48 * 1024, "the TMA variant stays within the default dynamic shared memory limit");
+        mssc::compact_keyframes_tma_kernel<<<std::min(nkf, h->sm_count * 8), mssc::kT, sizeof(mssc::TmaSmem), h->stream>>>(
+            reinterpret_cast<const mssc::KfPayload*>(up.p), nkf, m ? m->slot_mp.p : nullptr, m ? m->S : 0, reinterpret_cast<int*>(up.p + off_out));
+    } else {
+        mssc::compact_keyframes_kernel<<<std::min(nkf, h->sm_count * 8), mssc::kT, 0, h->stream>>>(
+            reinterpret_cast<const mssc::KfPayload*>(up.p), nkf, m ? m->slot_mp.p : nullptr, m ? m->S : 0, reinterpret_cast<int*>(up.p + off_out));
+    }
     MSS_CUDA(h, cudaGetLastError());
     h->stats.kernel_launches += 1;
     if (m) {                                                        // the mirror's own rows follow (EraseBadDescriptor semantics)

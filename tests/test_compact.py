@@ -37,9 +37,11 @@ def random_payload(rng, n):
 
 
 @pytest.mark.gpu
-def test_compaction_matches_the_reference_semantics(eng):
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_compaction_matches_the_reference_semantics(eng, tma, monkeypatch):
     """ragged keyframes (0, 1, 255, 256, 257, 2000, 5000 rows), all / none / random survivors, missing arrays"""
     from ms_slam_b200.mirror import KeyframePayload, compact_keyframes
+    monkeypatch.setenv("MSS_COMPACT_TMA", tma)           # TMA-staged chunks (default) / register-staged kernel
     rng = np.random.default_rng(0)
     cases = []
     for n, frac in [(0, 0.5), (1, 1.0), (1, 0.0), (255, 0.3), (256, 0.5), (257, 0.9), (2000, 0.15), (2000, 1.0), (2000, 0.0), (5000, 0.5), (777, 0.5)]:
