@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define MSS_VERSION 200            /* 0.2.0: result_memory, persistent device mirror (mss_mirror_*), keyframe compaction,
+#define MSS_VERSION 210            /* 0.2.1: mp_tie (tie-breaks on the caller's ranks), wire flags (one-byte nObs table), dual bound, BoW;
+                                      0.2.0: result_memory, persistent device mirror (mss_mirror_*), keyframe compaction,
                                       single-process multi-device handles; 0.1.3: packed transport layouts, components */
 
 #define MSS_GRID_COLS 64           /* FRAME_GRID_COLS, /root/reference/include/Frame.h:45 */
@@ -123,6 +124,11 @@ typedef struct mss_window_view {
     int32_t result_memory;     /* mss_result_memory of keep_bits / kf_cov / kf_slack of this window's mss_result */
     int32_t nobs8;             /* packed layouts: != 0 -> mp_nobs16 points to a uint8_t array [M] instead (valid when Observations() <= 255
                                   for every map point of the window: one byte less per map point on the wire) */
+    const uint32_t* mp_tie;    /* [M] optional (NULL = off): tie-break rank of every map point, lower wins.  Wherever the selection has to
+                                  choose between candidates of equal gain it prefers the lower TABLE INDEX by default, so the result
+                                  depends on how the caller numbered the table; with mp_tie (e.g. the rank of MapPoint::mnId, SURVEY 8b
+                                  "ties by (cost, MP gid)") it is the same for every numbering of the same window.  Same memory kind as
+                                  the other arrays. */
 } mss_window_view;
 
 /* Result of one window.  keep_bits / kf_cov / kf_slack are caller-allocated (same mss_memory as the view unless the view's

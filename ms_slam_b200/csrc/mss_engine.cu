@@ -200,7 +200,8 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             stage_bytes = align_up(stage_bytes, 128);     // a window's staging region starts on its own cache line (see `stage`)
             stage_bytes += align_up((size_t)(v.K + 1) * 4, 16) + align_up(slots_bytes(v), 16) + (pk ? 0 : align_up((size_t)v.F * 2, 16)) +
                            align_up((size_t)v.M * (pk ? (v.nobs8 ? 1 : 2) : 4), 16) + (pk ? 0 : align_up((size_t)(v.M + 1) * 4, 16)) +
-                           align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16);
+                           align_up((size_t)v.O * 4, 16) + align_up((size_t)v.H * 4, 16) +
+                           (v.mp_tie ? align_up((size_t)v.M * 4, 16) : 0);
         }
     }
     if (Mpad > 0x7FFFFF00LL || Ktot + Htot > 0x7FFFFF00LL || Ftot + Otot > 0x7FFFFF00LL) { h->err = "batch too large for 32-bit indices"; return MSS_E_BADARG; }
@@ -309,6 +310,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             d.mp_obs_ptr = pk ? nullptr : (const int*)stage(v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
             d.mp_obs_kf = (const int*)stage(pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
             d.okf_total = (const int*)stage(v.okf_total, (size_t)v.H * 4);
+            d.mp_tie = v.mp_tie ? (const unsigned*)stage(v.mp_tie, (size_t)v.M * 4) : nullptr;      // (behind the blob: its own copy)
         } else if (pk) {
             d.feat_ptr = v.feat_ptr; d.feat_mp = (const int*)slots_ptr(v); d.feat_cell = nullptr; d.mp_nobs = (const int*)v.mp_nobs16;
             d.mp_obs_ptr = nullptr; d.mp_obs_kf = (const int*)v.obs_pairs; d.okf_total = v.okf_total;
@@ -316,6 +318,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             d.feat_ptr = v.feat_ptr; d.feat_mp = v.feat_mp; d.feat_cell = v.feat_cell; d.mp_nobs = v.mp_nobs;
             d.mp_obs_ptr = v.mp_obs_ptr; d.mp_obs_kf = v.mp_obs_kf; d.okf_total = v.okf_total;
         }
+        if (v.memory != MSS_MEM_HOST) d.mp_tie = v.mp_tie;
         d.K = v.K; d.H = v.H; d.M = v.M; d.F = v.F; d.O = v.O;
         d.row_base = row_base; d.slot_base = slot_base; d.obs_base = obs_base; d.var_base = var_base;
         d.out_off = out_off[local[i]];
@@ -385,7 +388,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
                 if (len[a]) { if (static_cast<const uint8_t*>(src[a]) != base + off) blob = false; end = off + len[a]; }
                 off += align_up(len[a], 16);
             }
-            if (blob) { put(d.feat_ptr, base, end); return; }
+            if (blob) { put(d.feat_ptr, base, end); if (v.mp_tie) put(d.mp_tie, v.mp_tie, (size_t)v.M * 4); return; }
         }
         put(d.feat_ptr, v.feat_ptr, (size_t)(v.K + 1) * 4);
         put(d.feat_mp, slots_ptr(v), slots_bytes(v));
@@ -394,6 +397,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
         if (!pk) put(d.mp_obs_ptr, v.mp_obs_ptr, (size_t)(v.M + 1) * 4);
         put(d.mp_obs_kf, pk ? (const void*)v.obs_pairs : (const void*)v.mp_obs_kf, (size_t)v.O * 4);
         put(d.okf_total, v.okf_total, (size_t)v.H * 4);
+        if (v.mp_tie) put(d.mp_tie, v.mp_tie, (size_t)v.M * 4);
     };
     unsigned* d_ready = h->sync.p + ready_off;
     if (!gated) for (int q = 0; q < nl; ++q) copy_window(plan.order[q]);

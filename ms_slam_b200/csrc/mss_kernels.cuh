@@ -78,6 +78,7 @@ struct WinDesc {
     const int* mp_obs_ptr;
     const int* mp_obs_kf;
     const int* okf_total;
+    const unsigned* mp_tie;   // optional tie-break rank per map point (mss_window_view::mp_tie); nullptr = the table index
     int K, H, M, F, O;
     int row_base;    // first row of this window in the per-row arrays: K keyframe rows, then H outside rows
     int slot_base;   // first entry of this window's keyframe rows in ent[] / live[]
@@ -206,6 +207,9 @@ __device__ __forceinline__ unsigned f32_orderable(float g) {
 __device__ __forceinline__ unsigned long long make_key(float g, unsigned local_idx) {
     return ((unsigned long long)f32_orderable(g) << 32) | (unsigned long long)(0xFFFFFFFFu - local_idx);
 }
+
+// tie-break key of map point v of window D: the caller's rank, or the table index
+__device__ __forceinline__ unsigned tie_of(const WinDesc& D, unsigned v) { return D.mp_tie ? ldv(D.mp_tie + v) : v; }
 
 struct BlockScratch {
     int red[3][kWarps];
@@ -1166,7 +1170,7 @@ __device__ __forceinline__ void row_greedy_regs(const Params& P, const WinDesc& 
 #pragma unroll
     for (int b = 0; b < EPT; ++b) {
         const bool fr = X.e[b] != kEntInvalid && X.s[b] == ST_FREE;
-        key[b] = fr ? make_key(gain_w[X.e[b] >> kCellBits], X.e[b] >> kCellBits) : 0ull;
+        key[b] = fr ? make_key(gain_w[X.e[b] >> kCellBits], tie_of(D, X.e[b] >> kCellBits)) : 0ull;
         if (fr) { ++nfree; if ((X.e[b] & kCellCov) != kCellCov) keytab[X.e[b] & kCellCov] = 0ull; }
     }
     __syncthreads();
@@ -1215,14 +1219,14 @@ __device__ void row_greedy(const Params& P, const WinDesc& D, int R, int n, unsi
             const unsigned v = e >> kCellBits;
             if (st_w[v] != ST_FREE) continue;
             ++nfree;
-            if ((e & kCellCov) != kCellCov) atomicMax(&keytab[e & kCellCov], make_key(gain_w[v], v));
+            if ((e & kCellCov) != kCellCov) atomicMax(&keytab[e & kCellCov], make_key(gain_w[v], tie_of(D, v)));
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += kThreads) {
             const uint32_t e = src[i];
             const unsigned v = e >> kCellBits;
             if (st_w[v] != ST_FREE || (e & kCellCov) == kCellCov) continue;
-            if (keytab[e & kCellCov] != make_key(gain_w[v], v)) atomicOr(&acc_w[v], FLAG_BLOCKED);
+            if (keytab[e & kCellCov] != make_key(gain_w[v], tie_of(D, v))) atomicOr(&acc_w[v], FLAG_BLOCKED);
         }
         if (d > 0) {
             int z0 = 0, z1 = 0;
@@ -1231,13 +1235,13 @@ __device__ void row_greedy(const Params& P, const WinDesc& D, int R, int n, unsi
                 const unsigned long long thr = block_kth_largest(S, d, [&](auto sink) {
                     for (int i = threadIdx.x; i < n; i += kThreads) {
                         const unsigned v = src[i] >> kCellBits;
-                        if (st_w[v] == ST_FREE) sink(make_key(gain_w[v], v));
+                        if (st_w[v] == ST_FREE) sink(make_key(gain_w[v], tie_of(D, v)));
                     }
                 });
                 for (int i = threadIdx.x; i < n; i += kThreads) {
                     const unsigned v = src[i] >> kCellBits;
                     if (st_w[v] != ST_FREE) continue;
-                    atomicOr(&acc_w[v], make_key(gain_w[v], v) > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
+                    atomicOr(&acc_w[v], make_key(gain_w[v], tie_of(D, v)) > thr ? FLAG_NOMINATED : FLAG_BLOCKED);
                 }
             } else {
                 for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -1300,7 +1304,7 @@ __device__ __forceinline__ void warp_row_greedy(const Params& P, const WinDesc& 
     const unsigned v = e >> kCellBits;
     const int d = max(0, P.row_need[R] - P.row_cov[R]);
     const bool fr = valid && P.st[D.var_base + v] == ST_FREE;
-    const unsigned long long key = fr ? make_key(P.gain[D.var_base + v], v) : 0ull;
+    const unsigned long long key = fr ? make_key(P.gain[D.var_base + v], tie_of(D, v)) : 0ull;
     const unsigned cell = e & kCellCov;
     const bool unc = fr && cell != kCellCov;
     const unsigned mFR = __ballot_sync(0xFFFFFFFFu, fr);
@@ -1631,7 +1635,7 @@ __device__ __forceinline__ void row_d2_regs(const Params& P, const WinDesc& D, i
         key[b] = 0ull;
         if (X.e[b] != kEntInvalid && X.s[b] == ST_CAND) {
             const unsigned v = X.e[b] >> kCellBits, cell = X.e[b] & kCellCov;
-            key[b] = make_key(gain_w[v], v);
+            key[b] = make_key(gain_w[v], tie_of(D, v));
             if (cell != kCellCov && tab[cell] >= 2u) atomicMax(&keytab[cell], key[b]);
         }
     }
@@ -1689,27 +1693,27 @@ __device__ void row_d2(const Params& P, const WinDesc& D, int R, unsigned* tab, 
         const uint32_t e = src[i];
         const unsigned v = e >> kCellBits, cell = e & kCellCov;
         if (st_w[v] != ST_CAND || cell == kCellCov || tab[cell] < 2u) continue;
-        atomicMax(&keytab[cell], make_key(gain_w[v], v));
+        atomicMax(&keytab[cell], make_key(gain_w[v], tie_of(D, v)));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const uint32_t e = src[i];
         const unsigned v = e >> kCellBits, cell = e & kCellCov;
         if (st_w[v] != ST_CAND || cell == kCellCov || tab[cell] < 2u) continue;
-        if (make_key(gain_w[v], v) != keytab[cell]) atomicOr(&acc_w[v], FLAG_BLOCKED);
+        if (make_key(gain_w[v], tie_of(D, v)) != keytab[cell]) atomicOr(&acc_w[v], FLAG_BLOCKED);
     }
     const int u = cov - need;
     if (u > 0 && ncand > u) {
         const unsigned long long thr = block_kth_largest(S, u, [&](auto sink) {
             for (int i = threadIdx.x; i < n; i += kThreads) {
                 const unsigned v = src[i] >> kCellBits;
-                if (st_w[v] == ST_CAND) sink(make_key(gain_w[v], v));
+                if (st_w[v] == ST_CAND) sink(make_key(gain_w[v], tie_of(D, v)));
             }
         });
         for (int i = threadIdx.x; i < n; i += kThreads) {
             const unsigned v = src[i] >> kCellBits;
             if (st_w[v] != ST_CAND) continue;
-            if (!(make_key(gain_w[v], v) > thr)) atomicOr(&acc_w[v], FLAG_BLOCKED);
+            if (!(make_key(gain_w[v], tie_of(D, v)) > thr)) atomicOr(&acc_w[v], FLAG_BLOCKED);
         }
     }
 }
@@ -1866,7 +1870,8 @@ struct TailSmem {
     uint32_t acc_hi[kTailVars];            // [ubr:16 | lbr:16]
     float gain[kTailVars];
     int cost[kTailVars];
-    uint32_t mp[kTailVars];               // original map-point index (tie-break, write-back)
+    uint32_t mp[kTailVars];               // original map-point index (write-back)
+    uint32_t tie[kTailVars];              // tie-break key (mp_tie rank or the index)
     int rdef[kTailRows];                  // need - coverage of the row (may be negative)
     unsigned short rptr[kTailRows];
     unsigned short rn[kTailRows];
@@ -2020,7 +2025,7 @@ __device__ void tail_row_greedy(TailSmem& T, int lid) {
                 k[b] = 0ull;
                 if (i < n) {
                     const unsigned v = lst[i] >> kCellBits;
-                    if (T.st[v] == ST_FREE) k[b] = make_key(T.gain[v], T.mp[v]);
+                    if (T.st[v] == ST_FREE) k[b] = make_key(T.gain[v], T.tie[v]);
                 }
             }
             for (int bit = 63; bit >= 0; --bit) {
@@ -2037,7 +2042,7 @@ __device__ void tail_row_greedy(TailSmem& T, int lid) {
                 int c = 0;
                 for (int i = lane; i < n; i += 32) {
                     const unsigned v = lst[i] >> kCellBits;
-                    c += (T.st[v] == ST_FREE && make_key(T.gain[v], T.mp[v]) >= cand) ? 1 : 0;
+                    c += (T.st[v] == ST_FREE && make_key(T.gain[v], T.tie[v]) >= cand) ? 1 : 0;
                 }
                 c = __reduce_add_sync(0xFFFFFFFFu, c);
                 if (c > d) thr = cand;
@@ -2049,7 +2054,7 @@ __device__ void tail_row_greedy(TailSmem& T, int lid) {
         const uint32_t ea = (ia < n) ? lst[ia] : kEntInvalid;
         const unsigned va = ea >> kCellBits;
         const bool fra = (ia < n) && T.st[va] == ST_FREE;
-        const unsigned long long keya = fra ? make_key(T.gain[va], T.mp[va]) : 0ull;
+        const unsigned long long keya = fra ? make_key(T.gain[va], T.tie[va]) : 0ull;
         const unsigned cella = ea & kCellCov;
         const bool unca = fra && cella != kCellCov;
         unsigned long long best = 0ull;
@@ -2065,7 +2070,7 @@ __device__ void tail_row_greedy(TailSmem& T, int lid) {
                 const unsigned bmin = __reduce_min_sync(0xFFFFFFFFu, ub ? cellb : 0xFFFFu);
                 const unsigned bmax = __reduce_max_sync(0xFFFFFFFFu, ub ? cellb : 0u);
                 if (bmin > amax || bmax < amin) continue;
-                const unsigned long long keyb = ub ? make_key(T.gain[vb], T.mp[vb]) : 0ull;
+                const unsigned long long keyb = ub ? make_key(T.gain[vb], T.tie[vb]) : 0ull;
                 for (unsigned rem = __ballot_sync(0xFFFFFFFFu, ub && cellb >= amin && cellb <= amax); rem; rem &= rem - 1u) {
                     const int j = __ffs(rem) - 1;
                     const unsigned long long kj = __shfl_sync(0xFFFFFFFFu, keyb, j);
@@ -2093,6 +2098,7 @@ __device__ void tail_solve(const Params& P, const WinDesc& D, WinState& ws, Tail
         const int mp = vprev[i];
         const int g = D.var_base + mp;
         T.mp[i] = (uint32_t)mp;
+        T.tie[i] = tie_of(D, (unsigned)mp);
         T.st[i] = P.st[g];
         T.cost[i] = ws.n_max - ld_nobs(D, mp);
         T.acc_lo[i] = 0u;

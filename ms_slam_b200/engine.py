@@ -41,7 +41,7 @@ class mss_window_view(C.Structure):
                 ("mp_obs_ptr", C.c_void_p), ("mp_obs_kf", C.c_void_p), ("okf_total", C.c_void_p),
                 ("layout", C.c_int32), ("n_max_floor", C.c_int32),
                 ("slots", C.c_void_p), ("mp_nobs16", C.c_void_p), ("slots16", C.c_void_p), ("obs_pairs", C.c_void_p),
-                ("result_memory", C.c_int32), ("nobs8", C.c_int32)]
+                ("result_memory", C.c_int32), ("nobs8", C.c_int32), ("mp_tie", C.c_void_p)]
 
 
 def packed_c_view(K, H, M, F, O, memory, feat_ptr, slots, mp_nobs16, obs_pairs, okf_total, n_max_floor=0, tokens16=False,
@@ -203,17 +203,35 @@ class DeviceView:
             if a.nbytes:
                 engine._check(lib.mss_memcpy_h2d(h, p, a.ctypes.data, a.nbytes))
             self.ptrs[name] = p
+        self.d_tie = None
+        tie = self._tie_of(view)
+        if tie is not None:
+            self.d_tie = lib.mss_device_alloc(h, max(tie.nbytes, 4))
+            engine._check(lib.mss_memcpy_h2d(h, self.d_tie, tie.ctypes.data, tie.nbytes))
         words, rows = (self.M + 31) // 32, self.K + self.H
         self.d_keep = lib.mss_device_alloc(h, max(words * 4, 4))
         self.d_cov = lib.mss_device_alloc(h, max(rows * 4, 4))
         self.d_slack = lib.mss_device_alloc(h, max(rows * 4, 4))
 
+    @staticmethod
+    def _tie_of(view):
+        """uint32 tie-break ranks the view carries, or None"""
+        if isinstance(view, PackedView):
+            return None if view.mp_tie is None else np.ascontiguousarray(view.mp_tie, np.uint32)
+        if view.meta.get("tie_by_gid"):
+            from .window import tie_ranks
+            return tie_ranks(view)
+        return None
+
     def c_view(self) -> mss_window_view:
         if self.packed:
-            return packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
-                                 n_max_floor=self.n_max_floor, tokens16=self.tokens16, nobs8=self.nobs8)
-        return mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
-                               LAYOUT_SOA, self.n_max_floor)
+            cv = packed_c_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
+                               n_max_floor=self.n_max_floor, tokens16=self.tokens16, nobs8=self.nobs8)
+        else:
+            cv = mss_window_view(self.K, self.H, self.M, self.F, self.O, MEM_DEVICE, *[self.ptrs[n] for n in self._ARR],
+                                 LAYOUT_SOA, self.n_max_floor)
+        cv.mp_tie = self.d_tie
+        return cv
 
     def fetch(self):
         """copy the device-resident result arrays back to numpy (not part of any timed region)"""
@@ -231,7 +249,7 @@ class DeviceView:
 
     def free(self):
         lib, h = self.engine.lib, self.engine.handle
-        for p in list(self.ptrs.values()) + [self.d_keep, self.d_cov, self.d_slack]:
+        for p in list(self.ptrs.values()) + [self.d_keep, self.d_cov, self.d_slack] + ([self.d_tie] if self.d_tie else []):
             lib.mss_device_free(h, p)
         self.ptrs = {}
 
@@ -311,12 +329,18 @@ class Engine:
     @staticmethod
     def _host_view(v) -> mss_window_view:
         if isinstance(v, PackedView):
-            return packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
-                                 v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data,
-                                 n_max_floor=v.n_max_floor, tokens16=bool(v.meta.get("tokens16")), nobs8=bool(v.meta.get("nobs8")))
-        return mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
-                               v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
-                               v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data, LAYOUT_SOA, v.n_max_floor)
+            cv = packed_c_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.slots.ctypes.data,
+                               v.mp_nobs16.ctypes.data, v.obs_pairs.ctypes.data, v.okf_total.ctypes.data,
+                               n_max_floor=v.n_max_floor, tokens16=bool(v.meta.get("tokens16")), nobs8=bool(v.meta.get("nobs8")))
+        else:
+            cv = mss_window_view(v.K, v.H, v.M, v.F, v.O, MEM_HOST, v.feat_ptr.ctypes.data, v.feat_mp.ctypes.data,
+                                 v.feat_cell.ctypes.data, v.mp_nobs.ctypes.data, v.mp_obs_ptr.ctypes.data,
+                                 v.mp_obs_kf.ctypes.data, v.okf_total.ctypes.data, LAYOUT_SOA, v.n_max_floor)
+        tie = DeviceView._tie_of(v)
+        if tie is not None:
+            v.meta["_tie_keepalive"] = tie                 # (the array must outlive the call)
+            cv.mp_tie = tie.ctypes.data
+        return cv
 
     def components(self, view):
         """Connected components of a host window view (WindowView or PackedView): (row_label[K+H], mp_label[M], ncomp, n_max)"""

@@ -195,6 +195,7 @@ void SplitSnapshot(const WindowSnapshot& in, const vector<int32_t>& row_label, c
         WindowSnapshot& q = parts[comp_of[c]];
         mp_new[p] = (int32_t)q.mp_nobs.size();
         q.mp_nobs.push_back(in.mp_nobs[p]);
+        if (!in.mp_tie.empty()) q.mp_tie.push_back(in.mp_tie[p]);        // (ranks stay ordered: that is all a tie-break needs)
         q.is_var.push_back(1);
         q.vpMapPoints.push_back(in.vpMapPoints[p]);
         q.part_mp.push_back((int32_t)p);
@@ -244,6 +245,7 @@ mss_window_view WindowSnapshot::View() const {
         v.nobs8 = nobs8 ? 1 : 0;
         v.obs_pairs = reinterpret_cast<const uint32_t*>(blob->p + off_pairs);
         v.okf_total = reinterpret_cast<const int32_t*>(blob->p + off_okf);
+        v.mp_tie = mp_tie.size() == mp_nobs.size() && !mp_tie.empty() ? mp_tie.data() : nullptr;
         return v;
     }
     v.K = K; v.H = H; v.M = (int32_t)mp_nobs.size(); v.F = (int32_t)feat_mp.size(); v.O = (int32_t)mp_obs_kf.size();
@@ -251,6 +253,7 @@ mss_window_view WindowSnapshot::View() const {
     v.feat_ptr = feat_ptr.data(); v.feat_mp = feat_mp.data(); v.feat_cell = feat_cell.data();
     v.mp_nobs = mp_nobs.data(); v.mp_obs_ptr = mp_obs_ptr.data(); v.mp_obs_kf = mp_obs_kf.data();
     v.okf_total = okf_total.data();
+    v.mp_tie = mp_tie.size() == mp_nobs.size() && !mp_tie.empty() ? mp_tie.data() : nullptr;
     return v;
 }
 
@@ -366,6 +369,17 @@ void FlattenWindow(const vector<shared_ptr<KeyFrame>>& vpKFs, long unsigned int 
     });
     out.mp_ids.resize(M);
     for (size_t p = 0; p < M; ++p) out.mp_ids[p] = out.vpMapPoints[p]->mnId;
+    // MSS_TIE_GID=1: ties between equally good candidates break on MapPoint::mnId instead of on the table index,
+    // i.e. independently of the order in which this walk met the points (costs 4 bytes per map point on the wire)
+    out.mp_tie.clear();
+    static const bool tie_gid = std::getenv("MSS_TIE_GID") && std::atoi(std::getenv("MSS_TIE_GID")) != 0;
+    if (tie_gid) {
+        std::vector<uint32_t> order(M);
+        for (size_t p = 0; p < M; ++p) order[p] = (uint32_t)p;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return out.mp_ids[a] < out.mp_ids[b]; });
+        out.mp_tie.resize(M);
+        for (size_t r = 0; r < M; ++r) out.mp_tie[order[r]] = (uint32_t)r;
+    }
     out.okf_ids.resize(H);
     for (int j = 0; j < H; ++j) out.okf_ids[j] = out.vpOutsideKFs[j]->mnId;
     tD = MsSince(t0);

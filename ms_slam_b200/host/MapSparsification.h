@@ -35,6 +35,7 @@ struct WindowSnapshot {
     std::vector<std::shared_ptr<MapPoint>> vpMapPoints;       // table order = mnIndexForSparsification = bit position
     std::vector<std::shared_ptr<KeyFrame>> vpOutsideKFs;      // ordered by KeyFrame::mnId
     std::vector<long unsigned int> mp_ids, okf_ids;           // mnId of the above (stay valid after the objects are released)
+    std::vector<uint32_t> mp_tie;                             // rank of mp_ids (MSS_TIE_GID=1: mss_window_view::mp_tie), else empty
     int K = 0, H = 0;
     double flatten_ms = 0.0;
     // MSS_LAYOUT_PACKED16 transport form of the same arrays in ONE host blob (pinned when a CUDA device is present), laid

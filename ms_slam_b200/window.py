@@ -253,6 +253,7 @@ class PackedView:
     okf_total: np.ndarray     # int32 [H]
     meta: dict = field(default_factory=dict)
     n_max_floor: int = 0
+    mp_tie: np.ndarray = None  # uint32 [M] tie-break rank (mss_window_view::mp_tie), None = ties break on the table index
 
     @property
     def F(self) -> int:
@@ -264,6 +265,14 @@ class PackedView:
 
     def input_bytes(self) -> int:
         return int(self.feat_ptr.nbytes + self.slots.nbytes + self.mp_nobs16.nbytes + self.obs_pairs.nbytes + self.okf_total.nbytes)
+
+
+def tie_ranks(v) -> np.ndarray:
+    """uint32 [M]: rank of every map point's gid (mss_window_view::mp_tie: lower wins a tie) -- the same for every numbering
+    of the same window"""
+    r = np.empty(v.M, np.uint32)
+    r[np.argsort(v.mp_gid, kind="stable")] = np.arange(v.M, dtype=np.uint32)
+    return r
 
 
 def _tokens16(slots_sorted, feat_ptr):
@@ -292,12 +301,13 @@ def _tokens16(slots_sorted, feat_ptr):
     return tok, tptr
 
 
-def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False, nobs8=None) -> PackedView:
+def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False, nobs8=None, tie: bool = False) -> PackedView:
     """WindowView -> PackedView.  Raises ValueError when the window exceeds the packed form's ranges.
     sort_slots: order the slots of every keyframe by map-point index (the order of the slots inside a keyframe carries no
     meaning for the model; sorted, the 32 entries a warp handles touch neighbouring map points, which turns the state
     gathers of the row phases into nearly coalesced accesses).  FlattenWindow emits this order.
-    nobs8: Observations() as one byte per map point; None = what FlattenWindow does: with tokens16 whenever every value fits."""
+    nobs8: Observations() as one byte per map point; None = what FlattenWindow does: with tokens16 whenever every value fits.
+    tie: carry the tie-break ranks of the map points' gids (mp_tie)."""
     if v.M > (1 << 20) or v.H > 4095:
         raise ValueError("window too large for the packed layout")
     if v.M and int(v.mp_nobs.max()) > 65535:
@@ -325,10 +335,12 @@ def pack_view(v: WindowView, sort_slots: bool = False, tokens16: bool = False, n
         tok, tptr = _tokens16(slots[ok], ptr)
         return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=np.ascontiguousarray(tptr, dtype=np.int32), slots=np.ascontiguousarray(tok),
                           mp_nobs16=nobs, obs_pairs=np.ascontiguousarray(pairs),
-                          okf_total=v.okf_total, meta=dict(v.meta, packed=True, tokens16=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor)
+                          okf_total=v.okf_total, meta=dict(v.meta, packed=True, tokens16=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor,
+                          mp_tie=tie_ranks(v) if tie else None)
     return PackedView(K=v.K, H=v.H, M=v.M, feat_ptr=v.feat_ptr, slots=np.ascontiguousarray(slots),
                       mp_nobs16=nobs, obs_pairs=np.ascontiguousarray(pairs),
-                      okf_total=v.okf_total, meta=dict(v.meta, packed=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor)
+                      okf_total=v.okf_total, meta=dict(v.meta, packed=True, nobs8=bool(nobs8)), n_max_floor=v.n_max_floor,
+                      mp_tie=tie_ranks(v) if tie else None)
 
 
 def make_view(K, kf_slots, mp_nobs, outside=None, okf_total=None) -> WindowView:

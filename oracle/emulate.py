@@ -106,6 +106,13 @@ class Emulator:
         self.rounds = 0
         self.greedy_steps = 0
         self.log = []
+        # tie-break key of every variable: the table index, or -- mss_window_view::mp_tie -- the rank of its gid (the selection
+        # is then the same for every numbering of the window)
+        tie = getattr(view, "mp_tie", None)
+        if tie is None and getattr(view, "meta", {}).get("tie_by_gid"):
+            tie = np.empty(M, np.int64)
+            tie[np.argsort(view.mp_gid, kind="stable")] = np.arange(M)
+        self.tie = np.arange(M) if tie is None else np.asarray(tie, np.int64)
 
     # ---- shared per-round statistics -------------------------------------------------------------------
     def _stats(self):
@@ -153,7 +160,7 @@ class Emulator:
         # state and gain are current
         nin_c, cov = self.row_view
         d = np.maximum(0, self.need - cov)
-        key = make_key(self.gain, np.arange(M))
+        key = make_key(self.gain, self.tie)
         flags = np.zeros(M, np.int8)
         fe = (st[self.e_var] == FREE) & (nin_c[self.e_cell] == 0)
         best = np.zeros(self.K * N_CELLS, np.uint64)
@@ -189,7 +196,7 @@ class Emulator:
         if ncand == 0:
             self.log.append(("drop", 0, 0))
             return 0
-        key = make_key(-dF, np.arange(M))
+        key = make_key(-dF, self.tie)
         blocked = np.zeros(M, bool)
         ce = cand[self.e_var] & (nin_c[self.e_cell] >= 2)
         best = np.zeros(self.K * N_CELLS, np.uint64)

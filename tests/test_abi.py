@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(build_native):
     lib = build_native
     for name in declared_symbols():
         assert hasattr(lib, name), f"libmss.so does not export {name}"
-    assert lib.mss_version() == 200
+    assert lib.mss_version() == 210
 
 
 def test_struct_sizes_match_header(build_native):

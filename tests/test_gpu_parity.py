@@ -189,6 +189,45 @@ def test_packed_layout_same_result(eng, name, seed):
     check_against_cpu(view, N, pk)
 
 
+@pytest.mark.parametrize("name,seed", [("c1", 2), ("live", 5), ("c3", 0), ("c4", 1002)])
+def test_tie_break_on_gid_is_numbering_independent(eng, name, seed):
+    """mss_window_view::mp_tie (SURVEY 8b: ties by (cost, MP gid)): with the tie-break ranks of the map points' gids the
+    selection is THE SAME SET of map points for every numbering of the table -- as generated, in discovery order, randomly
+    permuted; SoA and packed16, host and device resident -- and equal to the CPU emulation with the same keys.  Without
+    them the numbering decides ties (test_discovery_order_view)."""
+    from ms_slam_b200.engine import DeviceView
+    from ms_slam_b200.window import pack_view
+    view, N = msgen.make_config(name, seed)
+    view.meta["tie_by_gid"] = True
+    eng.set_params(N, LAM, GLAM)
+    base = eng.solve(view)
+    ref = em.solve(view, N, LAM, GLAM)
+    assert np.array_equal(base.keep, ref["keep"]) and base.objective == ref["objective"] and base.rounds == ref["rounds"]
+    kept_gids = set(view.mp_gid[base.keep].tolist())
+    rng = np.random.default_rng(seed)
+    # a random renumbering of the table (gids travel with the points)
+    perm = rng.permutation(view.M)                       # new -> old
+    inv = np.empty(view.M, np.int64); inv[perm] = np.arange(view.M)
+    cnt = np.diff(view.mp_obs_ptr)[perm]
+    optr = np.zeros(view.M + 1, np.int32); optr[1:] = np.cumsum(cnt)
+    src = np.repeat(view.mp_obs_ptr[:-1][perm] - optr[:-1], cnt) + np.arange(int(optr[-1]))
+    shuffled = WindowView(K=view.K, H=view.H, feat_ptr=view.feat_ptr, feat_mp=np.where(view.feat_mp >= 0, inv[np.maximum(view.feat_mp, 0)], -1),
+                          feat_cell=view.feat_cell, mp_nobs=view.mp_nobs[perm], mp_obs_ptr=optr, mp_obs_kf=view.mp_obs_kf[src],
+                          okf_total=view.okf_total, kf_gid=view.kf_gid, mp_gid=view.mp_gid[perm], meta=dict(tie_by_gid=True))
+    for v in (view.compact().discovery_order(), shuffled, shuffled.compact().discovery_order()):
+        assert v.meta.get("tie_by_gid")
+        forms = [v, pack_view(v, tokens16=True, tie=True)]
+        for f in forms:
+            r = eng.solve(f)
+            assert set(v.mp_gid[r.keep].tolist()) == kept_gids and r.objective == base.objective and r.rounds == base.rounds
+        dv = DeviceView(eng, forms[1])
+        r = eng.solve(dv)
+        assert set(v.mp_gid[r.keep].tolist()) == kept_gids
+        dv.free()
+        e = em.solve(v, N, LAM, GLAM)
+        assert np.array_equal(r.keep, e["keep"])
+
+
 @pytest.mark.parametrize("name,seed", [("c1", 2), ("live", 5), ("c3", 0)])
 def test_discovery_order_view(eng, name, seed):
     """FlattenWindow's numbering (map points in discovery order): parity with the emulation on the renumbered view, and the
