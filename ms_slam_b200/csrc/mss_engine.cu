@@ -432,6 +432,7 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
     P.watchdog_ns = h->watchdog_ns;
     P.tail_vars = std::min(h->tail_vars, mss::kTailVars); P.tail_ents = std::min(h->tail_ents, mss::kTailEnts);
     P.ready = gated ? d_ready : nullptr;
+    P.w1_tma = h->w1_tma;
 
     // Once the persistent kernel is launched it may be spinning on ready flags that a failed copy will never set: any
     // error after the launch raises the device-side abort flag from the host and drains both streams before returning
@@ -711,6 +712,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     *h->h_one = 1u;
     if (const char* oc = getenv("MSS_OVERLAP_COPY")) h->overlap_copy = atoi(oc);
     if (const char* db = getenv("MSS_DUAL_BOUND")) h->want_bound = atoi(db) != 0;
+    if (const char* wt = getenv("MSS_W1_TMA")) h->w1_tma = atoi(wt) != 0;
     h->stats.sm_count = h->sm_count;
     *out = h;
     return MSS_OK;

@@ -57,6 +57,7 @@ struct mss_handle {
     mssi::DevBuf<int> rows;                // 7 per-row int arrays: row_off | ent_n | live_n | row_need | row_cov | row_ncell | ocursor
     // dual bound (mss_set_dual_bound): copy of the live lists at the snapshot, per-row and per-point scratch
     bool want_bound = false;
+    int w1_tma = 1;                        // token rows of PACKED16 views staged by bulk copies in W1 (MSS_W1_TMA)
     mssi::DevBuf<uint32_t> b_snap;
     mssi::DevBuf<int> b_rows;              // snap_n | snap_d
     mssi::DevBuf<unsigned> b_vars;         // share | red

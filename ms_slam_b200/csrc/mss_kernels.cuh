@@ -164,6 +164,8 @@ struct Params {
     int* b_snap_d;               // [Rtot]
     unsigned* b_share;           // [Mpad]
     unsigned* b_red;             // [Mpad]
+    int w1_tma;                  // PACKED16: stage the token rows with bulk copies (1 = default, MSS_W1_TMA=0 reads them through L1)
+    int pad3_;
     const unsigned* ready;       // optional [nwin] (queue order): set to 1 by a stream-ordered host->device copy once the views
                                  // of that window have landed in the staging buffer; nullptr = everything is resident
 };
@@ -206,6 +208,27 @@ __device__ __forceinline__ unsigned f32_orderable(float g) {
 // larger key = better: higher gain first, then lower (window-local) map-point index
 __device__ __forceinline__ unsigned long long make_key(float g, unsigned local_idx) {
     return ((unsigned long long)f32_orderable(g) << 32) | (unsigned long long)(0xFFFFFFFFu - local_idx);
+}
+
+// ---- bulk copies by the TMA unit + mbarrier (sm_90+; sm_100a here).  One elected thread arms the barrier with the byte count
+//      and issues the copy; every consumer thread waits on the barrier's phase parity.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // tie-break key of map point v of window D: the caller's rank, or the table index
@@ -441,7 +464,9 @@ __device__ __forceinline__ void load_row(RowRegs<EPT>& X, const uint32_t* __rest
 // coalesced or shared memory.  A map point becomes a variable exactly when its counters are non-zero after W1, so W2 can
 // derive the state array with coalesced stores; valid slots outside the grid only leave a "seen" mark for nMax.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, int par, unsigned* tab, BlockScratch& S) {
+// stok: this row's tokens staged in shared memory by a bulk copy (token 0 of the row), or nullptr: read them from global memory
+__device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, int k, int par, unsigned* tab, BlockScratch& S,
+                             const uint16_t* stok = nullptr) {
     const int R = D.row_base + k;
     const int beg = ldv(D.feat_ptr + k), end = ldv(D.feat_ptr + k + 1);
     if (beg < 0 || end < beg || end > D.F) {
@@ -477,7 +502,7 @@ __device__ void w1_build_row(const Params& P, const WinDesc& D, WinState& ws, in
                 int adv = 0;
                 bool slot = false;
                 unsigned c = kCellNone;
-                if (b < nb && idx < nslots) adv = tok_decode(ldv(tk + idx), slot, c);
+                if (b < nb && idx < nslots) adv = tok_decode(stok ? (unsigned)stok[idx] : (unsigned)ldv(tk + idx), slot, c);
                 int x = adv;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -2312,21 +2337,68 @@ __device__ bool solve_window(const Params& P, GroupCtx& G, int w, unsigned* tab,
     if (!group_sync(P, G)) return false;
     trace_mark(P, G, w, tn, 10, 0, t_win);
     // ---- W1: keyframe rows ---------------------------------------------------------------------------------------
-    for (int k = G.cta; k < D.K; k += G.ncta) {
-        if (k + G.ncta < D.K) {                  // next row of this CTA: pull its slots towards L1 while this one is processed
-            const int nb = ldv(D.feat_ptr + k + G.ncta), ne = ldv(D.feat_ptr + k + G.ncta + 1);
-            if (nb >= 0 && ne <= D.F) {
-                if (D.packed == 2) {
-                    const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp);
-                    for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(tk + i);
-                } else {
-                    for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
-                }
-                if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
-            }
+    // PACKED16: the tokens of this CTA's NEXT row are staged in shared memory by the TMA unit (cp.async.bulk, completion on an
+    // mbarrier) while the current row is processed -- they are there when the row starts, whatever the L1 held on to.  The two
+    // 4 KB buffers and the barriers live in the upper third of the key-table area, which the build phases do not use (the
+    // second cell table of the row parity scheme occupies its lower half).  A bulk copy needs 16-byte aligned addresses and
+    // sizes, a row starts at any token: the copy covers the aligned superset of the row, rows that touch the last partial
+    // 16 bytes of the token array (or are longer than 2048 tokens) are read from global memory as before.
+    {
+        unsigned char* free_area = reinterpret_cast<unsigned char*>(keytab) + (size_t)kCells * 4;      // 12 KB not used by W1
+        uint16_t* tbuf[2] = {reinterpret_cast<uint16_t*>(free_area), reinterpret_cast<uint16_t*>(free_area + 4608)};
+        unsigned long long* tbar = reinterpret_cast<unsigned long long*>(free_area + 2 * 4608);
+        const uintptr_t tk_base = reinterpret_cast<uintptr_t>(D.feat_mp);
+        const bool w1_tma = D.packed == 2 && (tk_base & 15u) == 0 && P.w1_tma;
+        if (w1_tma && threadIdx.x == 0) {
+            mbar_init(&tbar[0], 1);
+            mbar_init(&tbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        const int par = (k / G.ncta) & 1;              // cell table and scratch alternate: no barrier between rows
-        w1_build_row(P, D, ws, k, par, par ? reinterpret_cast<unsigned*>(keytab) : tab, S);
+        __syncthreads();
+        const uintptr_t lim = tk_base + (((size_t)D.F * 2) & ~(size_t)15);
+        // arms buffer `b` with the tokens of row k; returns the offset (in tokens) of the row's first token inside it, -1 = no
+        auto stage_row = [&](int k, int b) -> int {
+            if (!w1_tma || k >= D.K) return -1;
+            const int beg = ldv(D.feat_ptr + k), end = ldv(D.feat_ptr + k + 1);
+            if (beg < 0 || end <= beg || end > D.F || end - beg > kRegRow) return -1;
+            const uintptr_t a = tk_base + (size_t)beg * 2, a0 = a & ~(uintptr_t)15, a1 = (tk_base + (size_t)end * 2 + 15) & ~(uintptr_t)15;
+            if (a1 > lim) return -1;
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&tbar[b], (uint32_t)(a1 - a0));
+                bulk_g2s(tbuf[b], reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0), &tbar[b]);
+            }
+            return (int)((a - a0) >> 1);
+        };
+        unsigned uses[2] = {0u, 0u};
+        int it = 0;
+        int skip_cur = stage_row(G.cta, 0);
+        for (int k = G.cta; k < D.K; k += G.ncta, ++it) {
+            // (buffer (it + 1) & 1 was read by the row before this one; every thread has passed that row's barriers)
+            const int skip_next = stage_row(k + G.ncta, (it + 1) & 1);
+            if (!w1_tma && k + G.ncta < D.K) {           // other layouts: pull the next row's slots towards L1 while this one is processed
+                const int nb = ldv(D.feat_ptr + k + G.ncta), ne = ldv(D.feat_ptr + k + G.ncta + 1);
+                if (nb >= 0 && ne <= D.F) {
+                    if (D.packed == 2) {
+                        const uint16_t* tk = reinterpret_cast<const uint16_t*>(D.feat_mp);
+                        for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(tk + i);
+                    } else {
+                        for (int i = nb + (int)threadIdx.x * 32; i < ne; i += kThreads * 32) prefetch_l1(D.feat_mp + i);
+                    }
+                    if (!D.packed) for (int i = nb + (int)threadIdx.x * 64; i < ne; i += kThreads * 64) prefetch_l1(D.feat_cell + i);
+                }
+            }
+            const uint16_t* stok = nullptr;
+            if (skip_cur >= 0) {
+                mbar_wait(&tbar[it & 1], uses[it & 1] & 1u);
+                ++uses[it & 1];
+                stok = tbuf[it & 1] + skip_cur;
+            }
+            const int par = (k / G.ncta) & 1;              // cell table and scratch alternate: no barrier between rows
+            w1_build_row(P, D, ws, k, par, par ? reinterpret_cast<unsigned*>(keytab) : tab, S, stok);
+            skip_cur = skip_next;
+        }
+        __syncthreads();                                   // every staged row has been waited for and read
+        if (w1_tma && threadIdx.x == 0) { mbar_inval(&tbar[0]); mbar_inval(&tbar[1]); }
     }
     if (!group_sync(P, G)) return false;
     trace_mark(P, G, w, tn, 11, 0, t_win);
