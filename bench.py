@@ -576,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mirror", action="store_true", help="skip the persistent-device-mirror arm")
+    ap.add_argument("--e2e-handles", type=int, default=2, help="handles (host threads) taking alternate steps in the e2e arm")
     ap.add_argument("--no-extras", action="store_true", help="skip latency / host-API / c3 / c5 sub-entries (N=1, rank 0)")
     ap.add_argument("--order", default="discovery", choices=["generated", "discovery"],
                     help="map-point numbering of the synthetic windows: FlattenWindow's discovery order "
@@ -661,19 +662,22 @@ def main():
         #      staging copies of one batch travel while the other batch is being solved (one FIFO staging stream per device),
         #      so PCIe stays busy; every step still copies its inputs up and its results down inside the timed region ----------
         import threading
-        eng_b = E.Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
-        if world > 1:
-            eng_b.comm_init(msd.broadcast_unique_id(eng_b, rank), rank, world)
-        hr_b = (E.mss_result * nwin)()
-        keep_b = {}
-        for w in range(nwin):
-            if w in batch.views:
-                keep_b[w] = batch.pin_zeros(batch.words, np.uint32)
-                hr_b[w].keep_bits = keep_b[w].ctypes.data
-                hr_b[w].kf_cov = batch.pin_zeros(batch.rows, np.int32).ctypes.data
-                hr_b[w].kf_slack = batch.pin_zeros(batch.rows, np.int32).ctypes.data
-        lanes = [(eng, batch.hr), (eng_b, hr_b)]
-        rcs = [0, 0]
+        nh = max(2, args.e2e_handles)
+        extra, lanes, keep_x = [], [(eng, batch.hr)], []
+        for _ in range(nh - 1):
+            eng_b = E.Engine(N=N, lam=msgen.LAMBDA, grid_lam=msgen.GRID_LAMBDA, device=local_rank)
+            if world > 1:
+                eng_b.comm_init(msd.broadcast_unique_id(eng_b, rank), rank, world)
+            hr_b = (E.mss_result * nwin)()
+            keep_b = {}
+            for w in range(nwin):
+                if w in batch.views:
+                    keep_b[w] = batch.pin_zeros(batch.words, np.uint32)
+                    hr_b[w].keep_bits = keep_b[w].ctypes.data
+                    hr_b[w].kf_cov = batch.pin_zeros(batch.rows, np.int32).ctypes.data
+                    hr_b[w].kf_slack = batch.pin_zeros(batch.rows, np.int32).ctypes.data
+            extra.append(eng_b); lanes.append((eng_b, hr_b)); keep_x.append(keep_b)
+        rcs = [0] * nh
 
         def worker(t, steps):
             e, res = lanes[t]
@@ -682,13 +686,13 @@ def main():
                 if rc != 0:
                     rcs[t] = rc
                     return
-        for e, res in lanes:                                             # warm-up of both handles (arenas, staging buffers)
+        for e, res in lanes:                                             # warm-up of every handle (arenas, staging buffers)
             for _ in range(args.warmup):
                 assert e.solve_batch_raw(batch.hv, res, nwin) == 0, e.lib.mss_last_error(e.handle)
-        steps_each = (args.steps + 1) // 2
+        steps_each = (args.steps + nh - 1) // nh
         barrier()
         t0 = time.perf_counter()
-        th = [threading.Thread(target=worker, args=(t, steps_each)) for t in range(2)]
+        th = [threading.Thread(target=worker, args=(t, steps_each)) for t in range(nh)]
         for x in th:
             x.start()
         for x in th:
@@ -696,24 +700,27 @@ def main():
         torch.cuda.synchronize()
         ms_pipe = (time.perf_counter() - t0) * 1e3
         barrier()
-        assert rcs == [0, 0], (eng.lib.mss_last_error(eng.handle), eng_b.lib.mss_last_error(eng_b.handle))
+        assert rcs == [0] * nh, [e.lib.mss_last_error(e.handle) for e, _ in lanes]
         if world > 1:
             t = torch.tensor([ms_pipe], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_pipe = float(t.item())
+        keep_b = keep_x[0]
+        eng_b = extra[0]
         for w in mine:
             assert np.array_equal(keep_b[w], batch.keep_host_arm[w]), f"window {w}: the two handles disagree"
         st_b = eng_b.stats()
-        e2e = {"value": nwin * 2 * steps_each / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / (2 * steps_each),
-               "steps": 2 * steps_each,
+        e2e = {"value": nwin * nh * steps_each / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / (nh * steps_each),
+               "steps": nh * steps_each, "handles": nh,
                "h2d_bytes_per_step": int(st_host["last_h2d_bytes"]), "d2h_bytes_per_step": int(st_host["last_d2h_bytes"]),
                "timing": "host wall clock around all steps, device synchronised on both sides, max over ranks",
                "single_call": single,
                "what": "mss_solve_batch with one pinned host blob per window in, pinned host keep bits + row coverage of the "
-                       "owned windows out, every step; two handles on two host threads take alternate steps, so the copies of "
+                       f"owned windows out, every step; {nh} handles on {nh} host threads take the steps in turn, so the copies of "
                        "one step overlap the solve of the other (h2d / d2h bytes: per step, from the handle's own counters "
                        f"{int(st_b['last_h2d_bytes'])} / {int(st_b['last_d2h_bytes'])})"}
-        eng_b.close()
+        for e in extra:
+            e.close()
 
     # ---- the same windows from the persistent device mirror: K keyframe handles up, deleted-handle bitmask down -------------
     e2e_mirror = None

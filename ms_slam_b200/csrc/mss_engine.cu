@@ -474,9 +474,15 @@ int mssi::solve_batch_impl(mss_handle* h, int nwin, const mss_window_view* views
             // batch is enqueued under the device's staging mutex: batches of different handles travel one after the other
             std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(h->copy_mutex));
             copy_err = cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0);
+            // (the ready flags of kFlagBatch consecutive windows of the queue are raised by ONE small copy behind the last of
+            // them: every tiny copy between two blobs costs the DMA stream ~2 us)
+            constexpr int kFlagBatch = 4;
             for (int q = 0; q < nl && copy_err == cudaSuccess; ++q) {
                 copy_window(plan.order[q]);
-                if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(d_ready + q, h->h_one, 4, cudaMemcpyHostToDevice, h->copy_stream);
+                if (copy_err == cudaSuccess && ((q + 1) % kFlagBatch == 0 || q + 1 == nl)) {
+                    const int q0 = q - (q % kFlagBatch);
+                    copy_err = cudaMemcpyAsync(d_ready + q0, h->h_one, (size_t)(q + 1 - q0) * 4, cudaMemcpyHostToDevice, h->copy_stream);
+                }
             }
             if (copy_err == cudaSuccess) copy_err = cudaEventRecord(h->ev_copied, h->copy_stream);
             MSS_CUDA_LAUNCHED(h, copy_err);
@@ -709,7 +715,7 @@ int mss_create(const mss_config* cfg, mss_handle** out) {
     if ((e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void**)&h->h_one, 64, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
-    *h->h_one = 1u;
+    for (int i = 0; i < 16; ++i) h->h_one[i] = 1u;
     if (const char* oc = getenv("MSS_OVERLAP_COPY")) h->overlap_copy = atoi(oc);
     if (const char* db = getenv("MSS_DUAL_BOUND")) h->want_bound = atoi(db) != 0;
     if (const char* wt = getenv("MSS_W1_TMA")) h->w1_tma = atoi(wt) != 0;
