@@ -508,3 +508,40 @@ def test_flush_of_the_cpp_class_over_two_gpus(build_native):
             w.close()
     assert out[2][1]["devices"] == 2 and out[None][1]["devices"] == 1 and out[2][1]["components"] >= 8
     assert np.array_equal(out[2][0], out[None][0]) and out[2][1]["objective"] == out[None][1]["objective"]
+
+
+def test_two_handles_on_two_threads_pipeline_batches(build_native):
+    """Handles are single-threaded, but two handles on one device may be driven from two threads at the same time: their
+    staging copies queue FIFO on the device's shared staging stream (batch after batch, flags raised four windows at a time)
+    while the other handle's batch is being solved.  Every call must return exactly what a lone handle returns."""
+    import threading
+    from ms_slam_b200.engine import Engine
+    from ms_slam_b200.window import pack_view
+    N = 100
+    batches = [[pack_view(msgen.make_config("live", 40 + 7 * b + i)[0].compact().discovery_order(), tokens16=True) for i in range(7)] +
+               [pack_view(msgen.make_config("c4", 1010 + b, M=6000, K=50)[0].compact(), tokens16=True)] for b in range(4)]
+    lone = Engine(N=N, lam=LAM, grid_lam=GLAM)
+    want = [[(r.keep_bits.copy(), r.objective, r.rounds) for r in lone.solve_batch(b)] for b in batches]
+    lone.close()
+    engines = [Engine(N=N, lam=LAM, grid_lam=GLAM), Engine(N=N, lam=LAM, grid_lam=GLAM)]
+    got, errs = {}, []
+
+    def worker(t):
+        try:
+            for rep in range(6):
+                for b in range(t, len(batches), 2):
+                    got[(t, rep, b)] = [(r.keep_bits.copy(), r.objective, r.rounds) for r in engines[t].solve_batch(batches[b])]
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for e in engines:
+        e.close()
+    assert not errs, errs
+    assert len(got) == 6 * len(batches)
+    for (t, rep, b), res in got.items():
+        for (kb, obj, rounds), (wkb, wobj, wrounds) in zip(res, want[b]):
+            assert np.array_equal(kb, wkb) and obj == wobj and rounds == wrounds
