@@ -31,7 +31,8 @@ struct mss_mirror {
     DevBuf<MpRec> mp;
     DevBuf<uint8_t> win;                      // per-call window buffers (descriptors, handle lists, counts, view arrays)
     DevBuf<uint8_t> upload;                   // staging of ops / bulk loads
-    uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;    // pinned: descriptors up, counters and bitmask words down
+    uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;    // pinned: descriptors up, counters down
+    uint8_t* h_del = nullptr; size_t h_del_cap = 0;    // pinned: the deleted-handle words of a call
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     mss_mirror_stats stats{};
 };
@@ -115,6 +116,7 @@ struct Assembly {
     int Kmax = 0;
     bool tables = false;
     float build_ms = 0.f;
+    size_t del_base = 0, del_bytes = 0;     // the block of all windows' deleted-handle words inside mss_mirror::win
 };
 
 int assemble(mss_mirror* m, int nwin, const mss_mirror_window* win, Assembly& A) {
@@ -199,9 +201,18 @@ int assemble(mss_mirror* m, int nwin, const mss_mirror_window* win, Assembly& A)
         L.nobs16 = off; off += align_up((size_t)std::max(c[C_M], 1) * 2, 256);
         L.mp_handle = off; off += align_up((size_t)std::max(c[C_M], 1) * 4, 256);
         L.pairs = off; off += align_up((size_t)std::max(c[C_O], 1) * 4, 256);
-        const int dwords = c[C_M] > 0 ? ((c[C_HHI] + 31) >> 5) - (c[C_HLO] >> 5) : 0;
-        L.del = off; off += align_up((size_t)std::max(dwords, 1) * 4, 256);
     }
+    // the deleted-handle words of all windows lie in ONE block: they come back with one copy (a copy per window costs the
+    // DMA stream a few microseconds each, whatever its size)
+    A.del_base = off;
+    for (int w = 0; w < nwin; ++w) {
+        const int* c = A.h_cnt + (size_t)w * C_COUNT;
+        if (c[C_ERR]) continue;
+        const int dwords = c[C_M] > 0 ? ((c[C_HHI] + 31) >> 5) - (c[C_HLO] >> 5) : 0;
+        A.lay[w].del = off; off += align_up((size_t)std::max(dwords, 1) * 4, 16);
+    }
+    A.del_bytes = off - A.del_base;
+    off = align_up(off, 256);
     if (off > m->win.cap) {
         // the phase-A buffers hold live data: grow with copy
         if ((rc = ensure(h, m->win, off + 256, true))) return rc;
@@ -298,6 +309,7 @@ void mss_mirror_destroy(mss_mirror* m) {
     release(m->slot_cell); release(m->kf_key); release(m->okf_mark); release(m->win);
     release(m->upload);
     if (m->h_pin) cudaFreeHost(m->h_pin);
+    if (m->h_del) cudaFreeHost(m->h_del);
     if (m->e0) cudaEventDestroy(m->e0);
     if (m->e1) cudaEventDestroy(m->e1);
     delete m;
@@ -530,6 +542,8 @@ int mss_mirror_solve(mss_mirror* m, int32_t nwin, mss_mirror_window* windows, ms
     int64_t d2h = (int64_t)nwin * C_COUNT * 4;
     // (the sizes read below are the ones of the first read-back; this copy adds the number of deleted points)
     std::vector<int> c0(A.h_cnt, A.h_cnt + (size_t)nwin * C_COUNT);
+    bool want_del = false;
+    int rc2 = MSS_OK;
     MSS_CUDA(h, cudaMemcpyAsync(A.h_cnt, m->win.p + A.lay[0].cnt, (size_t)nwin * C_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
     for (int w = 0; w < nwin; ++w) {
         const int* c = c0.data() + (size_t)w * C_COUNT;
@@ -537,11 +551,7 @@ int mss_mirror_solve(mss_mirror* m, int32_t nwin, mss_mirror_window* windows, ms
         q.M = c[C_ERR] ? 0 : c[C_M]; q.H = c[C_ERR] ? 0 : c[C_H]; q.F = c[C_ERR] ? 0 : c[C_F]; q.O = c[C_ERR] ? 0 : c[C_O];
         const bool has = !c[C_ERR] && c[C_M] > 0;
         q.h_lo = has ? c[C_HLO] : 0; q.h_hi = has ? c[C_HHI] : 0;
-        if (q.del_bits && has && solved) {
-            const int lo = q.h_lo >> 5, hi = (q.h_hi + 31) >> 5;
-            MSS_CUDA(h, cudaMemcpyAsync(q.del_bits + lo, m->win.p + A.lay[w].del, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, h->stream));
-            d2h += (int64_t)(hi - lo) * 4;
-        }
+        if (q.del_bits && has && solved) { want_del = true; d2h += (int64_t)(((q.h_hi + 31) >> 5) - (q.h_lo >> 5)) * 4; }
         if (q.mp_handle && has) {
             if (q.mp_cap < c[C_M]) { h->err = "mirror solve: mp_handle buffer smaller than the window's map-point table"; rc = MSS_E_BADARG; }
             else {
@@ -550,7 +560,19 @@ int mss_mirror_solve(mss_mirror* m, int32_t nwin, mss_mirror_window* windows, ms
             }
         }
     }
+    if (want_del && A.del_bytes > 0) {
+        if ((rc2 = ensure_pinned(h, (void**)&m->h_del, &m->h_del_cap, A.del_bytes))) return rc2;
+        MSS_CUDA(h, cudaMemcpyAsync(m->h_del, m->win.p + A.del_base, A.del_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
     MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (want_del && A.del_bytes > 0)
+        for (int w = 0; w < nwin; ++w) {
+            const int* c = c0.data() + (size_t)w * C_COUNT;
+            const mss_mirror_window& q = windows[w];
+            if (!q.del_bits || c[C_ERR] || c[C_M] <= 0 || !solved) continue;
+            const int lo = q.h_lo >> 5, hi = (q.h_hi + 31) >> 5;
+            memcpy(q.del_bits + lo, m->h_del + (A.lay[w].del - A.del_base), (size_t)(hi - lo) * 4);
+        }
     for (int w = 0; w < nwin; ++w) {
         const int* c = A.h_cnt + (size_t)w * C_COUNT;
         windows[w].n_deleted = c[C_ERR] ? 0 : c[C_NDEL];
