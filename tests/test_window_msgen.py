@@ -209,3 +209,31 @@ def test_components_oracle_vs_naive_union_find(K, M, seed):
     assert nc == len(roots)
     assert rl.tolist() == [dense[find(r)] for r in range(K + H)]
     assert ml.tolist() == [dense[find(K + H + p)] if isvar[p] else -1 for p in range(M)]
+
+
+def test_one_byte_nobs_table_is_chosen_only_when_every_value_fits():
+    """mss_window_view::nobs8: pack_view (like FlattenWindow) sends Observations() as bytes with the u16-token layout whenever
+    max <= 255, keeps u16 otherwise, and refuses an explicit nobs8 that would truncate"""
+    import pytest
+    from ms_slam_b200 import make_view
+    from ms_slam_b200.window import pack_view
+    slots = [[(0, 5), (1, 6), (2, 7)], [(1, 8), (2, 9), (3, 10)]]
+    small = make_view(2, slots, [4, 8, 255, 3])
+    big = make_view(2, slots, [4, 8, 256, 3])
+    a, b = pack_view(small, tokens16=True), pack_view(big, tokens16=True)
+    assert a.meta["nobs8"] and a.mp_nobs16.dtype == np.uint8 and a.mp_nobs16.tolist() == [4, 8, 255, 3]
+    assert not b.meta["nobs8"] and b.mp_nobs16.dtype == np.uint16 and b.mp_nobs16.tolist() == [4, 8, 256, 3]
+    assert not pack_view(small).meta["nobs8"]                      # the u32-slot layout keeps u16 unless asked
+    assert pack_view(small, nobs8=True).mp_nobs16.dtype == np.uint8
+    with pytest.raises(ValueError):
+        pack_view(big, nobs8=True)
+    assert a.input_bytes() == b.input_bytes() - 4
+
+
+def test_tie_ranks_follow_the_gids_not_the_numbering():
+    from ms_slam_b200.window import tie_ranks, pack_view
+    v, _ = msgen.make_config("c1", 3)
+    d = v.compact().discovery_order()
+    assert np.array_equal(tie_ranks(v), np.arange(v.M, dtype=np.uint32))           # generated gids are ascending
+    assert np.array_equal(tie_ranks(d), d.meta["mp_perm"].astype(np.uint32))       # rank = the original index, wherever the point went
+    assert np.array_equal(pack_view(d, tokens16=True, tie=True).mp_tie, tie_ranks(d)) and pack_view(d).mp_tie is None
