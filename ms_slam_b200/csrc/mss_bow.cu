@@ -249,15 +249,19 @@ int mss_voc_create(mss_handle* h, int32_t n_nodes, int32_t levels, const int32_t
     mss_vocabulary* v = new (std::nothrow) mss_vocabulary();
     if (!v) return MSS_E_NOMEM;
     v->h = h; v->n = n_nodes; v->L = levels; v->n_words = nw;
-    MSS_CUDA(h, cudaSetDevice(h->device));
-    int rc;
-    if ((rc = ensure(h, v->desc, (size_t)n_nodes * 2)) || (rc = ensure(h, v->ints, (size_t)4 * n_nodes)) || (rc = ensure(h, v->weight, (size_t)n_nodes)) ||
-        (rc = ensure(h, v->word_count, (size_t)std::max(nw, 1) + 8)) || (rc = ensure(h, v->bitmap, (size_t)(nw + 31) / 32 + 1))) { delete v; return rc; }
-    MSS_CUDA(h, cudaMemcpyAsync(v->desc.p, d.data(), d.size(), cudaMemcpyHostToDevice, h->stream));
-    MSS_CUDA(h, cudaMemcpyAsync(v->ints.p, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    MSS_CUDA(h, cudaMemcpyAsync(v->weight.p, wt.data(), wt.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    MSS_CUDA(h, cudaMemsetAsync(v->word_count.p, 0, ((size_t)std::max(nw, 1) + 8) * 4, h->stream));
-    MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    auto upload = [&]() -> int {
+        MSS_CUDA(h, cudaSetDevice(h->device));
+        int rc;
+        if ((rc = ensure(h, v->desc, (size_t)n_nodes * 2)) || (rc = ensure(h, v->ints, (size_t)4 * n_nodes)) || (rc = ensure(h, v->weight, (size_t)n_nodes)) ||
+            (rc = ensure(h, v->word_count, (size_t)std::max(nw, 1) + 8)) || (rc = ensure(h, v->bitmap, (size_t)(nw + 31) / 32 + 1))) return rc;
+        MSS_CUDA(h, cudaMemcpyAsync(v->desc.p, d.data(), d.size(), cudaMemcpyHostToDevice, h->stream));
+        MSS_CUDA(h, cudaMemcpyAsync(v->ints.p, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        MSS_CUDA(h, cudaMemcpyAsync(v->weight.p, wt.data(), wt.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        MSS_CUDA(h, cudaMemsetAsync(v->word_count.p, 0, ((size_t)std::max(nw, 1) + 8) * 4, h->stream));
+        MSS_CUDA(h, cudaStreamSynchronize(h->stream));
+        return MSS_OK;
+    };
+    if (const int rc = upload()) { mss_voc_destroy(v); return rc; }      // (nothing is left behind on a failed upload)
     *out = v;
     return MSS_OK;
 }
