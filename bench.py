@@ -772,7 +772,10 @@ def main():
     for w in mine:
         assert cr[w].status == 0 and cr[w].n_kept > 0 and cr[w].rounds > 0
         if not args.no_e2e:
-            assert np.array_equal(batch.keep_dev_arm[w], batch.keep_host_arm[w]), f"window {w}: device-view and host-view arms differ"
+            if not np.array_equal(batch.keep_dev_arm[w], batch.keep_host_arm[w]):
+                ref = eng.solve(batch.views[w]).keep_bits
+                raise AssertionError(f"window {w}: device-view and host-view arms differ (value arm == fresh solve: "
+                                     f"{np.array_equal(batch.keep_dev_arm[w], ref)}, e2e arm == fresh solve: {np.array_equal(batch.keep_host_arm[w], ref)})")
     r0 = cr[mine[0]]
     quality = {"objective_w0": r0.objective, "kept_w0": r0.n_kept, "vars_w0": r0.n_vars, "rounds_w0": r0.rounds}
 
